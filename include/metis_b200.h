@@ -1,0 +1,215 @@
+/*
+ * metis_b200.h - C ABI of libmetis_b200.so (hand-written sm_100a CUDA).
+ *
+ * The reference (SamsungLabs/Metis @ ed41176) is pure Python and has no FFI
+ * layer; its seam for the plan-search hot path is the pair of Python functions
+ *     cost_het_cluster(args, gpu_cluster, profile_data, model_config,
+ *                      cost_estimator, layer_load_balancer)   cost_het_cluster.py:21-50
+ *     cost_homo_cluster(args, gpu_cluster, cost_estimator)    cost_homo_cluster.py:21-37
+ * Each entry point below replaces the body of one of those loops (or one of the
+ * functions they call); INTEGRATION.md shows the ctypes stub a maintainer would
+ * add to the reference.  Conventions:
+ *   - plain pointers and sizes only; every buffer is caller-allocated and
+ *     caller-freed; pointers marked [device] must be CUDA device memory on the
+ *     current device, [host] ordinary (ideally pinned) host memory;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as
+ *     void*, NULL = default stream) and returns; results are valid after the
+ *     caller synchronises that stream;
+ *   - return value 0 on success, a negative METIS_E_* code otherwise; the
+ *     library never throws and keeps no global state;
+ *   - no CPU fallback exists: without a CUDA device every compute entry point
+ *     returns METIS_E_CUDA.
+ */
+#ifndef METIS_B200_H
+#define METIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define METIS_ABI_VERSION 1
+
+/* return codes */
+#define METIS_OK            0
+#define METIS_E_CUDA       -1   /* CUDA runtime error (see metis_last_error) */
+#define METIS_E_ARG        -2   /* bad argument / unsupported size            */
+#define METIS_E_CAPACITY   -3   /* caller buffer too small                    */
+
+/* per-plan fatal codes (the reference would abort the whole search, quirk Q8) */
+#define METIS_FATAL_NONE        0
+#define METIS_FATAL_KEY_EXEC    1   /* KeyError 'tp{t}_bs{b}' in StagePerformance (model/device_group.py:38,49,79) */
+#define METIS_FATAL_KEY_MEMORY  2   /* KeyError in _get_stage_memory_demand (model/load_balancer.py:43,51)          */
+#define METIS_FATAL_INDEX       3   /* IndexError: fewer profiled layers than --num_layers (load_balancer.py:219)   */
+#define METIS_FATAL_HANG        4   /* reference loop at load_balancer.py:96-104 would not terminate                */
+#define METIS_FATAL_SCRATCH     5   /* internal scratch exceeded (more stages / leftovers than compiled limits)     */
+#define METIS_FATAL_ZERODIV     6   /* ZeroDivisionError in the reference (zero profiled time / zero total)         */
+
+/* limits compiled into the kernels */
+#define METIS_MAX_TYPES   8
+#define METIS_MAX_STAGES  128
+#define METIS_MAX_LAYERS  256
+
+/*
+ * Flattened search problem: the dict-of-dicts `profile_data` (data_loader.py:39-61),
+ * `GPUCluster` (gpu_cluster.py:8-58), `ModelConfig` / `GPTActivationAndParam`
+ * (utils.py:72-79, model/activation_parameter.py:5-51) and the flags read on the
+ * hot path (cost_het_cluster.py:25-36) as dense arrays.
+ *
+ * A profile key 'tp{t}_bs{b}' of device type d is  key_index[(d*num_tp + log2(t))*num_bs + (b-1)]
+ * (-1 = not profiled).  Layer tables are zero-padded to `lpad` entries.
+ */
+typedef struct MetisProblem {
+    int32_t num_types;            /* distinct device types in the cluster                          */
+    int32_t num_tp;               /* tp levels 1,2,4,.. covered by key_index                        */
+    int32_t num_bs;               /* batch sizes 1..num_bs covered by key_index                     */
+    int32_t num_keys;             /* profiled (type,tp,bs) keys                                     */
+    int32_t lpad;                 /* padded length of the per-layer tables                          */
+    int32_t num_layers;           /* --num_layers                                                   */
+    int32_t norm_len;             /* len(norm_layer_duration)  (load_balancer.py:22-27)             */
+    int32_t gbs;                  /* --gbs                                                          */
+    int32_t max_tp;               /* --max_profiled_tp_degree                                       */
+    int32_t max_bs;               /* --max_profiled_batch_size                                      */
+    int32_t num_nodes;            /* gpu_cluster.get_num_nodes()                                    */
+    int32_t devices_per_node;     /* gpu_cluster.get_num_devices_per_node() (node 0, quirk Q10)     */
+    int32_t total_devices;
+    int32_t num_node_sequences;
+    int32_t uniform_bw;           /* 1 when every type has the same first/min bandwidth             */
+    int32_t reserved0;
+    int64_t sequence_length, hidden_size, vocab_size;
+    double optimizer_time;        /* profile_data['model']['optimizer_time'] (= 2 x optimizer_time_ms) */
+    double batch_generator;       /* profile_data['model']['batch_generator']                       */
+    double input_params, transformer_params, output_params;   /* activation_parameter.py:22-24      */
+    double node0_bandwidth;       /* gpu_cluster.get_intra_bandwidth(0) (homo path, cluster_bandwidth.py:75-76) */
+    double node0_memory;          /* gpu_cluster.get_device_memory(0)   (cost_estimator.py:31-32)    */
+    const int16_t *key_index;     /* [device] [num_types][num_tp][num_bs]                           */
+    const double *layer_compute;  /* [device] [num_keys][lpad]  'layer-computes'                    */
+    const double *layer_memory;   /* [device] [num_keys][lpad]  'memory'                            */
+    const double *exec_full;      /* [device] [num_keys]  sum(layer-computes)   (Python sum, host)  */
+    const double *fb_sync;        /* [device] [num_keys]  0.0 = falsy -> KeyError (quirk Q9)        */
+    const double *norm_lc;        /* [device] [norm_len]                                            */
+    const double *type_memory;    /* [device] [num_types] get_device_memory_for_device_type()       */
+    const double *type_bw_first;  /* [device] [num_types] _get_intra_bandwidth(type)                */
+    const double *type_bw_min;    /* [device] [num_types] _get_inter_bandwidth([type]) (quirk Q2)   */
+    const uint8_t *ns_run_type;   /* [device] [num_node_sequences][num_types] type id of k-th run   */
+    const int32_t *ns_run_end;    /* [device] [num_node_sequences][num_types] cumulative rank count */
+} MetisProblem;
+
+/* One block of inter-stage plans sharing (ns_idx, num_stage): plan.py:153-175 incl. quirk Q1. */
+typedef struct MetisPlanBlock {
+    int64_t first_ordinal;        /* ordinal of (row 0, batches = gbs)                              */
+    int64_t rows_offset;          /* byte offset of row 0 in MetisPlanSpace.rows                    */
+    int32_t num_rows;             /* device-group rows in the block                                 */
+    int16_t ns_idx;
+    int16_t label_stage;          /* InterStagePlan.num_stage as emitted (1 for Q1 blocks)          */
+    int16_t num_stage;            /* len(device_groups)                                             */
+    int16_t reserved[3];
+} MetisPlanBlock;
+
+/*
+ * The enumerated candidate space.  ordinal = first_ordinal + row*num_div + div_idx
+ * reproduces the order of InterStagePlanGenerator.__next__ (plan.py:153-175).
+ * Rows hold log2(group size), one byte per stage (device_group.py:93-107 order).
+ */
+typedef struct MetisPlanSpace {
+    int64_t num_plans;
+    int32_t num_blocks;
+    int32_t num_div;
+    const MetisPlanBlock *blocks; /* [device] [num_blocks]                                          */
+    const int32_t *batches;       /* [device] [num_div] divisors of gbs, descending (plan.py:120-124) */
+    const uint8_t *rows;          /* [device]                                                       */
+} MetisPlanSpace;
+
+/* 16-byte record per costed candidate (one per estimate_costs.append, cost_het_cluster.py:44-46). */
+typedef struct MetisRecord {
+    double cost;
+    uint32_t ordinal;             /* inter-stage plan ordinal                                       */
+    uint16_t step;                /* index of the yield inside the plan's intra-stage chain         */
+    uint8_t num_repartition;      /* IntraStagePlan.num_repartition (1..3)                          */
+    uint8_t num_stage;
+} MetisRecord;
+
+/* Summary written to host memory by metis_het_search (valid after stream sync). */
+typedef struct MetisSearchSummary {
+    uint64_t num_records;         /* C: candidates costed (may exceed record capacity: then truncated) */
+    uint64_t num_partition_calls; /* B: LayerLoadBalancer.partition_layer invocations               */
+    uint64_t num_balancer_runs;   /* LayerComputeBalancer.run invocations                           */
+    uint64_t num_keyerror;        /* candidates skipped by `except KeyError` (cost_het_cluster.py:47) */
+    uint64_t fatal_ordinal;       /* lowest ordinal that hit a fatal condition, UINT64_MAX if none  */
+    uint32_t fatal_code;          /* METIS_FATAL_* of that ordinal                                  */
+    uint32_t fatal_aux;           /* tp<<16 | bs of the missing key when applicable                 */
+    MetisRecord best;             /* argmin (cost, ordinal, step); cost = +inf when no record       */
+    uint64_t reserved[2];
+} MetisSearchSummary;
+
+/* Shard of the ordinal space evaluated by one call (multi-GPU: rank r of n, interleaved tiles). */
+typedef struct MetisShard {
+    int32_t rank;                 /* 0 <= rank < world                                              */
+    int32_t world;
+    int32_t tile;                 /* plans per interleave tile (multiple of 32)                     */
+    int32_t reserved;
+} MetisShard;
+
+const char *metis_last_error(void);
+int metis_abi_version(void);
+
+/* Bytes of device scratch the calls below need for `num_plans` plans (workspace argument);
+ * metis_het_detail / metis_homo_cost need metis_het_workspace_bytes(problem, 0). */
+int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans);
+
+/*
+ * Replaces the loop of cost_het_cluster.py:24-48 for the shard's plans.
+ *   records      [device] capacity MetisRecord slots (unordered; sort by (ordinal, step) to get
+ *                estimate_costs order); may be NULL with capacity 0 when only the best is wanted
+ *   detail       [device] optional, capacity * detail_stride bytes: per record
+ *                dp code[num_stage], tp code[num_stage] (log2) then layer_partition[num_stage+1]
+ *                (uint8 each); detail_stride >= 3*METIS_MAX_STAGES+1, or NULL
+ *   workspace    [device] metis_het_workspace_bytes(plans in shard) bytes
+ *   summary      [host]   filled asynchronously (use pinned memory)
+ */
+int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, const MetisShard *shard,
+                     MetisRecord *records, int64_t capacity, uint8_t *detail, int32_t detail_stride,
+                     void *workspace, int64_t workspace_bytes, MetisSearchSummary *summary, void *stream);
+
+/*
+ * Re-evaluates the listed (ordinal, step) candidates and writes their strategies and
+ * partition (same layout as `detail` above).  Used to materialise the winner / a ranked slice.
+ *   picks [device] n MetisRecord (only ordinal and step are read)
+ */
+int metis_het_detail(const MetisProblem *problem, const MetisPlanSpace *space, const MetisRecord *picks,
+                     int64_t n, uint8_t *detail, int32_t detail_stride, void *workspace,
+                     int64_t workspace_bytes, void *stream);
+
+/*
+ * Replaces HomoCostEstimator.get_cost (model/cost_estimator.py:98-138) for n UniformPlans
+ * (search_space/plan.py:12-18), as called from cost_homo_cluster.py:29.
+ *   plans  [device] n x 5 int32 (dp, pp, tp, mbs, gbs)
+ *   cost   [device] n doubles;  status [device] n int32: 0 ok, 1 KeyError (plan skipped), 2 oom flag set
+ */
+int metis_homo_cost(const MetisProblem *problem, int32_t type_id, const int32_t *plans, int64_t n,
+                    double *cost, int32_t *status, void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
+ * LayerComputeBalancer.run (model/load_balancer.py:197-207) for n independent instances.
+ *   capa [device] n x stride doubles (stage capacities), num_stage [device] n int32,
+ *   lc [device] norm_len doubles, partition [device] n x (stride+1) uint16 out (0xFFFF first = error),
+ *   workspace [device] >= norm_len*8 + 256 bytes
+ */
+int metis_layer_balance(const double *capa, const int32_t *num_stage, int64_t n, int32_t stride,
+                        const double *lc, int32_t norm_len, int32_t num_layers, uint16_t *partition,
+                        void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
+ * Host-side enumeration of gen_dgroups_for_stages_with_variance (search_space/device_group.py:93-107)
+ * in reference order.  Writes log2 codes, num_stages bytes per row, into out (host memory) and
+ * returns the number of rows, or METIS_E_CAPACITY if capacity_rows is too small (call with
+ * out == NULL to count).
+ */
+int64_t metis_enum_device_groups(int32_t num_stages, int32_t num_gpus, double variance,
+                                 int32_t max_permute_len, uint8_t *out, int64_t capacity_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METIS_B200_H */

@@ -1,0 +1,856 @@
+// metis_eval.cuh - per-plan evaluator of the Metis plan-search hot path.
+//
+// One *thread* evaluates one inter-stage plan:
+// the intra-stage strategy chain, the layer load balancer with its memory
+// feasibility loop and the hetero cost model, all in IEEE binary64 in the
+// reference's evaluation order (compile with -fmad=false: no FMA contraction).
+//
+// The code is plain C++ (no CUDA intrinsics) so that tests/hostsim can compile
+// the very same source with g++ for CPU-side debugging of the device logic.
+// That shim lives in tests/ and is never loaded by the metis_b200 package.
+//
+// Reference citations (paths relative to the reference root) are given at each
+// function.  State is kept compact instead of the reference's per-sub-layer
+// lists; see DESIGN.md "Load balancer on device" for why each step is equivalent.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/metis_b200.h"
+
+#if defined(__CUDACC__)
+#define MB_HD __host__ __device__ __forceinline__
+#define MB_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define MB_HD inline
+#define MB_HD_NOINLINE
+#endif
+
+namespace metis {
+
+constexpr int kH = 7;                 // hallucination (model/load_balancer.py:183)
+constexpr double kMemCoef = 5.0;      // mem_coef (model/load_balancer.py:31)
+constexpr uint8_t kDropped = 0xFF;    // real layer kept by no stage (quirk Q5)
+
+// Tables as seen by the evaluator (pointers into shared or global memory).
+struct Tables {
+    MetisProblem p;
+    const int16_t *key_index;
+    const double *lc;          // [num_keys][lpad]
+    const double *mem;         // [num_keys][lpad]
+    const double *exec_full;   // [num_keys]
+    const double *fb_sync;     // [num_keys]
+    const double *norm_lc;     // [norm_len]
+    const double *dlay;        // [num_layers] norm_lc[r] / 7   (load_balancer.py:190-193)
+    const double *type_memory, *bw_first, *bw_min;
+    const uint8_t *run_type;   // [ns][num_types]
+    const int32_t *run_end;    // [ns][num_types]
+};
+
+// One inter-stage plan (search_space/plan.py:21-29).
+struct PlanDesc {
+    uint32_t ordinal;
+    int ns;            // ns_idx
+    int S;             // len(device_groups)
+    int label;         // InterStagePlan.num_stage as emitted (quirk Q1)
+    int batches;
+    const uint8_t *row;  // log2(group size) per stage
+};
+
+template <int MAXS, int MAXL>
+struct Scratch {
+    static constexpr int kLeft = 2 * MAXS + 64;
+    double perf[MAXS];     // stage compute performance of the current attempt (sc_capa_bak)
+    double capa[MAXS];     // working capacities / scratch
+    double mstate[MAXS];   // memory_state of the last partition_layer call / scratch in adjust
+    double extra[MAXS];    // additional_alloc_sc_capa / memory demand
+    uint16_t fs[MAXS], fe[MAXS];   // forward interval [fs,fe) in sub-layers; later first/last real layer
+    uint16_t cnt[MAXS];    // real layers per stage
+    uint16_t part[MAXS + 1];
+    uint16_t lid[kLeft];   // leftover sub-layer ids, ascending
+    uint8_t lst[kLeft];    // stage each leftover was placed on
+    uint8_t gcode[MAXS];   // log2(device group size)
+    uint8_t tpc[MAXS];     // log2(tp)
+    uint8_t flag[MAXS];    // bit0 stage broke in forward pass, bit1 skip taken by backward pass, bit2 got a leftover
+    uint8_t owner[MAXL];   // stage owning each real layer after the majority vote
+};
+
+// ---------------------------------------------------------------------------
+// CPython >= 3.12 builtin sum() over a float slice x[a:b] (Neumaier; see oracle fsum)
+// ---------------------------------------------------------------------------
+MB_HD double py_sum_range(const double *x, int a, int b) {
+    if (a >= b) return 0.0;
+    double f = 0.0 + x[a];
+    double c = 0.0;
+    for (int i = a + 1; i < b; ++i) {
+        const double v = x[i];
+        const double t = f + v;
+        if (fabs(f) >= fabs(v)) c += (f - t) + v;
+        else c += (v - t) + f;
+        f = t;
+    }
+    if (c != 0.0 && isfinite(c)) f += c;
+    return f;
+}
+
+// Running form of the same sum for values produced on the fly.
+struct PySum {
+    double f, c;
+    int n;
+    MB_HD PySum() : f(0.0), c(0.0), n(0) {}
+    MB_HD void add(double v) {
+        if (n == 0) { f = 0.0 + v; }
+        else {
+            const double t = f + v;
+            if (fabs(f) >= fabs(v)) c += (f - t) + v;
+            else c += (v - t) + f;
+            f = t;
+        }
+        ++n;
+    }
+    MB_HD double result() const {
+        double r = f;
+        if (c != 0.0 && isfinite(c)) r += c;
+        return r;
+    }
+};
+
+MB_HD int type_of_rank(const Tables &T, int ns, int rank) {
+    const int nt = T.p.num_types;
+    const int32_t *end = T.run_end + ns * nt;
+    const uint8_t *typ = T.run_type + ns * nt;
+    for (int k = 0; k < nt; ++k)
+        if (rank < end[k]) return typ[k];
+    return typ[nt - 1];
+}
+
+MB_HD int key_of(const Tables &T, int type, int tpc, int bs) {
+    if (tpc >= T.p.num_tp || bs < 1 || bs > T.p.num_bs) return -1;
+    return T.key_index[(type * T.p.num_tp + tpc) * T.p.num_bs + (bs - 1)];
+}
+
+// ---------------------------------------------------------------------------
+// LayerComputeBalancer.run  (model/load_balancer.py:197-207, passes :216-364)
+// in : w.perf[0..S) = sc_capa (kept as sc_capa_bak), out: w.part[0..S], w.cnt
+// returns METIS_FATAL_* (0 = ok)
+// ---------------------------------------------------------------------------
+template <int MAXS, int MAXL>
+MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
+    const int L = T.p.num_layers;
+    if (T.p.norm_len < L) return METIS_FATAL_INDEX;       // expand_lc_demand[layer_id] IndexError (:219/:238)
+    const double *dlay = T.dlay;
+    const double *lc = T.norm_lc;
+    const int N = kH * L;
+    const int lim = N - 1 - kH;                            // :218
+    const int last = S - 1;
+
+    for (int s = 0; s < S; ++s) { w.capa[s] = w.perf[s]; w.flag[s] = 0; }
+
+    // ---- forward pass (:216-231) as one flat scan over sub-layers --------------------------
+    int k = 0;
+    if (S > 1) {
+        int s = 0;
+        double c = w.capa[0];
+        w.fs[0] = 0;
+        int r = 0, sub = 0;
+        double d = dlay[0];
+        int j = 0;
+        bool done = false;
+        for (; j < lim; ++j) {
+            if (c > d) {
+                c -= d;
+            } else {                                        // sub-layer j does not fit: skipped, stage closes
+                w.capa[s] = c; w.fe[s] = (uint16_t)j; w.flag[s] = 1;
+                ++s;
+                if (s == last) { k = j + 1; done = true; break; }
+                c = w.capa[s];
+                w.fs[s] = (uint16_t)(j + 1);
+            }
+            if (++sub == kH) { sub = 0; ++r; d = dlay[r]; }
+        }
+        if (!done) {                                        // ran into the reserved tail: later stages stay empty
+            w.capa[s] = c; w.fe[s] = (uint16_t)lim;
+            for (int t = s + 1; t < last; ++t) { w.fs[t] = (uint16_t)lim; w.fe[t] = (uint16_t)lim; }
+            k = lim;
+        }
+    }
+
+    // ---- backward pass (:233-249): last stage takes a contiguous tail [m, N) -----------------
+    int m;
+    {
+        double c = w.capa[last];
+        const double dl = dlay[L - 1];
+        for (int i = 0; i < kH; ++i) c -= dl;               // unconditional while len < hallucination (:237-241)
+        m = N - kH;
+        int sp = S - 2;
+        while (m > 0) {
+            const int j = m - 1;
+            bool un = (j >= k);
+            if (!un) {                                       // below k only skipped sub-layers are unassigned
+                while (sp >= 0 && (!(w.flag[sp] & 1) || w.fe[sp] > j)) --sp;
+                un = (sp >= 0 && w.fe[sp] == j);
+            }
+            if (!un) break;                                  // (layer_id + 1) != min(...) from here on (:243)
+            const double d = dlay[j / kH];
+            if (!(c > d)) break;                             // :246 fails; every later id fails :243
+            c -= d;
+            m = j;
+            if (j < k) w.flag[sp] |= 2;
+        }
+        w.capa[last] = c;
+    }
+
+    // ---- leftovers (:251-287) ----------------------------------------------------------------
+    int nl = 0;
+    for (int s = 0; s < last; ++s)
+        if ((w.flag[s] & 3) == 1) {
+            if (nl >= Scratch<MAXS, MAXL>::kLeft) return METIS_FATAL_SCRATCH;
+            w.lid[nl++] = w.fe[s];
+        }
+    for (int j = k; j < m; ++j) {
+        if (nl >= Scratch<MAXS, MAXL>::kLeft) return METIS_FATAL_SCRATCH;
+        w.lid[nl++] = (uint16_t)j;
+    }
+    {
+        int x = -1;                                          // forward stages 0..x lie entirely below the query
+        for (int i = 0; i < nl; ++i) {
+            const int j = w.lid[i];
+            while (x + 1 < last && w.fe[x + 1] <= j) ++x;
+            // lo: stage of the largest assigned id < j whose stage holds nothing above j
+            int lo = 0;
+            {
+                int a = i - 1, u = x;
+                for (;;) {
+                    while (u >= 0 && w.fe[u] == w.fs[u]) --u;
+                    const int pf = (u >= 0) ? (int)w.fe[u] - 1 : -1;
+                    const int pl = (a >= 0) ? (int)w.lid[a] : -1;
+                    if (pf < 0 && pl < 0) break;
+                    if (pf > pl) { lo = u; break; }
+                    const int t = w.lst[a];
+                    const bool above = (t == last) || (w.fe[t] > w.fs[t] && (int)w.fs[t] > j);
+                    if (!above) { lo = t; break; }
+                    --a;
+                }
+            }
+            // hi: first stage above j that holds nothing below j
+            int hi = x + 1;
+            while (hi < last && (w.fe[hi] == w.fs[hi] || (w.flag[hi] & 4))) ++hi;
+            if (hi > last) hi = last;
+            if (lo > hi) return METIS_FATAL_SCRATCH;
+            int pick = lo;
+            double best = w.capa[lo];
+            for (int t = lo + 1; t <= hi; ++t)
+                if (w.capa[t] > best) { best = w.capa[t]; pick = t; }
+            w.capa[pick] -= dlay[j / kH];
+            w.lst[i] = (uint8_t)pick;
+            w.flag[pick] |= 4;
+        }
+    }
+
+    // ---- majority vote back to real layers (:290-308) ----------------------------------------
+    {
+        int lf = 0, u = 0;
+        for (int r = 0; r < L; ++r) {
+            const int j0 = kH * r, j6 = j0 + kH - 1;
+            while (u < last && (int)w.fe[u] <= j0) ++u;
+            uint8_t own;
+            if (u < last && (int)w.fs[u] <= j0 && j6 < (int)w.fe[u]) {
+                own = (uint8_t)u;
+            } else if (j0 >= m) {
+                own = (uint8_t)last;
+            } else {
+                int st[kH];
+                int uu = u;
+                for (int q = 0; q < kH; ++q) {
+                    const int j = j0 + q;
+                    if (lf < nl && (int)w.lid[lf] == j) st[q] = w.lst[lf++];
+                    else if (j >= m) st[q] = last;
+                    else { while (uu < last && (int)w.fe[uu] <= j) ++uu; st[q] = uu; }
+                }
+                int cand = st[0], votes = 1;                // Boyer-Moore, then exact count
+                for (int q = 1; q < kH; ++q) {
+                    if (votes == 0) { cand = st[q]; votes = 1; }
+                    else if (st[q] == cand) ++votes;
+                    else --votes;
+                }
+                int n = 0;
+                for (int q = 0; q < kH; ++q) n += (st[q] == cand);
+                own = (2 * n > kH) ? (uint8_t)cand : kDropped;   // count > hallucination / 2 (:295)
+            }
+            w.owner[r] = own;
+        }
+    }
+    for (int s = 0; s < S; ++s) w.cnt[s] = 0;
+    for (int r = 0; r < L; ++r) {
+        const int o = w.owner[r];
+        if (o == kDropped) continue;
+        if (w.cnt[o] == 0) w.fs[o] = (uint16_t)r;
+        w.fe[o] = (uint16_t)r;
+        ++w.cnt[o];
+    }
+    for (int s = 0; s < S; ++s)                              // :300-306
+        w.capa[s] = w.cnt[s] ? w.perf[s] - py_sum_range(lc, w.fs[s], (int)w.fe[s] + 1) : w.perf[s];
+
+    // ---- boundary adjustment (:310-356): at most three committed single-layer moves ---------
+    for (int n = 1; n <= 3; ++n) {
+        int top = 0;
+        double maxc = w.capa[0];
+        for (int t = 1; t < S; ++t)
+            if (w.capa[t] > maxc) { maxc = w.capa[t]; top = t; }
+        int nb = -1;
+        double val = INFINITY;
+        if (top - 1 >= 0 && w.capa[top - 1] < val) { nb = top - 1; val = w.capa[top - 1]; }
+        if (top + 1 < S && w.capa[top + 1] < val) { nb = top + 1; }
+        if (nb < 0 || w.cnt[nb] <= 1) break;                 // no-op rounds leave the state unchanged
+        int layer = -1;
+        if (top > nb) { for (int r = L - 1; r >= 0; --r) if (w.owner[r] == nb) { layer = r; break; } }
+        else          { for (int r = 0; r < L; ++r) if (w.owner[r] == nb) { layer = r; break; } }
+        const double dl = lc[layer];
+        const double ntop = w.capa[top] - dl;
+        const double nnb = w.capa[nb] + dl;
+        double newmax = -INFINITY;
+        for (int t = 0; t < S; ++t) {
+            const double v = (t == top) ? ntop : (t == nb) ? nnb : w.capa[t];
+            if (v > newmax) newmax = v;
+        }
+        if (newmax > maxc) break;                            // :352 (not committed)
+        w.owner[layer] = (uint8_t)top;
+        w.capa[top] = ntop;
+        w.capa[nb] = nnb;
+        ++w.cnt[top];
+        --w.cnt[nb];
+    }
+
+    w.part[0] = 0;                                           // :358-364
+    for (int s = 0; s < S; ++s) w.part[s + 1] = (uint16_t)(w.part[s] + w.cnt[s]);
+    return METIS_FATAL_NONE;
+}
+
+// ---------------------------------------------------------------------------
+// DataLoadBalancer.partition_data (model/load_balancer.py:155-179) on a rank range.
+// Replicas are grouped in runs of equal device type (ranks are laid out type by type).
+// ---------------------------------------------------------------------------
+struct HSplit {
+    int nruns;
+    int type[METIS_MAX_TYPES];
+    int n[METIS_MAX_TYPES];      // replicas in the run
+    int base[METIS_MAX_TYPES];   // int(bs * share)
+    int plus[METIS_MAX_TYPES];   // leading replicas of the run that get +1
+};
+
+MB_HD_NOINLINE int partition_data(const Tables &T, int ns, int rank_lo, int count, int dp, int tpc, int bs,
+                                  HSplit &out, uint32_t &aux) {
+    const int gsz = count / dp;
+    double perf[METIS_MAX_TYPES];
+    PySum total;
+    out.nruns = 0;
+    for (int i = 0; i < dp; ++i) {
+        const int t = type_of_rank(T, ns, rank_lo + i * gsz);
+        if (out.nruns == 0 || out.type[out.nruns - 1] != t) {
+            const int key = key_of(T, t, tpc, 1);
+            if (key < 0) { aux = ((uint32_t)tpc << 16) | 1u; return METIS_FATAL_KEY_EXEC; }
+            const double e = T.exec_full[key];
+            if (e == 0.0) return METIS_FATAL_ZERODIV;
+            out.type[out.nruns] = t;
+            out.n[out.nruns] = 0;
+            perf[out.nruns] = 1. / e;
+            ++out.nruns;
+        }
+        ++out.n[out.nruns - 1];
+        total.add(perf[out.nruns - 1]);
+    }
+    const double tot = total.result();
+    double frac[METIS_MAX_TYPES];
+    int assigned = 0;
+    for (int r = 0; r < out.nruns; ++r) {
+        const double v = (double)bs * (perf[r] / tot);
+        const int b = (int)v;
+        out.base[r] = b;
+        out.plus[r] = 0;
+        frac[r] = v - (double)b;
+        assigned += b * out.n[r];
+    }
+    int rem = bs - assigned;
+    bool used[METIS_MAX_TYPES];
+    for (int r = 0; r < out.nruns; ++r) used[r] = false;
+    for (int it = 0; it < out.nruns && rem > 0; ++it) {      // stable descending order of the remainders
+        int pick = -1;
+        for (int r = 0; r < out.nruns; ++r)
+            if (!used[r] && (pick < 0 || frac[r] > frac[pick])) pick = r;
+        used[pick] = true;
+        const int g = rem < out.n[pick] ? rem : out.n[pick];
+        out.plus[pick] = g;
+        rem -= g;
+    }
+    if (rem > 0) return METIS_FATAL_SCRATCH;                  // reference would raise IndexError (:177)
+    return METIS_FATAL_NONE;
+}
+
+// Sink interface expected by evaluate_plan (see metis_search.cu / tests/hostsim):
+//   void partition_call(); void balancer_run(); void keyerror();
+//   void fatal(uint32_t ordinal, int code, uint32_t aux);
+//   void emit(const PlanDesc&, int step, int nrep, double cost, const uint8_t *tpc, const uint16_t *part);
+
+template <int MAXS, int MAXL>
+struct PlanEvaluator {
+    const Tables &T;
+    Scratch<MAXS, MAXL> &w;
+    PlanDesc pd;
+    int bs_total;         // gbs // batches
+    uint32_t aux;
+
+    MB_HD PlanEvaluator(const Tables &t, Scratch<MAXS, MAXL> &s) : T(t), w(s), bs_total(0), aux(0) {}
+
+    MB_HD int group(int s) const { return 1 << w.gcode[s]; }
+    MB_HD int dp_of(int s) const { return (1 << w.gcode[s]) >> w.tpc[s]; }
+
+    // IntraStagePlanGenerator._is_valid_strategies (search_space/plan.py:238-249)
+    MB_HD bool valid() const {
+        for (int s = 0; s < pd.S; ++s) {
+            const int mbs = T.p.gbs / dp_of(s) / pd.batches;
+            if (mbs == 0 || mbs > T.p.max_bs) return false;
+            if ((1 << w.tpc[s]) > T.p.max_tp) return false;
+        }
+        return true;
+    }
+
+    // IntraStagePlanGenerator._next_strategy (search_space/plan.py:251-268)
+    MB_HD bool next_strategy(bool have_state) {
+        int pick = -1;
+        if (have_state) {
+            for (int s = 0; s < pd.S; ++s)
+                if (dp_of(s) != 1 && (pick < 0 || w.mstate[s] < w.mstate[pick])) pick = s;
+        } else {                                             // default state 1/dp: largest dp first
+            for (int s = 0; s < pd.S; ++s)
+                if (dp_of(s) != 1 && (pick < 0 || dp_of(s) > dp_of(pick))) pick = s;
+        }
+        if (pick < 0) return false;
+        ++w.tpc[pick];
+        return true;
+    }
+
+    // StagePerformance.get_device_group_memory_capacity, one stage (model/device_group.py:87-101)
+    MB_HD double memory_capacity(int a, int b) const {
+        const int nt = T.p.num_types;
+        const int32_t *end = T.run_end + pd.ns * nt;
+        const uint8_t *typ = T.run_type + pd.ns * nt;
+        PySum acc;
+        int lo = 0;
+        for (int k = 0; k < nt; ++k) {
+            const int hi = end[k];
+            const int x = (a > lo ? a : lo), y = (b < hi ? b : hi);
+            if (y > x) acc.add(T.type_memory[typ[k]] * (double)(y - x));
+            lo = hi;
+        }
+        return acc.result();
+    }
+
+    // hetero replica cost for StagePerformance (model/device_group.py:40-52): sum of full-model times
+    MB_HD int replica_perf_cost(int type, int tpc, int h, double &out) {
+        double acc = 0.;
+        for (int bit = 30; bit >= 0; --bit) {
+            const int piece = 1 << bit;
+            if (!(h & piece)) continue;
+            const int key = key_of(T, type, tpc, piece);
+            if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)piece; return METIS_FATAL_KEY_EXEC; }
+            acc += T.exec_full[key];
+        }
+        out = acc;
+        return 0;
+    }
+
+    // StagePerformance.get_intra_stage_compute_performance (model/device_group.py:54-85) -> w.perf
+    MB_HD_NOINLINE int compute_performance() {
+        PySum total;
+        int a = 0;
+        for (int s = 0; s < pd.S; ++s) {
+            const int b = a + group(s);
+            const int dp = dp_of(s), tpc = w.tpc[s];
+            const int ta = type_of_rank(T, pd.ns, a), tb = type_of_rank(T, pd.ns, b - 1);
+            double p;
+            if (ta == tb) {
+                const int bs = T.p.gbs / pd.batches / dp;
+                const int key = key_of(T, ta, tpc, bs);
+                if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; return METIS_FATAL_KEY_EXEC; }
+                const double e = T.exec_full[key];
+                if (e == 0.0) return METIS_FATAL_ZERODIV;
+                p = 1. / e;
+            } else {
+                HSplit hs;
+                int rc = partition_data(T, pd.ns, a, b - a, dp, tpc, bs_total, hs, aux);
+                if (rc) return rc;
+                double mx = -INFINITY;
+                for (int r = 0; r < hs.nruns; ++r) {
+                    double c;
+                    if (hs.plus[r] > 0) {
+                        rc = replica_perf_cost(hs.type[r], tpc, hs.base[r] + 1, c);
+                        if (rc) return rc;
+                        if (c > mx) mx = c;
+                    }
+                    if (hs.plus[r] < hs.n[r]) {
+                        rc = replica_perf_cost(hs.type[r], tpc, hs.base[r], c);
+                        if (rc) return rc;
+                        if (c > mx) mx = c;
+                    }
+                }
+                p = (mx != 0.0) ? 1. / mx : 0.0;
+            }
+            w.perf[s] = p;
+            total.add(p);
+            a = b;
+        }
+        const double tot = total.result();
+        if (tot == 0.0) return METIS_FATAL_ZERODIV;
+        for (int s = 0; s < pd.S; ++s) w.perf[s] = w.perf[s] / tot;
+        return 0;
+    }
+
+    // LayerLoadBalancer._get_stage_memory_demand, one stage (model/load_balancer.py:29-55, quirk Q6)
+    MB_HD_NOINLINE int memory_demand(int s, int a, int b, double &out) {
+        const int la = w.part[s], lb = w.part[s + 1];
+        const int type0 = T.run_type[pd.ns * T.p.num_types];
+        const int tpc = w.tpc[s];
+        double demand = 0.001;
+        if (type_of_rank(T, pd.ns, a) == type_of_rank(T, pd.ns, b - 1)) {
+            const int bs = T.p.gbs / pd.batches / dp_of(s);
+            const int key = key_of(T, type0, tpc, bs);
+            if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; return METIS_FATAL_KEY_MEMORY; }
+            demand += py_sum_range(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
+        } else {
+            HSplit hs;                                       // whole-cluster device list (quirk Q6)
+            const int rc = partition_data(T, pd.ns, 0, T.p.total_devices, dp_of(s), tpc, bs_total, hs, aux);
+            if (rc) return rc;
+            for (int r = 0; r < hs.nruns; ++r)
+                for (int i = 0; i < hs.n[r]; ++i) {
+                    const int h = hs.base[r] + (i < hs.plus[r] ? 1 : 0);
+                    for (int bit = 30; bit >= 0; --bit) {
+                        const int piece = 1 << bit;
+                        if (!(h & piece)) continue;
+                        const int key = key_of(T, type0, tpc, piece);
+                        if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)piece; return METIS_FATAL_KEY_MEMORY; }
+                        demand += py_sum_range(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
+                    }
+                }
+        }
+        out = demand;
+        return 0;
+    }
+
+    // LayerLoadBalancer._adj_compute_performance (model/load_balancer.py:71-107)
+    // in: w.perf (c_capa), w.extra (m_demand); out: w.perf; returns 1 = None, 0 ok, <0 fatal (negated code)
+    MB_HD_NOINLINE int adjust_performance() {
+        const int S = pd.S;
+        double need = 0.;
+        PySum avail_sum;
+        int a = 0;
+        for (int s = 0; s < S; ++s) {
+            const int b = a + group(s);
+            const double c = w.perf[s], mc = memory_capacity(a, b), md = w.extra[s];
+            double av, adj;
+            if (mc > md) {
+                adj = c;
+                av = (c * mc / md) - c;
+            } else {
+                av = 0.0;
+                adj = c * (mc / md) * 0.9;
+                need += (c - adj);
+            }
+            w.capa[s] = av;           // available_compute_capacity
+            w.mstate[s] = adj;        // adj_sc_capa
+            avail_sum.add(av);
+            a = b;
+        }
+        if (avail_sum.result() < need) return 1;
+        for (int s = 0; s < S; ++s) w.extra[s] = 0.;
+        int guard = 0;
+        while (need > 0.01) {
+            PySum tot;
+            for (int s = 0; s < S; ++s) tot.add(w.capa[s] > 0.001 ? w.perf[s] : 0.0);
+            const double tmp_total = tot.result();
+            for (int s = 0; s < S; ++s) {
+                const double av = w.capa[s];
+                const double ratio = av > 0.001 ? w.perf[s] / tmp_total : 0.0;
+                const double want = need * ratio;
+                const double give = want > av ? av : want;
+                w.extra[s] += give;
+                w.capa[s] -= give;
+                need -= give;
+            }
+            if (++guard > 4096) return -METIS_FATAL_HANG;
+        }
+        for (int s = 0; s < S; ++s) w.perf[s] = w.extra[s] + w.mstate[s];
+        return 0;
+    }
+
+    // LayerLoadBalancer.partition_layer (model/load_balancer.py:121-144)
+    // returns attempt number 1..3, 0 = (None, -1, None), <0 = fatal (negated code)
+    template <class Sink>
+    MB_HD_NOINLINE int partition_layer(Sink &sink) {
+        const int S = pd.S;
+        for (int attempt = 1; attempt <= 3; ++attempt) {
+            sink.balancer_run();
+            int rc = balance_run<MAXS, MAXL>(T, S, w);
+            if (rc) return -rc;
+            bool oom = false;
+            int a = 0;
+            for (int s = 0; s < S; ++s) {
+                const int b = a + group(s);
+                double md;
+                rc = memory_demand(s, a, b, md);
+                if (rc) return -rc;
+                const double st = memory_capacity(a, b) - md;
+                w.extra[s] = md;
+                w.capa[s] = st;
+                if (st < 0) oom = true;
+                a = b;
+            }
+            if (!oom) {
+                for (int s = 0; s < S; ++s) w.mstate[s] = w.capa[s];
+                return attempt;
+            }
+            rc = adjust_performance();
+            if (rc < 0) return rc;
+            if (rc == 1) return 0;
+        }
+        return 0;
+    }
+
+    // bandwidth of a set of ranks given as node range / strided group (model/cluster_bandwidth.py:169-195)
+    MB_HD double bw_of_node_range(int n0, int n1) const {
+        const int per = T.p.devices_per_node;
+        if (n0 == n1) return T.bw_first[type_of_rank(T, pd.ns, n0 * per)];
+        double slow = INFINITY;
+        const int nt = T.p.num_types;
+        const int32_t *end = T.run_end + pd.ns * nt;
+        const uint8_t *typ = T.run_type + pd.ns * nt;
+        int lo = 0;
+        for (int k = 0; k < nt; ++k) {                       // types whose node run intersects [n0, n1]
+            const int hi = end[k];
+            if (hi > lo && n0 * per < hi && (n1 + 1) * per > lo) {
+                const double v = T.bw_min[typ[k]];
+                if (v < slow) slow = v;
+            }
+            lo = hi;
+        }
+        return slow;
+    }
+
+    MB_HD double dp_bandwidth(int a, int dp, int tp) const {
+        const int per = T.p.devices_per_node;
+        double slow = INFINITY;
+        for (int d = 0; d < dp; ++d) {                       // group d = ranks a + d + i*dp (:148-156)
+            const int n0 = (a + d) / per;
+            int nlast = n0;
+            bool multi = false;
+            double gmin = INFINITY;
+            int tprev = -1;
+            for (int i = 0; i < tp; ++i) {
+                const int node = (a + d + i * dp) / per;
+                if (node != nlast) { multi = true; nlast = node; }
+                const int t = type_of_rank(T, pd.ns, node * per);
+                if (t != tprev) { const double v = T.bw_min[t]; if (v < gmin) gmin = v; tprev = t; }
+            }
+            const double bw = multi ? gmin : T.bw_first[type_of_rank(T, pd.ns, n0 * per)];
+            if (bw < slow) slow = bw;
+        }
+        return slow;
+    }
+
+    // HeteroCostEstimator.get_cost (model/cost_estimator.py:199-244); returns 0 ok, 1 KeyError
+    MB_HD_NOINLINE int get_cost(double &cost_out) {
+        const int per = T.p.devices_per_node;
+        const int Lm = T.p.num_layers;
+        const int nstage = pd.label < pd.S ? pd.label : pd.S;  // zip(range(plan.num_stage), strategies)
+        PySum lens_sum;
+        double max_len = -INFINITY, max_upd = -INFINITY, max_dp = -INFINITY;
+        double pp_cost = 0., fb_sync = 0.;
+        int a = 0;
+        for (int s = 0; s < nstage; ++s) {
+            const int b = a + group(s);
+            const int la = w.part[s], lb = w.part[s + 1];
+            const int dp = dp_of(s), tpc = w.tpc[s], tp = 1 << tpc;
+            const int ta = type_of_rank(T, pd.ns, a), tb = type_of_rank(T, pd.ns, b - 1);
+            const int mbs = T.p.gbs / dp / pd.batches;
+            double len;
+            if (ta == tb) {                                   // _get_execution_cost :175-188
+                const int key = key_of(T, ta, tpc, mbs);
+                if (key < 0) return 1;
+                len = py_sum_range(T.lc + (size_t)key * T.p.lpad, la, lb);
+            } else {                                          // :189-197 with :152-173
+                HSplit hs;
+                uint32_t dummy;
+                if (partition_data(T, pd.ns, a, b - a, dp, tpc, bs_total, hs, dummy)) return 1;
+                len = -INFINITY;
+                for (int r = 0; r < hs.nruns; ++r)
+                    for (int v = 0; v < 2; ++v) {
+                        const int cntv = v ? hs.plus[r] : hs.n[r] - hs.plus[r];
+                        const int h = hs.base[r] + v;
+                        if (cntv <= 0 || h == 0) continue;
+                        double acc = 0.;
+                        for (int bit = 30; bit >= 0; --bit) {
+                            const int piece = 1 << bit;
+                            if (!(h & piece)) continue;
+                            if (piece > T.p.max_bs) return 1;            // :166-167
+                            const int key = key_of(T, hs.type[r], tpc, piece);
+                            if (key < 0) return 1;
+                            acc += py_sum_range(T.lc + (size_t)key * T.p.lpad, la, lb);
+                        }
+                        if (acc > len) len = acc;
+                    }
+            }
+            lens_sum.add(len);
+            if (len > max_len) max_len = len;
+
+            if (s == nstage - 1) {                            // _get_fb_sync_cost :57-72 (quirk Q9)
+                const int nt = T.p.num_types;
+                const int32_t *end = T.run_end + pd.ns * nt;
+                const uint8_t *typ = T.run_type + pd.ns * nt;
+                double mx = -INFINITY;
+                int lo = 0;
+                for (int k = 0; k < nt; ++k) {
+                    const int hi = end[k];
+                    if ((a > lo ? a : lo) < (b < hi ? b : hi)) {
+                        const int key = key_of(T, typ[k], tpc, mbs);
+                        if (key < 0) return 1;
+                        const double v = T.fb_sync[key];
+                        if (v == 0.0) return 1;               // falsy -> KeyError
+                        if (v > mx) mx = v;
+                    }
+                    lo = hi;
+                }
+                fb_sync = mx * (double)pd.batches;
+            } else {                                          // :224-227
+                double act;
+                if (lb == Lm - 1)
+                    act = (double)((int64_t)mbs * T.p.sequence_length * T.p.vocab_size) / (double)tp;
+                else
+                    act = (double)((int64_t)mbs * T.p.sequence_length * T.p.hidden_size);
+                const int b2 = b + group(s + 1);
+                const double bw = T.p.uniform_bw ? T.bw_first[0] : bw_of_node_range(a / per, (b2 - 1) / per);
+                pp_cost += act / (bw * 1048576.0);
+            }
+            // get_parameter_size_by_stage (model/activation_parameter.py:40-51)
+            int ntr = lb - la;
+            double params = 0.0;
+            if (la == 0) { params += T.p.input_params / (double)tp; --ntr; }
+            if (lb == Lm) { params += T.p.output_params / (double)tp; --ntr; }
+            params += T.p.transformer_params / (double)tp * (double)ntr;
+            const double bwd = (T.p.uniform_bw ? T.bw_first[0] : dp_bandwidth(a, dp, tp)) * 1048576.0;
+            const double dpc = (double)(2 * (dp - 1)) / ((double)dp * bwd) * params;    // :37-43
+            if (dpc > max_dp) max_dp = dpc;
+            const double upd = T.p.optimizer_time / (double)tp * ((double)(lb - la) / (double)Lm);   // :145-147
+            if (upd > max_upd) max_upd = upd;
+            a = b;
+        }
+        const double exec = ((double)(pd.batches - 1) * max_len) + lens_sum.result();   // :235-236
+        const double bg = T.p.batch_generator * (double)pd.batches;
+        cost_out = exec + fb_sync + max_upd + max_dp + pp_cost + bg;                   // :241-242
+        return 0;
+    }
+
+    // cost_het_cluster.py:31-48 for one inter-stage plan, with IntraStagePlanGenerator.has_next
+    // (search_space/plan.py:192-226) inlined.  `only_step` >= 0 stops after emitting that step.
+    template <class Sink>
+    MB_HD_NOINLINE void run(const PlanDesc &plan, Sink &sink, int only_step = -1) {
+        pd = plan;
+        if (pd.S > MAXS || T.p.num_layers > MAXL) { sink.fatal(pd.ordinal, METIS_FATAL_SCRATCH, 0); return; }
+        bs_total = T.p.gbs / pd.batches;
+        for (int s = 0; s < pd.S; ++s) { w.gcode[s] = pd.row[s]; w.tpc[s] = 0; }
+        bool started = false, have_state = false;
+        int nrep = 0, step = 0;
+        for (;;) {
+            if (nrep == 1) return;                            // plan.py:194-195
+            int attempt = 0;
+            for (;;) {
+                if (!started) started = true;                 // _initial_strategies :231-236
+                else if (!next_strategy(have_state)) return;  // :203-204
+                if (!valid()) continue;
+                sink.partition_call();
+                int rc = compute_performance();
+                if (rc) { sink.fatal(pd.ordinal, rc, aux); return; }
+                attempt = partition_layer(sink);
+                if (attempt < 0) { sink.fatal(pd.ordinal, -attempt, aux); return; }
+                have_state = attempt > 0;                     // memory_state is None after a failure (:225)
+                if (attempt > 0) break;
+            }
+            nrep = attempt;
+            double cost;
+            if (get_cost(cost) == 0) sink.emit(pd, step, nrep, cost, w.tpc, w.part);
+            else sink.keyerror();
+            if (only_step >= 0 && step == only_step) return;
+            ++step;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// HomoCostEstimator.get_cost (model/cost_estimator.py:98-138) for one UniformPlan.
+// returns 0 ok, 1 KeyError; *oom = _detect_oom_occurrence
+// ---------------------------------------------------------------------------
+MB_HD int homo_cost(const Tables &T, int type, int dp, int pp, int tp, int mbs, int gbs, double &cost_out,
+                    int &oom) {
+    const int L = T.p.num_layers;
+    const int per = T.p.devices_per_node;
+    int tpc = 0;
+    while ((1 << tpc) < tp) ++tpc;
+    const int key = ((1 << tpc) == tp) ? key_of(T, type, tpc, mbs) : -1;   // unprofiled tp -> KeyError (:93-94)
+    if (key < 0) return 1;
+    const int num_mbs = gbs / mbs / dp;
+    (void)type;
+    const double intra = T.p.node0_bandwidth;                                // cluster_bandwidth.py:75-76
+    const double inter = T.p.node0_bandwidth;                                // quirk Q2: same field
+    const int base = (L - 2) / pp, rem = (L - 2) % pp;                       // model/utils.py:5-31
+    PySum lens_sum;
+    double max_len = -INFINITY, max_params = -INFINITY, max_mem = -INFINITY;
+    double pp_cost = 0., fb_sync = 0.;
+    int a = 0;
+    for (int s = 0; s < pp; ++s) {
+        int count = base + ((s >= 1 && s <= rem) ? 1 : 0) + (s == 0 ? 1 : 0) + (s == pp - 1 ? 1 : 0);
+        const int b = a + count;
+        const double len = py_sum_range(T.lc + (size_t)key * T.p.lpad, a, b);
+        lens_sum.add(len);
+        if (len > max_len) max_len = len;
+        // sum(model_parameters[a:b]) over get_parameter_size(tp) (model/activation_parameter.py:34-38)
+        PySum ps;
+        for (int r = a; r < b && r < L; ++r) {
+            const double v = (r == 0) ? T.p.input_params / (double)tp
+                           : (r == L - 1) ? T.p.output_params / (double)tp
+                           : T.p.transformer_params / (double)tp;
+            ps.add(v);
+        }
+        const double sp = ps.result();
+        if (sp > max_params) max_params = sp;
+        const double sm = py_sum_range(T.mem + (size_t)key * T.p.lpad, a, b);
+        if (sm > max_mem) max_mem = sm;
+        if (s == pp - 1) {
+            const double v = T.fb_sync[key];
+            if (v == 0.0) return 1;
+            fb_sync = v * (double)num_mbs;
+        } else {
+            double act;
+            if (b == L - 1) act = (double)((int64_t)mbs * T.p.sequence_length * T.p.vocab_size) / (double)tp;
+            else act = (double)((int64_t)mbs * T.p.sequence_length * T.p.hidden_size);
+            double bw = intra;                                // cluster_bandwidth.py:111-123
+            for (int d = 0; d < dp; ++d)
+                for (int t = 0; t < tp; ++t) {
+                    const int r0 = s * dp * tp + d * tp + t, r1 = r0 + dp * tp;
+                    if (r0 / per != r1 / per) bw = inter;
+                }
+            pp_cost += act / (bw * 1048576.0);
+        }
+        a = b;
+    }
+    oom = (T.p.node0_memory < max_mem) ? 1 : 0;              // cost_estimator.py:31-32
+    const double exec = ((double)(num_mbs - 1) * max_len) + lens_sum.result();
+    const double upd = T.p.optimizer_time / (double)pp / (double)tp;
+    double bw = intra;                                        // :125-132
+    for (int p = 0; p < pp; ++p)
+        if ((p * dp * tp) / per != ((p + 1) * dp * tp - 1) / per) bw = inter;
+    const double dpc = (double)(2 * (dp - 1)) / ((double)dp * (bw * 1048576.0)) * max_params;
+    const double bg = T.p.batch_generator * (double)num_mbs;
+    cost_out = exec + fb_sync + upd + dpc + pp_cost + bg;
+    return 0;
+}
+
+}  // namespace metis

@@ -1,0 +1,555 @@
+// metis_search.cu - sm_100a kernels + C ABI of libmetis_b200.so (see include/metis_b200.h).
+//
+// Kernel map:
+//   pack_tables_kernel    flattens the profile tables into one 16 B-aligned blob (+ norm_lc/7)
+//   het_search_kernel     a2..a16: one thread per inter-stage plan; tables staged into shared
+//                         memory by one TMA bulk copy (cp.async.bulk + mbarrier) per block;
+//                         16 B record per costed candidate; warp-shuffle + block argmin
+//   het_finalize_kernel   grid argmin over the per-block bests, counters -> summary
+//   het_detail_kernel     replays chosen (ordinal, step) candidates to materialise strategies/partition
+//   homo_cost_kernel      a17: one thread per UniformPlan
+//   layer_balance_kernel  a10 alone, for unit parity
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no FMA contraction: parity).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "metis_eval.cuh"
+
+namespace metis {
+
+constexpr int kThreads = 128;
+constexpr int kMaxS = METIS_MAX_STAGES;
+constexpr int kMaxL = METIS_MAX_LAYERS;
+constexpr int kSmemBlobMax = 160 * 1024;
+
+static thread_local char g_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return METIS_E_CUDA;
+}
+static int arg_fail(const char *what) {
+    snprintf(g_err, sizeof(g_err), "%s", what);
+    return METIS_E_ARG;
+}
+
+struct BlobLayout {
+    uint32_t total;
+    uint32_t key, lc, mem, exec_full, fb, norm, dlay, tmem, bwf, bwm, runt, rune;
+};
+
+static uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+
+static BlobLayout make_layout(const MetisProblem &p) {
+    BlobLayout l;
+    uint32_t o = 0;
+    const uint32_t nkey = (uint32_t)p.num_types * p.num_tp * p.num_bs;
+    l.key = o;       o = align16(o + nkey * 2);
+    l.lc = o;        o = align16(o + (uint32_t)p.num_keys * p.lpad * 8);
+    l.mem = o;       o = align16(o + (uint32_t)p.num_keys * p.lpad * 8);
+    l.exec_full = o; o = align16(o + (uint32_t)p.num_keys * 8);
+    l.fb = o;        o = align16(o + (uint32_t)p.num_keys * 8);
+    l.norm = o;      o = align16(o + (uint32_t)p.norm_len * 8);
+    l.dlay = o;      o = align16(o + (uint32_t)p.norm_len * 8);
+    l.tmem = o;      o = align16(o + (uint32_t)p.num_types * 8);
+    l.bwf = o;       o = align16(o + (uint32_t)p.num_types * 8);
+    l.bwm = o;       o = align16(o + (uint32_t)p.num_types * 8);
+    l.runt = o;      o = align16(o + (uint32_t)p.num_node_sequences * p.num_types);
+    l.rune = o;      o = align16(o + (uint32_t)p.num_node_sequences * p.num_types * 4);
+    l.total = o;
+    return l;
+}
+
+__device__ __forceinline__ Tables make_tables(const MetisProblem &p, const BlobLayout &l, const uint8_t *base) {
+    Tables T;
+    T.p = p;
+    T.key_index = reinterpret_cast<const int16_t *>(base + l.key);
+    T.lc = reinterpret_cast<const double *>(base + l.lc);
+    T.mem = reinterpret_cast<const double *>(base + l.mem);
+    T.exec_full = reinterpret_cast<const double *>(base + l.exec_full);
+    T.fb_sync = reinterpret_cast<const double *>(base + l.fb);
+    T.norm_lc = reinterpret_cast<const double *>(base + l.norm);
+    T.dlay = reinterpret_cast<const double *>(base + l.dlay);
+    T.type_memory = reinterpret_cast<const double *>(base + l.tmem);
+    T.bw_first = reinterpret_cast<const double *>(base + l.bwf);
+    T.bw_min = reinterpret_cast<const double *>(base + l.bwm);
+    T.run_type = base + l.runt;
+    T.run_end = reinterpret_cast<const int32_t *>(base + l.rune);
+    return T;
+}
+
+__device__ __forceinline__ void copy_bytes(uint8_t *dst, const void *src, uint32_t n, uint32_t tid, uint32_t nthr) {
+    const uint8_t *s = static_cast<const uint8_t *>(src);
+    for (uint32_t i = tid; i < n; i += nthr) dst[i] = s[i];
+}
+
+__global__ void pack_tables_kernel(MetisProblem p, BlobLayout l, uint8_t *blob) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const uint32_t nkey = (uint32_t)p.num_types * p.num_tp * p.num_bs;
+    copy_bytes(blob + l.key, p.key_index, nkey * 2, tid, nthr);
+    copy_bytes(blob + l.lc, p.layer_compute, (uint32_t)p.num_keys * p.lpad * 8, tid, nthr);
+    copy_bytes(blob + l.mem, p.layer_memory, (uint32_t)p.num_keys * p.lpad * 8, tid, nthr);
+    copy_bytes(blob + l.exec_full, p.exec_full, (uint32_t)p.num_keys * 8, tid, nthr);
+    copy_bytes(blob + l.fb, p.fb_sync, (uint32_t)p.num_keys * 8, tid, nthr);
+    copy_bytes(blob + l.norm, p.norm_lc, (uint32_t)p.norm_len * 8, tid, nthr);
+    copy_bytes(blob + l.tmem, p.type_memory, (uint32_t)p.num_types * 8, tid, nthr);
+    copy_bytes(blob + l.bwf, p.type_bw_first, (uint32_t)p.num_types * 8, tid, nthr);
+    copy_bytes(blob + l.bwm, p.type_bw_min, (uint32_t)p.num_types * 8, tid, nthr);
+    copy_bytes(blob + l.runt, p.ns_run_type, (uint32_t)p.num_node_sequences * p.num_types, tid, nthr);
+    copy_bytes(blob + l.rune, p.ns_run_end, (uint32_t)p.num_node_sequences * p.num_types * 4, tid, nthr);
+    double *dlay = reinterpret_cast<double *>(blob + l.dlay);
+    for (uint32_t r = tid; r < (uint32_t)p.norm_len; r += nthr)
+        dlay[r] = p.norm_lc[r] / 7.0;                       // tmp_demand = c_demand / hallucination (:191)
+}
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier --------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void stage_blob_tma(uint8_t *smem, const uint8_t *blob, uint32_t bytes, uint64_t *mbar) {
+    const uint32_t bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        constexpr uint32_t kChunk = 32768;
+        for (uint32_t off = 0; off < bytes; off += kChunk) {
+            const uint32_t n = (bytes - off < kChunk) ? bytes - off : kChunk;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(smem_u32(smem + off)), "l"(blob + off), "r"(n), "r"(bar)
+                : "memory");
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+    }
+}
+
+// ---- ordinal -> plan ---------------------------------------------------------------------------
+__device__ __forceinline__ bool decode_plan(const MetisPlanSpace &sp, int64_t ordinal, PlanDesc &pd) {
+    if (ordinal < 0 || ordinal >= sp.num_plans) return false;
+    int lo = 0, hi = sp.num_blocks - 1;
+    while (lo < hi) {                                         // last block with first_ordinal <= ordinal
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&sp.blocks[mid].first_ordinal) <= ordinal) lo = mid; else hi = mid - 1;
+    }
+    const MetisPlanBlock b = sp.blocks[lo];
+    const int64_t rel = ordinal - b.first_ordinal;
+    const int64_t row = rel / sp.num_div;
+    const int div = (int)(rel - row * sp.num_div);
+    pd.ordinal = (uint32_t)ordinal;
+    pd.ns = b.ns_idx;
+    pd.S = b.num_stage;
+    pd.label = b.label_stage;
+    pd.batches = __ldg(&sp.batches[div]);
+    pd.row = sp.rows + b.rows_offset + row * b.num_stage;
+    return true;
+}
+
+__device__ __forceinline__ bool rec_less(double c0, uint32_t o0, uint32_t s0, double c1, uint32_t o1, uint32_t s1) {
+    if (c0 < c1) return true;
+    if (c0 > c1) return false;
+    if (o0 != o1) return o0 < o1;
+    return s0 < s1;
+}
+
+struct DeviceOut {
+    MetisRecord *records;
+    long long capacity;
+    uint8_t *detail;
+    int detail_stride;
+    unsigned long long *counters;   // [0] records [1] partition calls [2] balancer runs [3] keyerrors [4] fatal key
+    MetisRecord *block_best;
+};
+
+struct DeviceSink {
+    const DeviceOut &o;
+    unsigned int n_part, n_run, n_key;
+    double best_cost;
+    uint32_t best_ord, best_step, best_meta;
+    __device__ DeviceSink(const DeviceOut &out)
+        : o(out), n_part(0), n_run(0), n_key(0), best_cost(INFINITY), best_ord(0xFFFFFFFFu), best_step(0xFFFFu),
+          best_meta(0) {}
+    __device__ void partition_call() { ++n_part; }
+    __device__ void balancer_run() { ++n_run; }
+    __device__ void keyerror() { ++n_key; }
+    __device__ void fatal(uint32_t ordinal, int code, uint32_t aux) {
+        const unsigned long long key = ((unsigned long long)ordinal << 32) | ((unsigned long long)(code & 0xFF) << 24) |
+                                       (unsigned long long)(((aux >> 16) & 0xFF) << 16) | (aux & 0xFFFF);
+        atomicMin(&o.counters[4], key);
+    }
+    __device__ void emit(const PlanDesc &pd, int step, int nrep, double cost, const uint8_t *tpc, const uint16_t *part) {
+        const unsigned long long slot = atomicAdd(&o.counters[0], 1ULL);
+        if ((long long)slot < o.capacity) {
+            MetisRecord r;
+            r.cost = cost; r.ordinal = pd.ordinal; r.step = (uint16_t)step;
+            r.num_repartition = (uint8_t)nrep; r.num_stage = (uint8_t)pd.S;
+            o.records[slot] = r;
+            if (o.detail) {
+                uint8_t *d = o.detail + (size_t)slot * o.detail_stride;
+                for (int s = 0; s < pd.S; ++s) { d[s] = (uint8_t)(pd.row[s] - tpc[s]); d[pd.S + s] = tpc[s]; }
+                for (int s = 0; s <= pd.S; ++s) d[2 * pd.S + s] = (uint8_t)part[s];
+            }
+        }
+        if (rec_less(cost, pd.ordinal, (uint32_t)step, best_cost, best_ord, best_step)) {
+            best_cost = cost; best_ord = pd.ordinal; best_step = (uint32_t)step;
+            best_meta = ((uint32_t)nrep << 8) | (uint32_t)pd.S;
+        }
+    }
+};
+
+template <int MAXS, int MAXL>
+__global__ void __launch_bounds__(kThreads)
+het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
+                  const MetisShard sh, const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob,
+                  const int use_smem, const __grid_constant__ DeviceOut out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    __shared__ double s_cost[kThreads / 32];
+    __shared__ uint32_t s_ord[kThreads / 32], s_step[kThreads / 32], s_meta[kThreads / 32];
+
+    const uint8_t *base = blob;
+    if (use_smem) {
+        stage_blob_tma(smem, blob, lay.total, &mbar);
+        base = smem;
+    }
+    const Tables T = make_tables(p, lay, base);
+
+    DeviceSink sink(out);
+    {
+        const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;          // plan index inside the shard
+        const long long ordinal = ((i / sh.tile) * sh.world + sh.rank) * sh.tile + (i % sh.tile);
+        PlanDesc pd;
+        if (decode_plan(sp, ordinal, pd)) {
+            Scratch<MAXS, MAXL> w;
+            PlanEvaluator<MAXS, MAXL> ev(T, w);
+            ev.run(pd, sink);
+        }
+    }
+
+    // counters: warp reduce, one atomic per warp
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned np = __reduce_add_sync(full, sink.n_part);
+    const unsigned nr = __reduce_add_sync(full, sink.n_run);
+    const unsigned nk = __reduce_add_sync(full, sink.n_key);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        if (np) atomicAdd(&out.counters[1], (unsigned long long)np);
+        if (nr) atomicAdd(&out.counters[2], (unsigned long long)nr);
+        if (nk) atomicAdd(&out.counters[3], (unsigned long long)nk);
+    }
+    // argmin (cost, ordinal, step): __shfl_sync butterfly inside the warp, then across warps
+    double c = sink.best_cost;
+    uint32_t o = sink.best_ord, st = sink.best_step, mt = sink.best_meta;
+    for (int d = 16; d > 0; d >>= 1) {
+        const double c2 = __shfl_xor_sync(full, c, d);
+        const uint32_t o2 = __shfl_xor_sync(full, o, d), s2 = __shfl_xor_sync(full, st, d),
+                       m2 = __shfl_xor_sync(full, mt, d);
+        if (rec_less(c2, o2, s2, c, o, st)) { c = c2; o = o2; st = s2; mt = m2; }
+    }
+    if (lane == 0) { s_cost[warp] = c; s_ord[warp] = o; s_step[warp] = st; s_meta[warp] = mt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int wi = 1; wi < kThreads / 32; ++wi)
+            if (rec_less(s_cost[wi], s_ord[wi], s_step[wi], c, o, st)) { c = s_cost[wi]; o = s_ord[wi]; st = s_step[wi]; mt = s_meta[wi]; }
+        MetisRecord r;
+        r.cost = c; r.ordinal = o; r.step = (uint16_t)st; r.num_repartition = (uint8_t)(mt >> 8); r.num_stage = (uint8_t)mt;
+        out.block_best[blockIdx.x] = r;
+    }
+}
+
+__global__ void het_finalize_kernel(const MetisRecord *block_best, int nblocks, const unsigned long long *counters,
+                                    MetisSearchSummary *summary) {
+    __shared__ double s_cost[32];
+    __shared__ uint32_t s_ord[32], s_step[32], s_meta[32];
+    double c = INFINITY;
+    uint32_t o = 0xFFFFFFFFu, st = 0xFFFFu, mt = 0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+        const MetisRecord r = block_best[i];
+        if (rec_less(r.cost, r.ordinal, r.step, c, o, st)) {
+            c = r.cost; o = r.ordinal; st = r.step; mt = ((uint32_t)r.num_repartition << 8) | r.num_stage;
+        }
+    }
+    const unsigned full = 0xFFFFFFFFu;
+    for (int d = 16; d > 0; d >>= 1) {
+        const double c2 = __shfl_xor_sync(full, c, d);
+        const uint32_t o2 = __shfl_xor_sync(full, o, d), s2 = __shfl_xor_sync(full, st, d),
+                       m2 = __shfl_xor_sync(full, mt, d);
+        if (rec_less(c2, o2, s2, c, o, st)) { c = c2; o = o2; st = s2; mt = m2; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_cost[warp] = c; s_ord[warp] = o; s_step[warp] = st; s_meta[warp] = mt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) / 32;
+        for (int wi = 1; wi < nw; ++wi)
+            if (rec_less(s_cost[wi], s_ord[wi], s_step[wi], c, o, st)) { c = s_cost[wi]; o = s_ord[wi]; st = s_step[wi]; mt = s_meta[wi]; }
+        MetisSearchSummary s;
+        memset(&s, 0, sizeof(s));
+        s.num_records = counters[0];
+        s.num_partition_calls = counters[1];
+        s.num_balancer_runs = counters[2];
+        s.num_keyerror = counters[3];
+        const unsigned long long fk = counters[4];
+        if (fk == 0xFFFFFFFFFFFFFFFFULL) { s.fatal_ordinal = 0xFFFFFFFFFFFFFFFFULL; s.fatal_code = 0; s.fatal_aux = 0; }
+        else { s.fatal_ordinal = fk >> 32; s.fatal_code = (uint32_t)((fk >> 24) & 0xFF); s.fatal_aux = (uint32_t)(fk & 0xFFFFFF); }
+        s.best.cost = c; s.best.ordinal = o; s.best.step = (uint16_t)st;
+        s.best.num_repartition = (uint8_t)(mt >> 8); s.best.num_stage = (uint8_t)mt;
+        *summary = s;
+    }
+}
+
+// replays single candidates: writes dp code, tp code, partition for (ordinal, step)
+struct DetailSink {
+    uint8_t *dst;
+    int want_step;
+    __device__ void partition_call() {}
+    __device__ void balancer_run() {}
+    __device__ void keyerror() {}
+    __device__ void fatal(uint32_t, int, uint32_t) {}
+    __device__ void emit(const PlanDesc &pd, int step, int, double, const uint8_t *tpc, const uint16_t *part) {
+        if (step != want_step) return;
+        for (int s = 0; s < pd.S; ++s) { dst[s] = (uint8_t)(pd.row[s] - tpc[s]); dst[pd.S + s] = tpc[s]; }
+        for (int s = 0; s <= pd.S; ++s) dst[2 * pd.S + s] = (uint8_t)part[s];
+    }
+};
+
+template <int MAXS, int MAXL>
+__global__ void __launch_bounds__(kThreads)
+het_detail_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
+                  const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob,
+                  const MetisRecord *__restrict__ picks, long long n, uint8_t *detail, int stride) {
+    const Tables T = make_tables(p, lay, blob);
+    const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    PlanDesc pd;
+    if (!decode_plan(sp, picks[i].ordinal, pd)) return;
+    DetailSink sink{detail + (size_t)i * stride, (int)picks[i].step};
+    Scratch<MAXS, MAXL> w;
+    PlanEvaluator<MAXS, MAXL> ev(T, w);
+    ev.run(pd, sink, (int)picks[i].step);
+}
+
+__global__ void __launch_bounds__(kThreads)
+homo_cost_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ BlobLayout lay,
+                 const uint8_t *__restrict__ blob, int type_id, const int32_t *__restrict__ plans, long long n,
+                 double *cost, int32_t *status) {
+    const Tables T = make_tables(p, lay, blob);
+    const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const int32_t *q = plans + i * 5;
+    double c = 0.0;
+    int oom = 0;
+    const int rc = homo_cost(T, type_id, q[0], q[1], q[2], q[3], q[4], c, oom);
+    cost[i] = rc ? NAN : c;
+    status[i] = rc ? 1 : (oom ? 2 : 0);
+}
+
+template <int MAXS, int MAXL>
+__global__ void __launch_bounds__(kThreads)
+layer_balance_kernel(const double *__restrict__ capa, const int32_t *__restrict__ num_stage, long long n, int stride,
+                     const double *__restrict__ lc, const double *__restrict__ dlay, int norm_len, int num_layers,
+                     uint16_t *partition) {
+    const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    Tables T;
+    memset(&T, 0, sizeof(T));
+    T.p.num_layers = num_layers;
+    T.p.norm_len = norm_len;
+    T.norm_lc = lc;
+    T.dlay = dlay;
+    Scratch<MAXS, MAXL> w;
+    const int S = num_stage[i];
+    uint16_t *out = partition + i * (stride + 1);
+    if (S < 1 || S > MAXS || num_layers > MAXL) { out[0] = 0xFFFF; return; }
+    for (int s = 0; s < S; ++s) w.perf[s] = capa[i * stride + s];
+    const int rc = balance_run<MAXS, MAXL>(T, S, w);
+    if (rc) { out[0] = 0xFFFF; return; }
+    for (int s = 0; s <= S; ++s) out[s] = w.part[s];
+}
+
+__global__ void divide_by_seven_kernel(const double *lc, int n, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lc[i] / 7.0;
+}
+
+static int check_problem(const MetisProblem *p) {
+    if (!p) return arg_fail("problem is NULL");
+    if (p->num_types < 1 || p->num_types > METIS_MAX_TYPES) return arg_fail("num_types out of range");
+    if (p->num_layers < 1 || p->num_layers > METIS_MAX_LAYERS) return arg_fail("num_layers out of range (METIS_MAX_LAYERS)");
+    if (p->lpad < p->num_layers) return arg_fail("lpad < num_layers");
+    if (p->num_keys < 1 || p->num_tp < 1 || p->num_bs < 1 || p->norm_len < 1) return arg_fail("empty profile tables");
+    if (p->devices_per_node < 1 || p->total_devices < 1) return arg_fail("empty cluster");
+    return METIS_OK;
+}
+
+}  // namespace metis
+
+using namespace metis;
+
+extern "C" {
+
+const char *metis_last_error(void) { return g_err; }
+int metis_abi_version(void) { return METIS_ABI_VERSION; }
+
+static int64_t shard_plan_slots(int64_t num_plans, const MetisShard *sh) {
+    const int64_t tile = sh->tile, world = sh->world;
+    const int64_t rounds = (num_plans + tile * world - 1) / (tile * world);
+    return rounds * tile;
+}
+
+int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans) {
+    if (check_problem(problem)) return METIS_E_ARG;
+    const BlobLayout lay = make_layout(*problem);
+    const int64_t nblocks = (num_plans + kThreads - 1) / kThreads + 64;
+    return 4096 + (int64_t)align16(lay.total) + nblocks * (int64_t)sizeof(MetisRecord) + 256;
+}
+
+struct Workspace {
+    MetisSearchSummary *summary;
+    unsigned long long *counters;
+    uint8_t *blob;
+    MetisRecord *block_best;
+};
+
+static Workspace carve(void *ws, const BlobLayout &lay) {
+    uint8_t *b = static_cast<uint8_t *>(ws);
+    uintptr_t a = (reinterpret_cast<uintptr_t>(b) + 127) & ~(uintptr_t)127;
+    b = reinterpret_cast<uint8_t *>(a);
+    Workspace w;
+    w.summary = reinterpret_cast<MetisSearchSummary *>(b);
+    w.counters = reinterpret_cast<unsigned long long *>(b + 1024);
+    w.blob = b + 2048;
+    w.block_best = reinterpret_cast<MetisRecord *>(b + 2048 + align16(lay.total));
+    return w;
+}
+
+int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, const MetisShard *shard,
+                     MetisRecord *records, int64_t capacity, uint8_t *detail, int32_t detail_stride,
+                     void *workspace, int64_t workspace_bytes, MetisSearchSummary *summary, void *stream_) {
+    int rc = check_problem(problem);
+    if (rc) return rc;
+    if (!space || !shard || !workspace || !summary) return arg_fail("NULL argument");
+    if (shard->world < 1 || shard->rank < 0 || shard->rank >= shard->world || shard->tile < 32 || shard->tile % 32)
+        return arg_fail("bad shard (tile must be a positive multiple of 32)");
+    if (space->num_plans > 0xFFFFFFF0LL) return arg_fail("more than 2^32 plans");
+    if (detail && detail_stride < 3 * METIS_MAX_STAGES + 1) return arg_fail("detail_stride too small");
+    if (capacity < 0 || (capacity > 0 && !records)) return arg_fail("records/capacity mismatch");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const BlobLayout lay = make_layout(*problem);
+    const int64_t slots = shard_plan_slots(space->num_plans, shard);
+    const int64_t nblocks = (slots + kThreads - 1) / kThreads;
+    const int64_t need = 4096 + (int64_t)align16(lay.total) + (nblocks + 1) * (int64_t)sizeof(MetisRecord);
+    if (workspace_bytes < need) { snprintf(g_err, sizeof(g_err), "workspace too small: need %lld", (long long)need); return METIS_E_CAPACITY; }
+    if (nblocks > 0x7FFFFFFFLL) return arg_fail("too many blocks");
+    const Workspace ws = carve(workspace, lay);
+
+    cudaError_t e;
+    e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "memset counters");
+    e = cudaMemsetAsync(ws.counters + 4, 0xFF, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "memset fatal key");
+    pack_tables_kernel<<<8, 256, 0, stream>>>(*problem, lay, ws.blob);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "pack_tables_kernel");
+
+    const int use_smem = lay.total <= (uint32_t)kSmemBlobMax;
+    const size_t dyn = use_smem ? lay.total : 0;
+    auto kern = het_search_kernel<kMaxS, kMaxL>;
+    if (dyn > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    }
+    DeviceOut out;
+    out.records = records; out.capacity = capacity; out.detail = detail; out.detail_stride = detail_stride;
+    out.counters = ws.counters; out.block_best = ws.block_best;
+    if (nblocks > 0) {
+        kern<<<(unsigned)nblocks, kThreads, dyn, stream>>>(*problem, *space, *shard, lay, ws.blob, use_smem, out);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "het_search_kernel");
+    }
+    het_finalize_kernel<<<1, 256, 0, stream>>>(ws.block_best, (int)nblocks, ws.counters, ws.summary);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "het_finalize_kernel");
+    e = cudaMemcpyAsync(summary, ws.summary, sizeof(MetisSearchSummary), cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "copy summary");
+    return METIS_OK;
+}
+
+int metis_het_detail(const MetisProblem *problem, const MetisPlanSpace *space, const MetisRecord *picks, int64_t n,
+                     uint8_t *detail, int32_t detail_stride, void *workspace, int64_t workspace_bytes, void *stream_) {
+    int rc = check_problem(problem);
+    if (rc) return rc;
+    if (!space || !picks || !detail || !workspace) return arg_fail("NULL argument");
+    if (detail_stride < 3 * METIS_MAX_STAGES + 1) return arg_fail("detail_stride too small");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const BlobLayout lay = make_layout(*problem);
+    if (workspace_bytes < 4096 + (int64_t)align16(lay.total)) return METIS_E_CAPACITY;
+    const Workspace ws = carve(workspace, lay);
+    pack_tables_kernel<<<8, 256, 0, stream>>>(*problem, lay, ws.blob);
+    if (n > 0) {
+        const unsigned nb = (unsigned)((n + kThreads - 1) / kThreads);
+        het_detail_kernel<kMaxS, kMaxL><<<nb, kThreads, 0, stream>>>(*problem, *space, lay, ws.blob, picks, n, detail,
+                                                                     detail_stride);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "het_detail_kernel");
+    return METIS_OK;
+}
+
+int metis_homo_cost(const MetisProblem *problem, int32_t type_id, const int32_t *plans, int64_t n, double *cost,
+                    int32_t *status, void *workspace, int64_t workspace_bytes, void *stream_) {
+    int rc = check_problem(problem);
+    if (rc) return rc;
+    if (!plans || !cost || !status || !workspace) return arg_fail("NULL argument");
+    if (type_id < 0 || type_id >= problem->num_types) return arg_fail("type_id out of range");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const BlobLayout lay = make_layout(*problem);
+    if (workspace_bytes < 4096 + (int64_t)align16(lay.total)) return METIS_E_CAPACITY;
+    const Workspace ws = carve(workspace, lay);
+    pack_tables_kernel<<<8, 256, 0, stream>>>(*problem, lay, ws.blob);
+    if (n > 0) {
+        const unsigned nb = (unsigned)((n + kThreads - 1) / kThreads);
+        homo_cost_kernel<<<nb, kThreads, 0, stream>>>(*problem, lay, ws.blob, type_id, plans, n, cost, status);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "homo_cost_kernel");
+    return METIS_OK;
+}
+
+int metis_layer_balance(const double *capa, const int32_t *num_stage, int64_t n, int32_t stride, const double *lc,
+                        int32_t norm_len, int32_t num_layers, uint16_t *partition, void *workspace,
+                        int64_t workspace_bytes, void *stream_) {
+    if (!capa || !num_stage || !lc || !partition || !workspace) return arg_fail("NULL argument");
+    if (stride < 1 || stride > METIS_MAX_STAGES) return arg_fail("stride out of range");
+    if (num_layers < 1 || num_layers > METIS_MAX_LAYERS || norm_len < 1) return arg_fail("layers out of range");
+    if (workspace_bytes < (int64_t)norm_len * 8 + 256) return METIS_E_CAPACITY;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    double *dlay = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(workspace) + 127) & ~(uintptr_t)127);
+    divide_by_seven_kernel<<<(norm_len + 127) / 128, 128, 0, stream>>>(lc, norm_len, dlay);
+    if (n > 0) {
+        const unsigned nb = (unsigned)((n + kThreads - 1) / kThreads);
+        layer_balance_kernel<kMaxS, kMaxL><<<nb, kThreads, 0, stream>>>(capa, num_stage, n, stride, lc, dlay, norm_len,
+                                                                        num_layers, partition);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "layer_balance_kernel");
+    return METIS_OK;
+}
+
+}  // extern "C"

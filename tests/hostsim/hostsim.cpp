@@ -1,0 +1,158 @@
+// hostsim.cpp - TEST-ONLY host build of the device evaluator (metis_b200/csrc/metis_eval.cuh).
+//
+// The build container has nvcc but no GPU.  Compiling the very same per-plan evaluator with
+// g++ lets the CPU test-suite check the *device logic* (compact load-balancer state, chain,
+// cost model) against the oracle before spending GPU time.  This shim is built and loaded only
+// by tests/ (tests/hostsim_util.py); the metis_b200 package never loads it and has no CPU path.
+// Build: g++ -O2 -ffp-contract=off -shared -fPIC (no FMA contraction, like nvcc -fmad=false).
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../metis_b200/csrc/metis_eval.cuh"
+
+using namespace metis;
+
+namespace {
+
+Tables host_tables(const MetisProblem &p, std::vector<double> &dlay) {
+    Tables T;
+    T.p = p;
+    T.key_index = p.key_index;
+    T.lc = p.layer_compute;
+    T.mem = p.layer_memory;
+    T.exec_full = p.exec_full;
+    T.fb_sync = p.fb_sync;
+    T.norm_lc = p.norm_lc;
+    dlay.resize(p.norm_len);
+    for (int r = 0; r < p.norm_len; ++r) dlay[r] = p.norm_lc[r] / 7.0;
+    T.dlay = dlay.data();
+    T.type_memory = p.type_memory;
+    T.bw_first = p.type_bw_first;
+    T.bw_min = p.type_bw_min;
+    T.run_type = p.ns_run_type;
+    T.run_end = p.ns_run_end;
+    return T;
+}
+
+bool decode(const MetisPlanSpace &sp, int64_t ordinal, PlanDesc &pd) {
+    if (ordinal < 0 || ordinal >= sp.num_plans) return false;
+    int b = 0;
+    for (int i = 0; i < sp.num_blocks; ++i)
+        if (sp.blocks[i].first_ordinal <= ordinal) b = i;
+    const MetisPlanBlock &blk = sp.blocks[b];
+    const int64_t rel = ordinal - blk.first_ordinal;
+    const int64_t row = rel / sp.num_div;
+    pd.ordinal = (uint32_t)ordinal;
+    pd.ns = blk.ns_idx;
+    pd.S = blk.num_stage;
+    pd.label = blk.label_stage;
+    pd.batches = sp.batches[rel - row * sp.num_div];
+    pd.row = sp.rows + blk.rows_offset + row * blk.num_stage;
+    return true;
+}
+
+struct HostSink {
+    MetisRecord *records;
+    int64_t capacity;
+    uint8_t *detail;
+    int stride;
+    MetisSearchSummary *sum;
+    void partition_call() { ++sum->num_partition_calls; }
+    void balancer_run() { ++sum->num_balancer_runs; }
+    void keyerror() { ++sum->num_keyerror; }
+    void fatal(uint32_t ordinal, int code, uint32_t aux) {
+        if ((uint64_t)ordinal < sum->fatal_ordinal) {
+            sum->fatal_ordinal = ordinal;
+            sum->fatal_code = (uint32_t)code;
+            sum->fatal_aux = aux;
+        }
+    }
+    void emit(const PlanDesc &pd, int step, int nrep, double cost, const uint8_t *tpc, const uint16_t *part) {
+        const int64_t slot = (int64_t)sum->num_records++;
+        if (slot < capacity) {
+            MetisRecord r;
+            r.cost = cost; r.ordinal = pd.ordinal; r.step = (uint16_t)step;
+            r.num_repartition = (uint8_t)nrep; r.num_stage = (uint8_t)pd.S;
+            records[slot] = r;
+            if (detail) {
+                uint8_t *d = detail + (size_t)slot * stride;
+                for (int s = 0; s < pd.S; ++s) { d[s] = (uint8_t)(pd.row[s] - tpc[s]); d[pd.S + s] = tpc[s]; }
+                for (int s = 0; s <= pd.S; ++s) d[2 * pd.S + s] = (uint8_t)part[s];
+            }
+        }
+        MetisRecord &b = sum->best;
+        if (cost < b.cost || (cost == b.cost && (pd.ordinal < b.ordinal || (pd.ordinal == b.ordinal && step < b.step)))) {
+            b.cost = cost; b.ordinal = pd.ordinal; b.step = (uint16_t)step;
+            b.num_repartition = (uint8_t)nrep; b.num_stage = (uint8_t)pd.S;
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const MetisShard *sh, MetisRecord *records,
+                       int64_t capacity, uint8_t *detail, int32_t stride, MetisSearchSummary *summary) {
+    std::vector<double> dlay;
+    const Tables T = host_tables(*p, dlay);
+    memset(summary, 0, sizeof(*summary));
+    summary->fatal_ordinal = ~0ULL;
+    summary->best.cost = INFINITY;
+    summary->best.ordinal = 0xFFFFFFFFu;
+    summary->best.step = 0xFFFF;
+    HostSink sink{records, capacity, detail, stride, summary};
+    static thread_local Scratch<METIS_MAX_STAGES, METIS_MAX_LAYERS> w;
+    const int64_t tile = sh->tile, world = sh->world;
+    const int64_t rounds = (sp->num_plans + tile * world - 1) / (tile * world);
+    for (int64_t i = 0; i < rounds * tile; ++i) {
+        const int64_t ordinal = ((i / tile) * world + sh->rank) * tile + (i % tile);
+        PlanDesc pd;
+        if (!decode(*sp, ordinal, pd)) continue;
+        PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> ev(T, w);
+        ev.run(pd, sink);
+    }
+    return 0;
+}
+
+int hostsim_homo_cost(const MetisProblem *p, int32_t type_id, const int32_t *plans, int64_t n, double *cost,
+                      int32_t *status) {
+    std::vector<double> dlay;
+    const Tables T = host_tables(*p, dlay);
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t *q = plans + i * 5;
+        double c = 0.0;
+        int oom = 0;
+        const int rc = homo_cost(T, type_id, q[0], q[1], q[2], q[3], q[4], c, oom);
+        cost[i] = rc ? NAN : c;
+        status[i] = rc ? 1 : (oom ? 2 : 0);
+    }
+    return 0;
+}
+
+int hostsim_layer_balance(const double *capa, const int32_t *num_stage, int64_t n, int32_t stride, const double *lc,
+                          int32_t norm_len, int32_t num_layers, uint16_t *partition) {
+    std::vector<double> dlay(norm_len);
+    for (int r = 0; r < norm_len; ++r) dlay[r] = lc[r] / 7.0;
+    Tables T;
+    memset(&T, 0, sizeof(T));
+    T.p.num_layers = num_layers;
+    T.p.norm_len = norm_len;
+    T.norm_lc = lc;
+    T.dlay = dlay.data();
+    static thread_local Scratch<METIS_MAX_STAGES, METIS_MAX_LAYERS> w;
+    for (int64_t i = 0; i < n; ++i) {
+        const int S = num_stage[i];
+        uint16_t *out = partition + i * (stride + 1);
+        for (int s = 0; s < S; ++s) w.perf[s] = capa[i * stride + s];
+        const int rc = balance_run<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, S, w);
+        if (rc) { out[0] = 0xFFFF; continue; }
+        for (int s = 0; s <= S; ++s) out[s] = w.part[s];
+    }
+    return 0;
+}
+
+}  // extern "C"

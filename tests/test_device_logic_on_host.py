@@ -1,0 +1,114 @@
+"""CPU checks of the device evaluator's *logic* (tests/hostsim = g++ build of
+metis_b200/csrc/metis_eval.cuh) plus the host flattening / C++ enumerator, against the golden
+files produced by the unmodified reference.  The GPU parity tests proper are in
+test_gpu_parity.py (-m gpu); this file exists because the build container has no GPU.
+"""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+import hostsim_util as hs
+from conftest import C1_DIR, GOLDEN, golden_rows, load_golden
+from metis_b200 import flatten, native
+
+
+def _lib_or_skip():
+    try:
+        return native.load_library()
+    except native.MetisNativeError as e:
+        pytest.skip(str(e))
+
+
+def _search(meta, root, profile_sub, num_layers, hidden, seq, vocab, gbs, variance, mpl, max_tp, max_bs,
+            **kw):
+    lib = _lib_or_skip()
+    cluster, profile, _types, cfg = hs.load_inputs(root, profile_sub, meta['file_order'], num_layers, hidden, seq, vocab)
+    seqs = [tuple(s) for s in meta['node_sequences']]
+    problem = flatten.build_problem(profile, cluster, cfg, gbs, max_tp, max_bs, seqs)
+    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), gbs, num_layers, variance, mpl, lib)
+    return problem, space, hs.host_het_search(problem, space, **kw)
+
+
+def _compare(cands, gold):
+    assert len(cands) == len(gold)
+    for c, g in zip(cands, gold):
+        assert c[:8] == g[:8], (c, g)
+        assert c[8] == g[8], (c[0], c[1], c[8].hex(), g[8].hex())
+
+
+def test_c1_het():
+    meta, arr = load_golden('c1_het')
+    problem, space, (rec, det, summary) = _search(meta, C1_DIR, 'profile_data_samples', 10, 4096, 1024, 51200,
+                                                  128, 1, 4, 4, 4)
+    assert space.num_plans == meta['counters']['A'] == 32
+    assert summary.num_records == 19 and summary.num_partition_calls == meta['counters']['B']
+    _compare(hs.unpack_candidates(rec, det, space), golden_rows(arr))
+    assert summary.best.cost == 621.8881853975784 and summary.best.ordinal == 7
+
+
+@pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight'])
+def test_synthetic(name, workload_dir):
+    meta, arr = load_golden(name)
+    w, root, _ = workload_dir(name)
+    problem, space, (rec, det, summary) = _search(meta, root, 'profile', w.num_layers, w.hidden_size,
+                                                  w.sequence_length, w.vocab_size, w.gbs, w.variance,
+                                                  w.max_permute_len, w.max_tp, w.max_bs)
+    c = meta['counters']
+    assert space.num_plans == c['A']
+    assert (summary.num_partition_calls, summary.num_balancer_runs, summary.num_records) == (c['B'], c['runs'], c['C'])
+    assert summary.fatal_ordinal == 2 ** 64 - 1
+    gold = golden_rows(arr)
+    _compare(hs.unpack_candidates(rec, det, space), gold)
+    best = min(gold, key=lambda g: (g[8], g[0], g[1]))
+    assert (summary.best.cost, summary.best.ordinal, summary.best.step) == (best[8], best[0], best[1])
+
+
+def test_sharded_union_equals_whole(workload_dir):
+    meta, arr = load_golden('c2_v100')
+    w, root, _ = workload_dir('c2_v100')
+    got = []
+    for rank in range(3):
+        problem, space, (rec, det, _s) = _search(meta, root, 'profile', w.num_layers, w.hidden_size,
+                                                 w.sequence_length, w.vocab_size, w.gbs, w.variance,
+                                                 w.max_permute_len, w.max_tp, w.max_bs, rank=rank, world=3, tile=64)
+        got += hs.unpack_candidates(rec, det, space)
+    got.sort(key=lambda c: (c[0], c[1]))
+    _compare(got, golden_rows(arr))
+
+
+def test_fatal_keyerror(workload_dir):
+    meta, _ = load_golden('fatal_gbs96')
+    w, root, _ = workload_dir('fatal_gbs96')
+    _, _, (_rec, _det, summary) = _search(meta, root, 'profile', w.num_layers, w.hidden_size, w.sequence_length,
+                                          w.vocab_size, w.gbs, w.variance, w.max_permute_len, w.max_tp, w.max_bs)
+    assert summary.fatal_ordinal == meta['fatal'][0]
+    assert summary.fatal_code == 1 and summary.fatal_aux == (0 << 16 | 3)     # 'tp1_bs3'
+
+
+@pytest.fixture(scope='module')
+def units():
+    with gzip.open(os.path.join(GOLDEN, 'units.json.gz'), 'rt') as fh:
+        return json.load(fh)
+
+
+def test_units_enumerator(units):
+    lib = _lib_or_skip()
+    for case in units['device_groups']:
+        rows = flatten.enumerate_device_groups(case['stages'], case['ndev'], case['variance'], case['mpl'], lib)
+        want = np.array(case['rows'], dtype=np.int64).reshape(-1, case['stages'])
+        assert rows.shape == want.shape, case
+        assert ((1 << rows.astype(np.int64)) == want).all(), case
+
+
+def test_units_balancer(units):
+    by_l = {}
+    for case in units['balancer']:
+        by_l.setdefault((case['L'], tuple(case['lc'])), []).append(case)
+    for (L, lc_hex), cases in by_l.items():
+        lc = [float.fromhex(x) for x in lc_hex]
+        got = hs.host_layer_balance([[float.fromhex(x) for x in c['capa']] for c in cases], lc, L)
+        for g, c in zip(got, cases):
+            assert g == c['part'], c

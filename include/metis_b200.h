@@ -154,6 +154,13 @@ typedef struct MetisShard {
 const char *metis_last_error(void);
 int metis_abi_version(void);
 
+/*
+ * Optional: CUDA events (cudaEvent_t as void*) that the NEXT metis_het_search call on this host
+ * thread records immediately before and after its search kernel, so a caller can time that kernel
+ * alone on the launching stream.  Pass NULLs to clear.
+ */
+void metis_set_profile_events(void *before_kernel, void *after_kernel);
+
 /* Bytes of device scratch the calls below need for `num_plans` plans (workspace argument);
  * metis_het_detail / metis_homo_cost need metis_het_workspace_bytes(problem, 0). */
 int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans);

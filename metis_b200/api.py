@@ -1,0 +1,251 @@
+"""Host-side mirror of the reference's interface for the plan-search path.
+
+Same class / function names, argument meaning and error behaviour as the reference, so that
+``cost_het_cluster.py`` / ``cost_homo_cluster.py`` read like the originals; the objects are thin
+holders of inputs - every evaluation happens on the GPU (metis_b200.search).
+
+  reference symbol                                   here
+  -------------------------------------------------  -------------------------------------------
+  model/activation_parameter.py GPTActivationAndParam  GPTActivationAndParam
+  model/cost_estimator.py HeteroCostEstimator           HeteroCostEstimator   (holder)
+  model/cost_estimator.py HomoCostEstimator             HomoCostEstimator     (holder)
+  model/load_balancer.py LayerLoadBalancer              LayerLoadBalancer     (holder + norm_layer_duration)
+  search_space/plan.py UniformPlan / InterStagePlan     same dataclasses
+  search_space/plan.py UniformPlanGenerator             UniformPlanGenerator  (host iterator)
+  search_space/plan.py InterStagePlanGenerator          InterStagePlanGenerator (iterator over the plan space)
+  cost_het_cluster.py cost_het_cluster()                cost_het_cluster()    -> GPU
+  cost_homo_cluster.py cost_homo_cluster()              cost_homo_cluster()   -> GPU
+"""
+from __future__ import annotations
+
+import argparse
+import time
+from dataclasses import dataclass
+from itertools import permutations
+from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import flatten, native
+from .utils import DeviceType, ModelConfig
+
+
+@dataclass
+class UniformPlan:
+    dp: int
+    pp: int
+    tp: int
+    mbs: int
+    gbs: int
+
+
+@dataclass
+class InterStagePlan:
+    ns_idx: int
+    node_sequence: List[DeviceType]
+    dg_idx: int
+    device_groups: List[int]
+    num_stage: int
+    batches: int
+    gbs: int
+
+
+class GPTActivationAndParam:
+    """model/activation_parameter.py:5-51 (only the three per-layer sizes reach the kernels)."""
+
+    def __init__(self, model_config: ModelConfig, model_params):
+        self.hidden_size = model_config.hidden_size
+        self.sequence_length = model_config.sequence_length
+        self.num_layers = model_config.num_layers
+        self.vocab_size = model_config.vocab_size
+        self.attention_head_size = model_config.attention_head_size
+        self.input_params = float(model_params[0])
+        self.output_params = float(model_params[-1])
+        self.transformer_params = float(model_params[1])
+
+    def get_num_layers(self):
+        return self.num_layers
+
+
+class _Estimator:
+    def __init__(self, profile_data: Dict, model_config: ModelConfig, model_volume, gpu_cluster):
+        self.profile_data = profile_data
+        self.model_config = model_config
+        self.model_volume = model_volume
+        self.gpu_cluster = gpu_cluster
+
+
+class HeteroCostEstimator(_Estimator):
+    """Inputs of model/cost_estimator.py:141-244; evaluated by het_search_kernel."""
+
+
+class HomoCostEstimator(_Estimator):
+    """Inputs of model/cost_estimator.py:83-138; evaluated by homo_cost_kernel."""
+
+
+class LayerLoadBalancer:
+    """Inputs of model/load_balancer.py:14-144; ``norm_layer_duration`` is computed at construction
+    like the reference (:20-27) and raises the same KeyError when tp1_bs1 is not profiled."""
+
+    def __init__(self, gpu_cluster, profile_data: Dict, model_config, gbs: int):
+        self.gpu_cluster = gpu_cluster
+        self.profile_data = profile_data
+        self.model_config = model_config
+        self.gbs = gbs
+        self.norm_layer_duration = flatten.norm_layer_duration(profile_data)
+
+
+class UniformPlanGenerator:
+    """search_space/plan.py:40-97; like the reference it re-yields ONE mutated object."""
+
+    def __init__(self, num_devices: int, max_tp: int, max_gbs: int):
+        self.num_devices = num_devices
+        self.max_tp = max_tp
+        self.max_gbs = max_gbs
+        self.curr = UniformPlan(dp=num_devices, pp=1, tp=1, gbs=num_devices, mbs=0)
+
+    def __iter__(self):
+        return self
+
+    def _advance_parallelism(self) -> bool:
+        p = self.curr
+        while True:
+            if p.tp == self.max_tp and p.pp == self.num_devices:
+                return False
+            if p.tp == self.max_tp:
+                p.pp += 1
+                p.dp = self.num_devices // p.pp
+                p.tp = self.num_devices // p.dp // p.pp
+            else:
+                p.tp += 1
+                p.dp = self.num_devices // p.tp // p.pp
+            if p.dp * p.pp * p.tp == self.num_devices:
+                return True
+
+    def __next__(self) -> UniformPlan:
+        p = self.curr
+        p.mbs += 1
+        while p.gbs % p.mbs > 0 and p.mbs <= p.gbs:
+            p.mbs += 1
+        if p.mbs * p.dp > p.gbs:
+            p.mbs = 1
+            p.gbs += 1
+            while self.max_gbs % p.gbs > 0 and p.gbs <= self.max_gbs:
+                p.gbs += 1
+        if p.gbs > self.max_gbs:
+            p.mbs = 1
+            if not self._advance_parallelism():
+                raise StopIteration
+            p.gbs = p.dp
+        return p
+
+
+class InterStagePlanGenerator:
+    """search_space/plan.py:100-175 as an iterator over the enumerated plan space (quirk Q1 included).
+    Each item is a fresh InterStagePlan (the reference mutates one object)."""
+
+    def __init__(self, device_types: set, num_devices: int, gbs: int, num_layers: int, variance: float = 0.5,
+                 max_permute_len: int = 4):
+        self.node_sequences = list(permutations(device_types))
+        self.gbs = gbs
+        self.space = flatten.build_plan_space(len(self.node_sequences), num_devices, gbs, num_layers, variance,
+                                              max_permute_len)
+
+    def __iter__(self) -> Iterator[InterStagePlan]:
+        for ordinal in range(self.space.num_plans):
+            ns, label, row, batches, codes = self.space.locate(ordinal)
+            yield InterStagePlan(ns_idx=ns, node_sequence=self.node_sequences[ns], dg_idx=row,
+                                 device_groups=[1 << int(c) for c in codes], num_stage=label, batches=batches,
+                                 gbs=self.gbs)
+
+
+class HetSearchResult(list):
+    """List of the reference's 7-tuples plus the counters of the run."""
+    summary: Dict[str, int]
+    timings: Dict[str, float]
+
+
+def het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer=None,
+                node_sequences: Optional[Sequence[Sequence]] = None):
+    """Flatten the inputs of cost_het_cluster() (order of ``set(device_types)`` = quirk Q4)."""
+    if node_sequences is None:
+        node_sequences = list(permutations(set(gpu_cluster.get_device_types())))
+    norm = layer_load_balancer.norm_layer_duration if layer_load_balancer is not None else None
+    problem = flatten.build_problem(profile_data, gpu_cluster, model_config, args.gbs,
+                                    args.max_profiled_tp_degree, args.max_profiled_batch_size, node_sequences,
+                                    norm)
+    space = flatten.build_plan_space(len(node_sequences), gpu_cluster.get_total_num_devices(), args.gbs,
+                                     args.num_layers, args.min_group_scale_variance, args.max_permute_len)
+    return problem, space, [tuple(s) for s in node_sequences]
+
+
+def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, model_config: ModelConfig,
+                     cost_estimator: HeteroCostEstimator, layer_load_balancer: LayerLoadBalancer,
+                     node_sequences: Optional[Sequence[Sequence]] = None, device=None) -> HetSearchResult:
+    """cost_het_cluster.py:21-50 on the GPU.  Returns the same list of
+    (node_sequence, device_groups, strategies, batches, layer_partition, num_repartition, cost) in the
+    same order.  With torch.distributed initialised the plans are sharded over the ranks and every
+    rank returns the full list."""
+    import torch
+    from . import search
+    t0 = time.perf_counter()
+    problem, space, seqs = het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer,
+                                       node_sequences)
+    t1 = time.perf_counter()
+    dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    dp = search.DeviceProblem(problem, space, device)
+    searcher = search.HetSearcher(dp, rank, world, want_records=True, want_detail=True)
+    out = searcher.run()
+    summary, records, detail = out.summary, out.records, out.detail
+    if dist:
+        summary = search.global_counters(summary, dp.device)
+        summary['fatal_ordinal'] = summary['global_fatal_ordinal'] if summary['global_fatal_ordinal'] < 2 ** 62 \
+            else 2 ** 64 - 1
+        gathered: List = [None] * world
+        dist.all_gather_object(gathered, (records, detail, out.summary['fatal_code'], out.summary['fatal_aux'],
+                                          out.summary['fatal_ordinal']))
+        records = np.concatenate([g[0] for g in gathered])
+        detail = np.concatenate([g[1] for g in gathered])
+        order = np.lexsort((records['step'], records['ordinal']))
+        records, detail = records[order], detail[order]
+        for g in gathered:
+            if g[4] == summary['fatal_ordinal']:
+                summary['fatal_code'], summary['fatal_aux'] = g[2], g[3]
+    if summary['fatal_ordinal'] != 2 ** 64 - 1:
+        # the reference dies at that plan: nothing is returned (quirk Q8)
+        search.raise_fatal(summary, problem)
+    t2 = time.perf_counter()
+    result = HetSearchResult(search.materialize(records, detail, space, seqs))
+    result.summary = dict(summary, num_plans=space.num_plans)
+    result.timings = {'flatten_enumerate_s': t1 - t0, 'gpu_search_s': t2 - t1,
+                      'materialize_s': time.perf_counter() - t2}
+    return result
+
+
+def cost_homo_cluster(args: argparse.Namespace, gpu_cluster, cost_estimator: HomoCostEstimator,
+                      device_type: Optional[str] = None, device=None) -> List[Tuple[UniformPlan, float]]:
+    """cost_homo_cluster.py:21-37 on the GPU: every gbs-matching UniformPlan is costed by
+    homo_cost_kernel; plans whose profile key is missing are skipped like ``except KeyError``."""
+    from copy import copy
+    from . import search
+    profile_data = cost_estimator.profile_data
+    if device_type is None:
+        device_type = next(k for k in profile_data if k.startswith('DeviceType.')).split('.', 1)[1]
+    for key in profile_data[f'DeviceType.{device_type}']:
+        tp = int(key[2:].split('_bs')[0])
+        if tp & (tp - 1):
+            raise NotImplementedError(f'profile key {key}: non power-of-two tp is not supported on the GPU path')
+    plans = [copy(p) for p in UniformPlanGenerator(num_devices=gpu_cluster.get_total_num_devices(),
+                                                   max_tp=args.max_profiled_tp_degree, max_gbs=args.gbs)
+             if p.gbs == args.gbs]
+    max_tp = max([p.tp for p in plans] + [1])
+    max_bs = max([p.mbs for p in plans] + [1])
+    cluster_types = [t.name for t in gpu_cluster.get_device_types()]
+    problem = flatten.build_problem(profile_data, gpu_cluster, cost_estimator.model_config, args.gbs,
+                                    max_tp, max_bs, [tuple(dict.fromkeys(cluster_types))])
+    if device_type not in problem.type_names:
+        raise KeyError(f'DeviceType.{device_type}')
+    table = np.array([[p.dp, p.pp, p.tp, p.mbs, p.gbs] for p in plans], dtype=np.int32).reshape(-1, 5)
+    cost, status = search.homo_costs(problem, problem.type_names.index(device_type), table, device)
+    return [(p, float(c)) for p, c, s in zip(plans, cost, status) if s != 1]

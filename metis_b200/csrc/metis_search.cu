@@ -26,6 +26,7 @@ constexpr int kMaxL = METIS_MAX_LAYERS;
 constexpr int kSmemBlobMax = 160 * 1024;
 
 static thread_local char g_err[256] = "";
+static thread_local cudaEvent_t g_ev_before = nullptr, g_ev_after = nullptr;
 
 static int cuda_fail(cudaError_t e, const char *what) {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -406,6 +407,10 @@ extern "C" {
 
 const char *metis_last_error(void) { return g_err; }
 int metis_abi_version(void) { return METIS_ABI_VERSION; }
+void metis_set_profile_events(void *before_kernel, void *after_kernel) {
+    g_ev_before = static_cast<cudaEvent_t>(before_kernel);
+    g_ev_after = static_cast<cudaEvent_t>(after_kernel);
+}
 
 static int64_t shard_plan_slots(int64_t num_plans, const MetisShard *sh) {
     const int64_t tile = sh->tile, world = sh->world;
@@ -479,8 +484,11 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     out.records = records; out.capacity = capacity; out.detail = detail; out.detail_stride = detail_stride;
     out.counters = ws.counters; out.block_best = ws.block_best;
     if (nblocks > 0) {
+        if (g_ev_before) cudaEventRecord(g_ev_before, stream);
         kern<<<(unsigned)nblocks, kThreads, dyn, stream>>>(*problem, *space, *shard, lay, ws.blob, use_smem, out);
         e = cudaGetLastError();
+        if (g_ev_after) cudaEventRecord(g_ev_after, stream);
+        g_ev_before = g_ev_after = nullptr;
         if (e != cudaSuccess) return cuda_fail(e, "het_search_kernel");
     }
     het_finalize_kernel<<<1, 256, 0, stream>>>(ws.block_best, (int)nblocks, ws.counters, ws.summary);

@@ -72,7 +72,7 @@ RECORD_DTYPE = [('cost', '<f8'), ('ordinal', '<u4'), ('step', '<u2'), ('num_repa
 BLOCK_DTYPE = [('first_ordinal', '<i8'), ('rows_offset', '<i8'), ('num_rows', '<i4'), ('ns_idx', '<i2'),
                ('label_stage', '<i2'), ('num_stage', '<i2'), ('reserved', '<i2', (3,))]
 
-SYMBOLS = ['metis_last_error', 'metis_abi_version', 'metis_het_workspace_bytes', 'metis_het_search',
+SYMBOLS = ['metis_last_error', 'metis_abi_version', 'metis_set_profile_events', 'metis_het_workspace_bytes', 'metis_het_search',
            'metis_het_detail', 'metis_homo_cost', 'metis_layer_balance', 'metis_enum_device_groups']
 
 _lib = None
@@ -94,6 +94,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib = C.CDLL(path)
     lib.metis_last_error.restype = C.c_char_p
     lib.metis_abi_version.restype = C.c_int
+    lib.metis_set_profile_events.restype = None
+    lib.metis_set_profile_events.argtypes = [C.c_void_p, C.c_void_p]
     lib.metis_het_workspace_bytes.restype = C.c_int64
     lib.metis_het_workspace_bytes.argtypes = [C.POINTER(MetisProblem), C.c_int64]
     lib.metis_het_search.restype = C.c_int

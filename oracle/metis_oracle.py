@@ -808,10 +808,72 @@ def het_cost(profile: Dict, cluster: OracleCluster, model: OracleModel, plan: di
     return exec_cost + fb_sync + max(upd) + max(dp_costs) + pp_cost + bg
 
 
+def het_evaluate_plan(profile: Dict, cluster: OracleCluster, model: OracleModel, norm_lc, plan: dict,
+                      ordinal: int, num_layers: int, max_tp: int, max_bs: int, counters: dict, out: list) -> None:
+    """Loop body of cost_het_cluster.py:31-48 for one inter-stage plan, with the
+    IntraStagePlanGenerator chain (search_space/plan.py:178-268) inlined."""
+    gbs = plan['gbs']
+    groups = plan['device_groups']
+    rank_types = rank_types_by_devices(cluster, plan['node_sequence'])
+    strategies: List[Tuple[int, int]] = []
+    mem_state = []
+    nrep = 0
+    step = 0
+    while True:
+        if nrep == 1:                                    # plan.py:194-195
+            break
+        found = False
+        while True:
+            if not strategies:                           # :198-201
+                strategies = [(g, 1) for g in groups]
+            else:
+                cur = list(strategies)
+                state = mem_state if mem_state else [1 / dp for dp, _ in strategies]   # :252-255
+                order = sorted(range(len(state)), key=lambda i: state[i])
+                nxt = None
+                for s in order:                          # :262-266
+                    dp, tp = cur[s]
+                    if dp != 1:
+                        cur[s] = (dp // 2, tp * 2)
+                        nxt = cur
+                        break
+                strategies = nxt
+            if not strategies:                           # :203-204
+                break
+            valid = True                                 # :238-249
+            for dp, tp in strategies:
+                mbs = gbs // dp // plan['batches']
+                if mbs == 0 or mbs > max_bs or tp > max_tp:
+                    valid = False
+                    break
+            if not valid:
+                continue
+            m_capa = stage_memory_capacity(cluster, rank_types, groups)
+            perf = stage_compute_performance(profile, rank_types, groups, strategies, gbs, plan['batches'])
+            counters['B'] += 1
+            part, n_rep, state = partition_layer(profile, cluster, norm_lc, num_layers, plan,
+                                                 strategies, perf, m_capa, counters)
+            mem_state = state
+            if part:                                     # :219-226
+                nrep = n_rep
+                found = True
+                break
+        if not found:
+            break
+        try:
+            cost = het_cost(profile, cluster, model, plan, strategies, part, rank_types, max_bs)
+            counters['C'] += 1
+            out.append((ordinal, step, plan['node_sequence'], list(groups), list(strategies),
+                        plan['batches'], list(part), nrep, cost))
+        except KeyError:
+            counters['keyerr'] += 1
+        step += 1
+
+
 def het_search(profile: Dict, cluster: OracleCluster, model: OracleModel, node_sequences, gbs: int,
                num_layers: int, variance, max_permute_len: int, max_tp: int, max_bs: int,
                plan_filter=None):
-    """cost_het_cluster.py:21-50 with the IntraStagePlanGenerator chain (plan.py:178-268) inlined.
+    """cost_het_cluster.py:21-50.
 
     Returns (candidates, counters); a candidate is
     (ordinal, step, node_sequence, device_groups, strategies, batches, partition, num_repartition, cost).
@@ -819,67 +881,14 @@ def het_search(profile: Dict, cluster: OracleCluster, model: OracleModel, node_s
     """
     norm_lc = norm_layer_duration(profile)
     counters = {'A': 0, 'B': 0, 'C': 0, 'runs': 0, 'keyerr': 0}
-    out = []
+    out: list = []
     for ordinal, plan in enumerate(inter_stage_plans(node_sequences, cluster.total_devices, gbs,
                                                      num_layers, variance, max_permute_len)):
         counters['A'] += 1
         if plan_filter is not None and not plan_filter(ordinal):
             continue
-        groups = plan['device_groups']
-        rank_types = rank_types_by_devices(cluster, plan['node_sequence'])
-        strategies: List[Tuple[int, int]] = []
-        mem_state = []
-        nrep = 0
-        step = 0
-        while True:
-            if nrep == 1:                                    # plan.py:194-195
-                break
-            found = False
-            while True:
-                if not strategies:                           # :198-201
-                    strategies = [(g, 1) for g in groups]
-                else:
-                    cur = list(strategies)
-                    state = mem_state if mem_state else [1 / dp for dp, _ in strategies]   # :252-255
-                    order = sorted(range(len(state)), key=lambda i: state[i])
-                    nxt = None
-                    for s in order:                          # :262-266
-                        dp, tp = cur[s]
-                        if dp != 1:
-                            cur[s] = (dp // 2, tp * 2)
-                            nxt = cur
-                            break
-                    strategies = nxt
-                if not strategies:                           # :203-204
-                    break
-                valid = True                                 # :238-249
-                for dp, tp in strategies:
-                    mbs = gbs // dp // plan['batches']
-                    if mbs == 0 or mbs > max_bs or tp > max_tp:
-                        valid = False
-                        break
-                if not valid:
-                    continue
-                m_capa = stage_memory_capacity(cluster, rank_types, groups)
-                perf = stage_compute_performance(profile, rank_types, groups, strategies, gbs, plan['batches'])
-                counters['B'] += 1
-                part, n_rep, state = partition_layer(profile, cluster, norm_lc, num_layers, plan,
-                                                     strategies, perf, m_capa, counters)
-                mem_state = state
-                if part:                                     # :219-226
-                    nrep = n_rep
-                    found = True
-                    break
-            if not found:
-                break
-            try:
-                cost = het_cost(profile, cluster, model, plan, strategies, part, rank_types, max_bs)
-                counters['C'] += 1
-                out.append((ordinal, step, plan['node_sequence'], list(groups), list(strategies),
-                            plan['batches'], list(part), nrep, cost))
-            except KeyError:
-                counters['keyerr'] += 1
-            step += 1
+        het_evaluate_plan(profile, cluster, model, norm_lc, plan, ordinal, num_layers, max_tp, max_bs,
+                          counters, out)
     return out, counters
 
 

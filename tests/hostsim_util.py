@@ -28,8 +28,10 @@ def hostsim():
                 os.path.join(HERE, '..', 'include', 'metis_b200.h')]
         if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
             os.makedirs(os.path.dirname(OUT), exist_ok=True)
+            tmp = f'{OUT}.{os.getpid()}.tmp'
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared',
-                                   '-o', OUT, SRC])
+                                   '-o', tmp, SRC])
+            os.replace(tmp, OUT)                             # atomic: concurrent test processes may race
         _lib = C.CDLL(OUT)
     return _lib
 

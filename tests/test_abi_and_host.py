@@ -170,6 +170,8 @@ def test_two_rank_reduction_gloo(tmp_path):
     """world_size 2 over gloo: each rank evaluates its interleaved shard, then the product's
     collective logic (search.global_best / global_counters) yields the golden winner and counters."""
     load_golden('c2_v100')
+    import hostsim_util
+    hostsim_util.hostsim()                      # build the test shim once, before the ranks start
     script = tmp_path / 'worker.py'
     script.write_text(WORKER)
     import socket

@@ -406,9 +406,10 @@ struct PlanEvaluator {
     MB_HD int dp_of(int s) const { return (1 << w.gcode[s]) >> w.tpc[s]; }
 
     // IntraStagePlanGenerator._is_valid_strategies (search_space/plan.py:238-249)
+    // gbs // dp // batches == (gbs // batches) >> log2(dp) because dp is a power of two.
     MB_HD bool valid() const {
         for (int s = 0; s < pd.S; ++s) {
-            const int mbs = T.p.gbs / dp_of(s) / pd.batches;
+            const int mbs = bs_total >> (w.gcode[s] - w.tpc[s]);
             if (mbs == 0 || mbs > T.p.max_bs) return false;
             if ((1 << w.tpc[s]) > T.p.max_tp) return false;
         }
@@ -583,35 +584,47 @@ struct PlanEvaluator {
         return 0;
     }
 
+    // One attempt of LayerLoadBalancer.partition_layer (model/load_balancer.py:127-143) after
+    // balance_run: memory demand, OOM test and, when memory is exceeded, the capacity re-weighting.
+    // returns 1 = partition accepted (w.mstate = memory_state), 2 = retry with the adjusted w.perf,
+    // 0 = (None, -1, None), <0 = fatal (negated code).  After the third failed attempt the reference
+    // still evaluates _adj_compute_performance and discards it; that call is skipped here.
+    MB_HD_NOINLINE int memory_phase(int attempt) {
+        const int S = pd.S;
+        bool oom = false;
+        int a = 0;
+        for (int s = 0; s < S; ++s) {
+            const int b = a + group(s);
+            double md;
+            const int rc = memory_demand(s, a, b, md);
+            if (rc) return -rc;
+            const double st = memory_capacity(a, b) - md;
+            w.extra[s] = md;
+            w.capa[s] = st;
+            if (st < 0) oom = true;
+            a = b;
+        }
+        if (!oom) {
+            for (int s = 0; s < S; ++s) w.mstate[s] = w.capa[s];
+            return 1;
+        }
+        if (attempt >= 3) return 0;
+        const int rc = adjust_performance();
+        if (rc < 0) return rc;
+        return rc == 1 ? 0 : 2;
+    }
+
     // LayerLoadBalancer.partition_layer (model/load_balancer.py:121-144)
     // returns attempt number 1..3, 0 = (None, -1, None), <0 = fatal (negated code)
     template <class Sink>
     MB_HD_NOINLINE int partition_layer(Sink &sink) {
-        const int S = pd.S;
         for (int attempt = 1; attempt <= 3; ++attempt) {
             sink.balancer_run();
-            int rc = balance_run<MAXS, MAXL>(T, S, w);
+            const int rc = balance_run<MAXS, MAXL>(T, pd.S, w);
             if (rc) return -rc;
-            bool oom = false;
-            int a = 0;
-            for (int s = 0; s < S; ++s) {
-                const int b = a + group(s);
-                double md;
-                rc = memory_demand(s, a, b, md);
-                if (rc) return -rc;
-                const double st = memory_capacity(a, b) - md;
-                w.extra[s] = md;
-                w.capa[s] = st;
-                if (st < 0) oom = true;
-                a = b;
-            }
-            if (!oom) {
-                for (int s = 0; s < S; ++s) w.mstate[s] = w.capa[s];
-                return attempt;
-            }
-            rc = adjust_performance();
-            if (rc < 0) return rc;
-            if (rc == 1) return 0;
+            const int r = memory_phase(attempt);
+            if (r == 1) return attempt;
+            if (r <= 0) return r;
         }
         return 0;
     }
@@ -749,14 +762,20 @@ struct PlanEvaluator {
         return 0;
     }
 
-    // cost_het_cluster.py:31-48 for one inter-stage plan, with IntraStagePlanGenerator.has_next
-    // (search_space/plan.py:192-226) inlined.  `only_step` >= 0 stops after emitting that step.
-    template <class Sink>
-    MB_HD_NOINLINE void run(const PlanDesc &plan, Sink &sink, int only_step = -1) {
+    MB_HD bool begin(const PlanDesc &plan) {
         pd = plan;
-        if (pd.S > MAXS || T.p.num_layers > MAXL) { sink.fatal(pd.ordinal, METIS_FATAL_SCRATCH, 0); return; }
+        if (pd.S > MAXS || T.p.num_layers > MAXL) return false;
         bs_total = T.p.gbs / pd.batches;
         for (int s = 0; s < pd.S; ++s) { w.gcode[s] = pd.row[s]; w.tpc[s] = 0; }
+        return true;
+    }
+
+    // cost_het_cluster.py:31-48 for one inter-stage plan, with IntraStagePlanGenerator.has_next
+    // (search_space/plan.py:192-226) inlined.  `only_step` >= 0 stops after emitting that step.
+    // Sequential form (replay kernel and tests); the search kernel uses search_loop below.
+    template <class Sink>
+    MB_HD_NOINLINE void run(const PlanDesc &plan, Sink &sink, int only_step = -1) {
+        if (!begin(plan)) { sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0); return; }
         bool started = false, have_state = false;
         int nrep = 0, step = 0;
         for (;;) {
@@ -783,6 +802,81 @@ struct PlanEvaluator {
         }
     }
 };
+
+// ---------------------------------------------------------------------------
+// Warp-synchronous search loop: every lane owns one inter-stage plan at a time and the lanes of a
+// warp move through the phases together, so the expensive phases (balance_run, memory check,
+// cost) execute with all lanes busy:
+//   F  fetch / advance: lanes without a ready strategy fetch the next plan or take chain steps
+//      (search_space/plan.py:192-268) until every lane is ready or out of work (cheap, divergent);
+//   P  stage performance of new strategies (model/device_group.py:54-85);
+//   R  LayerComputeBalancer.run (convergent: the forward scan has the same trip count in all lanes);
+//   M  memory demand / OOM / re-weighting (load_balancer.py:127-143); OOM lanes stay ready for R;
+//   C  cost of accepted partitions (cost_estimator.py:199-244) and record emission.
+// `Warp` supplies any(pred) and fetch(need, PlanDesc&) - a warp ballot / aggregated atomic on the
+// device, trivial on the host (tests/hostsim).
+// ---------------------------------------------------------------------------
+template <int MAXS, int MAXL, class Sink, class Warp>
+MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &warp) {
+    enum { NEED_PLAN = 0, ADVANCE = 1, READY_NEW = 2, READY_RETRY = 3, DONE = 4 };
+    PlanEvaluator<MAXS, MAXL> ev(T, w);
+    int state = NEED_PLAN, attempt = 0, nrep = 0, step = 0;
+    bool started = false, have_state = false;
+    for (;;) {
+        // ---- F ---------------------------------------------------------------------------------
+        while (warp.any(state == NEED_PLAN || state == ADVANCE)) {
+            PlanDesc plan;
+            const bool need = (state == NEED_PLAN);
+            const bool got = warp.fetch(need, plan);
+            if (need) {
+                if (!got) state = DONE;
+                else if (!ev.begin(plan)) sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0);
+                else { state = ADVANCE; started = false; have_state = false; nrep = 0; step = 0; }
+            } else if (state == ADVANCE) {
+                if (nrep == 1) state = NEED_PLAN;                         // plan.py:194-195
+                else {
+                    bool alive = true;
+                    if (!started) started = true;                         // _initial_strategies
+                    else alive = ev.next_strategy(have_state);
+                    if (!alive) state = NEED_PLAN;                        // plan.py:203-204
+                    else if (ev.valid()) { state = READY_NEW; attempt = 1; }
+                }
+            }
+        }
+        if (!warp.any(state == READY_NEW || state == READY_RETRY)) break;
+        // ---- P ---------------------------------------------------------------------------------
+        if (state == READY_NEW) {
+            sink.partition_call();
+            const int rc = ev.compute_performance();
+            if (rc) { sink.fatal(ev.pd.ordinal, rc, ev.aux); state = NEED_PLAN; }
+        }
+        // ---- R ---------------------------------------------------------------------------------
+        const bool ready = (state == READY_NEW || state == READY_RETRY);
+        int result = -1000;
+        if (ready) {
+            sink.balancer_run();
+            const int rc = balance_run<MAXS, MAXL>(T, ev.pd.S, w);
+            if (rc) { sink.fatal(ev.pd.ordinal, rc, ev.aux); state = NEED_PLAN; }
+            else result = 0;
+        }
+        // ---- M ---------------------------------------------------------------------------------
+        if (ready && result == 0) {
+            const int r = ev.memory_phase(attempt);
+            if (r < 0) { sink.fatal(ev.pd.ordinal, -r, ev.aux); state = NEED_PLAN; }
+            else if (r == 2) { state = READY_RETRY; ++attempt; }
+            else if (r == 0) { have_state = false; state = ADVANCE; }     // memory_state = None (:225)
+            else { have_state = true; nrep = attempt; result = 1; }
+        }
+        // ---- C ---------------------------------------------------------------------------------
+        if (ready && result == 1) {
+            double cost;
+            if (ev.get_cost(cost) == 0) sink.emit(ev.pd, step, nrep, cost, w.tpc, w.part);
+            else sink.keyerror();
+            ++step;
+            state = ADVANCE;
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------
 // HomoCostEstimator.get_cost (model/cost_estimator.py:98-138) for one UniformPlan.

@@ -214,11 +214,52 @@ struct DeviceSink {
     }
 };
 
+// Warp-level services of search_loop: ballots and an aggregated fetch of plan indices from the
+// launch-wide counter (one atomicAdd per warp per round, popc-ranked inside the warp).
+struct DeviceWarp {
+    const MetisPlanSpace &sp;
+    const MetisShard sh;
+    unsigned long long *counter;
+    long long slots;
+    int cur_block;
+    __device__ DeviceWarp(const MetisPlanSpace &s, const MetisShard &h, unsigned long long *c, long long n)
+        : sp(s), sh(h), counter(c), slots(n), cur_block(0) {}
+    __device__ bool any(bool p) const { return __any_sync(0xFFFFFFFFu, p); }
+    __device__ bool fetch(bool need, PlanDesc &pd) {
+        const unsigned full = 0xFFFFFFFFu;
+        const unsigned m = __ballot_sync(full, need);
+        if (m == 0) return false;
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+        base = __shfl_sync(full, base, leader);
+        if (!need) return false;
+        const long long i = (long long)base + __popc(m & ((1u << lane) - 1u));
+        if (i >= slots) return false;
+        const long long ordinal = ((i / sh.tile) * sh.world + sh.rank) * sh.tile + (i % sh.tile);
+        if (ordinal >= sp.num_plans) return false;
+        // plans are handed out in increasing order: walk forward from the block of the previous plan
+        int b = cur_block;
+        while (b + 1 < sp.num_blocks && __ldg(&sp.blocks[b + 1].first_ordinal) <= ordinal) ++b;
+        cur_block = b;
+        const MetisPlanBlock blk = sp.blocks[b];
+        const uint32_t rel = (uint32_t)(ordinal - blk.first_ordinal);
+        const uint32_t row = rel / (uint32_t)sp.num_div;
+        pd.ordinal = (uint32_t)ordinal;
+        pd.ns = blk.ns_idx;
+        pd.S = blk.num_stage;
+        pd.label = blk.label_stage;
+        pd.batches = __ldg(&sp.batches[rel - row * (uint32_t)sp.num_div]);
+        pd.row = sp.rows + blk.rows_offset + (size_t)row * blk.num_stage;
+        return true;
+    }
+};
+
 template <int MAXS, int MAXL>
 __global__ void __launch_bounds__(kThreads)
 het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                   const MetisShard sh, const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob,
-                  const int use_smem, const __grid_constant__ DeviceOut out) {
+                  const int use_smem, const long long slots, const __grid_constant__ DeviceOut out) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
     __shared__ double s_cost[kThreads / 32];
@@ -233,14 +274,9 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
 
     DeviceSink sink(out);
     {
-        const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;          // plan index inside the shard
-        const long long ordinal = ((i / sh.tile) * sh.world + sh.rank) * sh.tile + (i % sh.tile);
-        PlanDesc pd;
-        if (decode_plan(sp, ordinal, pd)) {
-            Scratch<MAXS, MAXL> w;
-            PlanEvaluator<MAXS, MAXL> ev(T, w);
-            ev.run(pd, sink);
-        }
+        Scratch<MAXS, MAXL> w;
+        DeviceWarp warp(sp, sh, &out.counters[5], slots);
+        search_loop<MAXS, MAXL>(T, w, sink, warp);
     }
 
     // counters: warp reduce, one atomic per warp
@@ -465,7 +501,7 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     const Workspace ws = carve(workspace, lay);
 
     cudaError_t e;
-    e = cudaMemsetAsync(ws.counters, 0, 4 * sizeof(unsigned long long), stream);
+    e = cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset counters");
     e = cudaMemsetAsync(ws.counters + 4, 0xFF, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset fatal key");
@@ -483,15 +519,24 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     DeviceOut out;
     out.records = records; out.capacity = capacity; out.detail = detail; out.detail_stride = detail_stride;
     out.counters = ws.counters; out.block_best = ws.block_best;
+    // persistent grid: one wave of resident blocks, plans are fetched from a launch-wide counter
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, dyn);
+    if (e != cudaSuccess || per_sm < 1 || sms < 1) return cuda_fail(e, "occupancy query");
+    const int64_t resident = (int64_t)sms * per_sm;
+    const int64_t grid = nblocks < resident ? nblocks : resident;
     if (nblocks > 0) {
         if (g_ev_before) cudaEventRecord(g_ev_before, stream);
-        kern<<<(unsigned)nblocks, kThreads, dyn, stream>>>(*problem, *space, *shard, lay, ws.blob, use_smem, out);
+        kern<<<(unsigned)grid, kThreads, dyn, stream>>>(*problem, *space, *shard, lay, ws.blob, use_smem,
+                                                        (long long)slots, out);
         e = cudaGetLastError();
         if (g_ev_after) cudaEventRecord(g_ev_after, stream);
         g_ev_before = g_ev_after = nullptr;
         if (e != cudaSuccess) return cuda_fail(e, "het_search_kernel");
     }
-    het_finalize_kernel<<<1, 256, 0, stream>>>(ws.block_best, (int)nblocks, ws.counters, ws.summary);
+    het_finalize_kernel<<<1, 256, 0, stream>>>(ws.block_best, (int)(nblocks > 0 ? grid : 0), ws.counters, ws.summary);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "het_finalize_kernel");
     e = cudaMemcpyAsync(summary, ws.summary, sizeof(MetisSearchSummary), cudaMemcpyDeviceToHost, stream);

@@ -259,7 +259,12 @@ def golden_het_workload(w: Workload, procs: int, sample_n: int = 0):
                                                       variance=args.min_group_scale_variance,
                                                       max_permute_len=args.max_permute_len)
             total = sum(1 for _ in gen)
-            sample = sorted(random.Random(1234).sample(range(total), min(sample_n, total)))
+            picks = set(random.Random(1234).sample(range(total), min(sample_n, total)))
+            nseq = len(gen.node_sequences)
+            for k in range(1, nseq):       # plus a window at the start of every later node sequence:
+                start = k * (total // nseq) - 64      # mislabelled Q1 blocks and mixed-type stages
+                picks.update(range(max(0, start), min(total, start + 1200)))
+            sample = sorted(picks)
         rows, counters, fatal, names, wall = run_het(w.name, argv, order, procs, sample)
         meta = {'workload': w.name, 'inputs_sha256': digest, 'file_order': order, 'node_sequences': names,
                 'counters': counters, 'fatal': fatal, 'reference_wall_s': wall, 'procs': procs,

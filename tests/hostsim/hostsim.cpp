@@ -96,7 +96,7 @@ struct HostSink {
 extern "C" {
 
 int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const MetisShard *sh, MetisRecord *records,
-                       int64_t capacity, uint8_t *detail, int32_t stride, MetisSearchSummary *summary) {
+                       int64_t capacity, uint8_t *detail, int32_t stride, MetisSearchSummary *summary, int32_t mode) {
     std::vector<double> dlay;
     const Tables T = host_tables(*p, dlay);
     memset(summary, 0, sizeof(*summary));
@@ -108,12 +108,30 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
     static thread_local Scratch<METIS_MAX_STAGES, METIS_MAX_LAYERS> w;
     const int64_t tile = sh->tile, world = sh->world;
     const int64_t rounds = (sp->num_plans + tile * world - 1) / (tile * world);
-    for (int64_t i = 0; i < rounds * tile; ++i) {
-        const int64_t ordinal = ((i / tile) * world + sh->rank) * tile + (i % tile);
-        PlanDesc pd;
-        if (!decode(*sp, ordinal, pd)) continue;
-        PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> ev(T, w);
-        ev.run(pd, sink);
+    if (mode == 0) {                      // sequential PlanEvaluator::run (also used by the replay kernel)
+        for (int64_t i = 0; i < rounds * tile; ++i) {
+            const int64_t ordinal = ((i / tile) * world + sh->rank) * tile + (i % tile);
+            PlanDesc pd;
+            if (!decode(*sp, ordinal, pd)) continue;
+            PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> ev(T, w);
+            ev.run(pd, sink);
+        }
+    } else {                              // the search kernel's state machine with a one-lane "warp"
+        struct HostWarp {
+            const MetisPlanSpace *sp; const MetisShard *sh; int64_t next, slots;
+            bool any(bool p) const { return p; }
+            bool fetch(bool need, PlanDesc &pd) {
+                if (!need) return false;
+                while (next < slots) {
+                    const int64_t i = next++;
+                    const int64_t ordinal = ((i / sh->tile) * sh->world + sh->rank) * sh->tile + (i % sh->tile);
+                    if (ordinal >= sp->num_plans) return false;
+                    if (decode(*sp, ordinal, pd)) return true;
+                }
+                return false;
+            }
+        } warp{sp, sh, 0, rounds * tile};
+        search_loop<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, warp);
     }
     return 0;
 }

@@ -45,7 +45,7 @@ def load_inputs(root, profile_sub, file_order, num_layers, hidden, seq, vocab):
 
 
 def host_het_search(problem: flatten.FlatProblem, space: flatten.FlatPlanSpace, rank=0, world=1, tile=32,
-                    capacity=None, want_detail=True):
+                    capacity=None, want_detail=True, mode=1):
     """Runs the host-compiled evaluator; returns (records, detail, summary)."""
     lib = hostsim()
     keep = dict(problem.arrays)
@@ -60,7 +60,7 @@ def host_het_search(problem: flatten.FlatProblem, space: flatten.FlatPlanSpace, 
     summary = native.MetisSearchSummary()
     rc = lib.hostsim_het_search(C.byref(p), C.byref(s), C.byref(shard), C.c_void_p(records.ctypes.data),
                                 C.c_int64(capacity), C.c_void_p(detail.ctypes.data if want_detail else 0),
-                                C.c_int32(native.DETAIL_STRIDE), C.byref(summary))
+                                C.c_int32(native.DETAIL_STRIDE), C.byref(summary), C.c_int32(mode))
     assert rc == 0
     n = min(int(summary.num_records), capacity)
     return records[:n], (detail[:n] if want_detail else None), summary

@@ -49,13 +49,14 @@ def test_c1_het():
     assert summary.best.cost == 621.8881853975784 and summary.best.ordinal == 7
 
 
+@pytest.mark.parametrize('mode', [0, 1], ids=['sequential_run', 'search_loop'])
 @pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight'])
-def test_synthetic(name, workload_dir):
+def test_synthetic(name, mode, workload_dir):
     meta, arr = load_golden(name)
     w, root, _ = workload_dir(name)
     problem, space, (rec, det, summary) = _search(meta, root, 'profile', w.num_layers, w.hidden_size,
                                                   w.sequence_length, w.vocab_size, w.gbs, w.variance,
-                                                  w.max_permute_len, w.max_tp, w.max_bs)
+                                                  w.max_permute_len, w.max_tp, w.max_bs, mode=mode)
     c = meta['counters']
     assert space.num_plans == c['A']
     assert (summary.num_partition_calls, summary.num_balancer_runs, summary.num_records) == (c['B'], c['runs'], c['C'])

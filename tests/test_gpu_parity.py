@@ -145,7 +145,6 @@ def test_full_size_c3_vs_golden(name, workload_dir):
     _assert_arrays_equal(out, space, arr)
     i = int(np.lexsort((arr['step'], arr['ordinal'], arr['cost']))[0])
     assert out.best[:3] == (float(arr['cost'][i]), int(arr['ordinal'][i]), int(arr['step'][i]))
-    assert out.best[0] == 9597.440191177611
 
 
 def test_c4_sampled_vs_golden(workload_dir):
@@ -199,7 +198,8 @@ def test_shards_partition_the_space(workload_dir):
     assert (rec['cost'].view(np.uint64) == arr['cost'].view(np.uint64)).all()
     c = meta['counters']
     assert counters.tolist() == [c['B'], c['runs'], c['C']]
-    assert min(b[:3] for b in bests if b) == (9597.440191177611, 4, 0)
+    i = int(np.lexsort((arr['step'], arr['ordinal'], arr['cost']))[0])
+    assert min(b[:3] for b in bests if b) == (float(arr['cost'][i]), int(arr['ordinal'][i]), int(arr['step'][i]))
 
 
 def test_rerun_is_idempotent(workload_dir):
@@ -216,7 +216,10 @@ def test_rerun_is_idempotent(workload_dir):
     a = searcher.run()            # capacity 8 forces the grow-and-rerun path
     b = searcher.run()
     assert a.summary == b.summary and a.best == b.best
-    assert (a.records == b.records).all() and (a.detail == b.detail).all()
+    assert (a.records == b.records).all()
+    for i in range(len(a.records)):               # bytes past 3S+1 of a detail row are unspecified
+        S = int(a.records['num_stage'][i])
+        assert (a.detail[i, :3 * S + 1] == b.detail[i, :3 * S + 1]).all()
     picks = a.records[[0, len(a.records) // 2, len(a.records) - 1]]
     replay = searcher.detail_for(picks)
     for k, i in enumerate([0, len(a.records) // 2, len(a.records) - 1]):

@@ -140,7 +140,7 @@ typedef struct MetisSearchSummary {
     uint32_t fatal_code;          /* METIS_FATAL_* of that ordinal                                  */
     uint32_t fatal_aux;           /* tp<<16 | bs of the missing key when applicable                 */
     MetisRecord best;             /* argmin (cost, ordinal, step); cost = +inf when no record       */
-    uint64_t reserved[2];
+    uint64_t reserved[6];         /* profiling builds: warp-cycles spent in phases F,P,R,M,C            */
 } MetisSearchSummary;
 
 /* Shard of the ordinal space evaluated by one call (multi-GPU: rank r of n, interleaved tiles). */

@@ -388,7 +388,7 @@ MB_HD_NOINLINE int partition_data(const Tables &T, int ns, int rank_lo, int coun
 }
 
 // Sink interface expected by evaluate_plan (see metis_search.cu / tests/hostsim):
-//   void partition_call(); void balancer_run(); void keyerror();
+//   void partition_call(); void balancer_run(); void keyerror(); void phase(int) (profiling hook);
 //   void fatal(uint32_t ordinal, int code, uint32_t aux);
 //   void emit(const PlanDesc&, int step, int nrep, double cost, const uint8_t *tpc, const uint16_t *part);
 
@@ -824,6 +824,7 @@ MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &s
     bool started = false, have_state = false;
     for (;;) {
         // ---- F ---------------------------------------------------------------------------------
+        sink.phase(0);
         while (warp.any(state == NEED_PLAN || state == ADVANCE)) {
             PlanDesc plan;
             const bool need = (state == NEED_PLAN);
@@ -845,6 +846,7 @@ MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &s
         }
         if (!warp.any(state == READY_NEW || state == READY_RETRY)) break;
         // ---- P ---------------------------------------------------------------------------------
+        sink.phase(1);
         if (state == READY_NEW) {
             sink.partition_call();
             const int rc = ev.compute_performance();
@@ -853,6 +855,7 @@ MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &s
         // ---- R ---------------------------------------------------------------------------------
         const bool ready = (state == READY_NEW || state == READY_RETRY);
         int result = -1000;
+        sink.phase(2);
         if (ready) {
             sink.balancer_run();
             const int rc = balance_run<MAXS, MAXL>(T, ev.pd.S, w);
@@ -860,6 +863,7 @@ MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &s
             else result = 0;
         }
         // ---- M ---------------------------------------------------------------------------------
+        sink.phase(3);
         if (ready && result == 0) {
             const int r = ev.memory_phase(attempt);
             if (r < 0) { sink.fatal(ev.pd.ordinal, -r, ev.aux); state = NEED_PLAN; }
@@ -868,6 +872,7 @@ MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &s
             else { have_state = true; nrep = attempt; result = 1; }
         }
         // ---- C ---------------------------------------------------------------------------------
+        sink.phase(4);
         if (ready && result == 1) {
             double cost;
             if (ev.get_cost(cost) == 0) sink.emit(ev.pd, step, nrep, cost, w.tpc, w.part);
@@ -876,6 +881,7 @@ MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &s
             state = ADVANCE;
         }
     }
+    sink.phase(5);
 }
 
 // ---------------------------------------------------------------------------

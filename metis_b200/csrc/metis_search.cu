@@ -186,6 +186,16 @@ struct DeviceSink {
     __device__ DeviceSink(const DeviceOut &out)
         : o(out), n_part(0), n_run(0), n_key(0), best_cost(INFINITY), best_ord(0xFFFFFFFFu), best_step(0xFFFFu),
           best_meta(0) {}
+#ifdef METIS_PROFILE_PHASES
+    long long t_last = 0; int cur = -1; long long acc[6] = {0, 0, 0, 0, 0, 0};
+    __device__ void phase(int k) {
+        const long long now = clock64();
+        if (cur >= 0) acc[cur] += now - t_last;
+        cur = k; t_last = now;
+    }
+#else
+    __device__ void phase(int) {}
+#endif
     __device__ void partition_call() { ++n_part; }
     __device__ void balancer_run() { ++n_run; }
     __device__ void keyerror() { ++n_key; }
@@ -279,6 +289,10 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
         search_loop<MAXS, MAXL>(T, w, sink, warp);
     }
 
+#ifdef METIS_PROFILE_PHASES
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 5; ++k) atomicAdd(&out.counters[8 + k], (unsigned long long)sink.acc[k]);
+#endif
     // counters: warp reduce, one atomic per warp
     const unsigned full = 0xFFFFFFFFu;
     const unsigned np = __reduce_add_sync(full, sink.n_part);
@@ -347,6 +361,8 @@ __global__ void het_finalize_kernel(const MetisRecord *block_best, int nblocks, 
         else { s.fatal_ordinal = fk >> 32; s.fatal_code = (uint32_t)((fk >> 24) & 0xFF); s.fatal_aux = (uint32_t)(fk & 0xFFFFFF); }
         s.best.cost = c; s.best.ordinal = o; s.best.step = (uint16_t)st;
         s.best.num_repartition = (uint8_t)(mt >> 8); s.best.num_stage = (uint8_t)mt;
+        s.reserved[0] = counters[8]; s.reserved[1] = counters[9];        // profiling builds: phase clocks
+        s.reserved[2] = counters[10]; s.reserved[3] = counters[11]; s.reserved[4] = counters[12];
         *summary = s;
     }
 }
@@ -355,6 +371,7 @@ __global__ void het_finalize_kernel(const MetisRecord *block_best, int nblocks, 
 struct DetailSink {
     uint8_t *dst;
     int want_step;
+    __device__ void phase(int) {}
     __device__ void partition_call() {}
     __device__ void balancer_run() {}
     __device__ void keyerror() {}
@@ -501,7 +518,7 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     const Workspace ws = carve(workspace, lay);
 
     cudaError_t e;
-    e = cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned long long), stream);
+    e = cudaMemsetAsync(ws.counters, 0, 16 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset counters");
     e = cudaMemsetAsync(ws.counters + 4, 0xFF, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset fatal key");

@@ -58,7 +58,7 @@ class MetisSearchSummary(C.Structure):
     _fields_ = [('num_records', C.c_uint64), ('num_partition_calls', C.c_uint64),
                 ('num_balancer_runs', C.c_uint64), ('num_keyerror', C.c_uint64),
                 ('fatal_ordinal', C.c_uint64), ('fatal_code', C.c_uint32), ('fatal_aux', C.c_uint32),
-                ('best', MetisRecord), ('reserved', C.c_uint64 * 2)]
+                ('best', MetisRecord), ('reserved', C.c_uint64 * 6)]
 
 
 class MetisShard(C.Structure):

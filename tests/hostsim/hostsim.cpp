@@ -60,6 +60,7 @@ struct HostSink {
     uint8_t *detail;
     int stride;
     MetisSearchSummary *sum;
+    void phase(int) {}
     void partition_call() { ++sum->num_partition_calls; }
     void balancer_run() { ++sum->num_balancer_runs; }
     void keyerror() { ++sum->num_keyerror; }

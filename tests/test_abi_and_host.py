@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(native.MetisRecord) == 16
     assert C.sizeof(native.MetisPlanBlock) == 32
     assert C.sizeof(native.MetisShard) == 16
-    assert C.sizeof(native.MetisSearchSummary) == 8 * 5 + 8 + 16 + 16
+    assert C.sizeof(native.MetisSearchSummary) == 8 * 5 + 8 + 16 + 48
     assert np.dtype(native.RECORD_DTYPE).itemsize == 16 and np.dtype(native.BLOCK_DTYPE).itemsize == 32
     # compile a probe with the real header and compare sizes / offsets
     probe = r'''

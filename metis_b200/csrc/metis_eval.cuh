@@ -15,6 +15,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <string.h>
 #include <math.h>
 
 #include "../../include/metis_b200.h"
@@ -42,11 +43,65 @@ struct Tables {
     const double *exec_full;   // [num_keys]
     const double *fb_sync;     // [num_keys]
     const double *norm_lc;     // [norm_len]
-    const double *dlay;        // [num_layers] norm_lc[r] / 7   (load_balancer.py:190-193)
     const double *type_memory, *bw_first, *bw_min;
     const uint8_t *run_type;   // [ns][num_types]
     const int32_t *run_end;    // [ns][num_types]
+    // derived once per launch (derive_tables): every entry is the result of the same single IEEE
+    // operation the reference performs, so looking it up is bit-identical to recomputing it
+    const double *dlay;        // [norm_len] norm_lc[r] / 7              (load_balancer.py:190-193)
+    const double *inv_exec;    // [num_keys] 1. / sum(layer-computes)    (model/device_group.py:80)
+    const double *ratio;       // [num_layers+1] n / num_layers          (cost_estimator.py:146)
+    const double *dpk;         // [kDpk] 2*(dp-1) / (dp * (bw*2^20)), dp = 2^i, uniform bandwidth only (:40-41)
+    const double *pp_hidden;   // [num_bs+1] mbs*seq*hidden / (bw*2^20), uniform bandwidth only (:45-47)
+    const double *pp_vocab;    // [num_bs+1][num_tp] (mbs*seq*vocab / tp) / (bw*2^20)
 };
+
+constexpr int kDpk = 16;
+
+// Sizes (in doubles) of the derived tables, in the order derive_tables fills them.
+struct DerivedLayout {
+    int dlay, inv_exec, ratio, dpk, pp_hidden, pp_vocab, total;
+};
+
+MB_HD DerivedLayout derived_layout(const MetisProblem &p) {
+    DerivedLayout d;
+    int o = 0;
+    d.dlay = o; o += p.norm_len;
+    d.inv_exec = o; o += p.num_keys;
+    d.ratio = o; o += p.num_layers + 1;
+    d.dpk = o; o += kDpk;
+    d.pp_hidden = o; o += p.num_bs + 1;
+    d.pp_vocab = o; o += (p.num_bs + 1) * p.num_tp;
+    d.total = o;
+    return d;
+}
+
+// One entry of the derived tables (index i of the flat array laid out by derived_layout).
+MB_HD double derive_entry(const MetisProblem &p, const DerivedLayout &d, const double *norm_lc,
+                          const double *exec_full, const double *bw_first, int i) {
+    if (i < d.inv_exec) return norm_lc[i - d.dlay] / 7.0;
+    if (i < d.ratio) return 1. / exec_full[i - d.inv_exec];
+    if (i < d.dpk) return (double)(i - d.ratio) / (double)p.num_layers;
+    const double bw = bw_first[0] * 1048576.0;
+    if (i < d.pp_hidden) {
+        const int dp = 1 << (i - d.dpk);
+        return (double)(2 * (dp - 1)) / ((double)dp * bw);
+    }
+    if (i < d.pp_vocab) return (double)((int64_t)(i - d.pp_hidden) * p.sequence_length * p.hidden_size) / bw;
+    const int e = i - d.pp_vocab;
+    const int mbs = e / p.num_tp, tpc = e - mbs * p.num_tp;
+    return ((double)((int64_t)mbs * p.sequence_length * p.vocab_size) / (double)(1 << tpc)) / bw;
+}
+
+MB_HD void bind_derived(Tables &T, const double *base) {
+    const DerivedLayout d = derived_layout(T.p);
+    T.dlay = base + d.dlay;
+    T.inv_exec = base + d.inv_exec;
+    T.ratio = base + d.ratio;
+    T.dpk = base + d.dpk;
+    T.pp_hidden = base + d.pp_hidden;
+    T.pp_vocab = base + d.pp_vocab;
+}
 
 // One inter-stage plan (search_space/plan.py:21-29).
 struct PlanDesc {
@@ -58,22 +113,29 @@ struct PlanDesc {
     const uint8_t *row;  // log2(group size) per stage
 };
 
+constexpr uint16_t kBroke = 0x8000;   // stage closed because a sub-layer did not fit (that sub-layer is skipped)
+constexpr uint16_t kTaken = 0x4000;   // that skipped sub-layer was taken by the backward pass
+constexpr uint16_t kPos = 0x3FFF;
+
+// Per-plan scratch (one per thread; indexed with lane-uniform indices wherever the algorithm
+// allows, so that the per-thread arrays are accessed coalesced across the warp).
 template <int MAXS, int MAXL>
 struct Scratch {
-    static constexpr int kLeft = 2 * MAXS + 64;
+    static constexpr int kBlock = MAXS + 64;   // leftover sub-layers between the forward and backward fills
     double perf[MAXS];     // stage compute performance of the current attempt (sc_capa_bak)
     double capa[MAXS];     // working capacities / scratch
     double mstate[MAXS];   // memory_state of the last partition_layer call / scratch in adjust
     double extra[MAXS];    // additional_alloc_sc_capa / memory demand
-    uint16_t fs[MAXS], fe[MAXS];   // forward interval [fs,fe) in sub-layers; later first/last real layer
-    uint16_t cnt[MAXS];    // real layers per stage
+    uint16_t fe[MAXS];     // end of the stage's forward interval in sub-layers | kBroke | kTaken
+    uint16_t first[MAXS], lastl[MAXS], cnt[MAXS];   // real layers owned by each stage
     uint16_t part[MAXS + 1];
-    uint16_t lid[kLeft];   // leftover sub-layer ids, ascending
-    uint8_t lst[kLeft];    // stage each leftover was placed on
     uint8_t gcode[MAXS];   // log2(device group size)
     uint8_t tpc[MAXS];     // log2(tp)
-    uint8_t flag[MAXS];    // bit0 stage broke in forward pass, bit1 skip taken by backward pass, bit2 got a leftover
+    uint8_t lstk[MAXS];    // stage on which the skipped sub-layer of stage s was placed
+    uint8_t got[MAXS];     // stage received a leftover sub-layer
+    uint8_t blk[kBlock];   // stage of each leftover of the middle block
     uint8_t owner[MAXL];   // stage owning each real layer after the majority vote
+    uint8_t sub[MAXL * kH + 8];   // stage of each sub-layer below the backward tail
 };
 
 // ---------------------------------------------------------------------------
@@ -116,6 +178,14 @@ struct PySum {
     }
 };
 
+// 2^-k as a double (k >= 0): dividing by tp = 2^k and multiplying by this round identically.
+MB_HD double pow2_neg(int k) {
+    const uint64_t bits = (uint64_t)(1023 - k) << 52;
+    double d;
+    memcpy(&d, &bits, sizeof(d));
+    return d;
+}
+
 MB_HD int type_of_rank(const Tables &T, int ns, int rank) {
     const int nt = T.p.num_types;
     const int32_t *end = T.run_end + ns * nt;
@@ -134,7 +204,24 @@ MB_HD int key_of(const Tables &T, int type, int tpc, int bs) {
 // LayerComputeBalancer.run  (model/load_balancer.py:197-207, passes :216-364)
 // in : w.perf[0..S) = sc_capa (kept as sc_capa_bak), out: w.part[0..S], w.cnt
 // returns METIS_FATAL_* (0 = ok)
+//
+// Written for lockstep execution by the 32 lanes of a warp (one plan per lane): the forward scan
+// is one flat predicated loop over sub-layers with the same trip count in every lane, the vote is
+// a uniform loop over real layers on a per-sub-layer stage map, and the rare general cases are
+// loops whose trip count is normally 1.
 // ---------------------------------------------------------------------------
+template <int MAXS, int MAXL>
+MB_HD int fwd_start(const Scratch<MAXS, MAXL> &w, int s) {
+    if (s == 0) return 0;
+    const uint16_t e = w.fe[s - 1];
+    return (e & kPos) + ((e & kBroke) ? 1 : 0);
+}
+
+template <int MAXS, int MAXL>
+MB_HD bool fwd_nonempty(const Scratch<MAXS, MAXL> &w, int s) {
+    return (int)(w.fe[s] & kPos) > fwd_start(w, s);
+}
+
 template <int MAXS, int MAXL>
 MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
     const int L = T.p.num_layers;
@@ -142,37 +229,48 @@ MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
     const double *dlay = T.dlay;
     const double *lc = T.norm_lc;
     const int N = kH * L;
-    const int lim = N - 1 - kH;                            // :218
+    const int lim = (N - 1 - kH) > 0 ? (N - 1 - kH) : 0;   // :218
     const int last = S - 1;
 
-    for (int s = 0; s < S; ++s) { w.capa[s] = w.perf[s]; w.flag[s] = 0; }
+    for (int s = 0; s < S; ++s) { w.capa[s] = w.perf[s]; w.got[s] = 0; w.cnt[s] = 0; }
 
-    // ---- forward pass (:216-231) as one flat scan over sub-layers --------------------------
-    int k = 0;
+    // ---- forward pass (:216-231): flat scan, layer by layer, 7 sub-layers each -----------------
+    int k = 0, sTop = -1;
+    bool topSkip = false;
     if (S > 1) {
-        int s = 0;
+        int s = 0, j = 0;
         double c = w.capa[0];
-        w.fs[0] = 0;
-        int r = 0, sub = 0;
-        double d = dlay[0];
-        int j = 0;
-        bool done = false;
-        for (; j < lim; ++j) {
-            if (c > d) {
-                c -= d;
-            } else {                                        // sub-layer j does not fit: skipped, stage closes
-                w.capa[s] = c; w.fe[s] = (uint16_t)j; w.flag[s] = 1;
-                ++s;
-                if (s == last) { k = j + 1; done = true; break; }
-                c = w.capa[s];
-                w.fs[s] = (uint16_t)(j + 1);
+        for (int r = 0; r + 1 < L; ++r) {
+            const double d = dlay[r];
+            const int nsub = (r == L - 2) ? kH - 1 : kH;     // the last 8 sub-layers are reserved
+#pragma unroll
+            for (int q = 0; q < kH; ++q) {
+                if (q < nsub) {
+                    if (s < last) {
+                        if (c > d) {
+                            c -= d;
+                            w.sub[j] = (uint8_t)s;
+                        } else {                                 // sub-layer j does not fit: skipped, stage closes
+                            w.capa[s] = c;
+                            w.fe[s] = (uint16_t)(j | kBroke);
+                            ++s;
+                            c = w.capa[s];
+                        }
+                    }
+                    ++j;
+                }
             }
-            if (++sub == kH) { sub = 0; ++r; d = dlay[r]; }
         }
-        if (!done) {                                        // ran into the reserved tail: later stages stay empty
-            w.capa[s] = c; w.fe[s] = (uint16_t)lim;
-            for (int t = s + 1; t < last; ++t) { w.fs[t] = (uint16_t)lim; w.fe[t] = (uint16_t)lim; }
+        if (s < last) {                                          // ran into the reserved tail
+            w.capa[s] = c;
+            w.fe[s] = (uint16_t)lim;
+            for (int t = s + 1; t < last; ++t) w.fe[t] = (uint16_t)lim;
             k = lim;
+            sTop = s;
+        } else {
+            k = (w.fe[last - 1] & kPos) + 1;
+            sTop = last - 1;
+            topSkip = true;
         }
     }
 
@@ -188,109 +286,110 @@ MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
             const int j = m - 1;
             bool un = (j >= k);
             if (!un) {                                       // below k only skipped sub-layers are unassigned
-                while (sp >= 0 && (!(w.flag[sp] & 1) || w.fe[sp] > j)) --sp;
-                un = (sp >= 0 && w.fe[sp] == j);
+                while (sp >= 0 && (!(w.fe[sp] & kBroke) || (int)(w.fe[sp] & kPos) > j)) --sp;
+                un = (sp >= 0 && (int)(w.fe[sp] & kPos) == j);
             }
             if (!un) break;                                  // (layer_id + 1) != min(...) from here on (:243)
             const double d = dlay[j / kH];
             if (!(c > d)) break;                             // :246 fails; every later id fails :243
             c -= d;
             m = j;
-            if (j < k) w.flag[sp] |= 2;
+            if (j < k) w.fe[sp] |= kTaken;
         }
         w.capa[last] = c;
     }
 
-    // ---- leftovers (:251-287) ----------------------------------------------------------------
-    int nl = 0;
-    for (int s = 0; s < last; ++s)
-        if ((w.flag[s] & 3) == 1) {
-            if (nl >= Scratch<MAXS, MAXL>::kLeft) return METIS_FATAL_SCRATCH;
-            w.lid[nl++] = w.fe[s];
+    // ---- leftovers (:251-287), ascending: first the skipped sub-layers, then the middle block --
+    // get_proper_stage: lo = stage of the largest assigned id below j whose stage holds nothing
+    // above j, hi = stage of the smallest assigned id above j whose stage holds nothing below j.
+    for (int s = 0; s < last; ++s) {
+        const uint16_t e = w.fe[s];
+        if ((e & (kBroke | kTaken)) != kBroke) continue;
+        const int j = e & kPos;
+        int lo = 0;
+        for (int u = s;; --u) {
+            if (u < s) {                                      // skipped sub-layer of stage u (already placed)
+                const int t = w.lstk[u];
+                const bool above = (t == last) || (fwd_nonempty(w, t) && fwd_start(w, t) > j);
+                if (!above) { lo = t; break; }
+            }
+            if (fwd_nonempty(w, u)) { lo = u; break; }
+            if (u == 0) break;
         }
-    for (int j = k; j < m; ++j) {
-        if (nl >= Scratch<MAXS, MAXL>::kLeft) return METIS_FATAL_SCRATCH;
-        w.lid[nl++] = (uint16_t)j;
+        int hi = s + 1;
+        while (hi < last && (!fwd_nonempty(w, hi) || w.got[hi])) ++hi;
+        if (lo > hi) return METIS_FATAL_SCRATCH;
+        int pick = lo;
+        double best = w.capa[lo];
+        for (int t = lo + 1; t <= hi; ++t)
+            if (w.capa[t] > best) { best = w.capa[t]; pick = t; }
+        w.capa[pick] -= dlay[j / kH];
+        w.lstk[s] = (uint8_t)pick;
+        w.got[pick] = 1;
+        w.sub[j] = (uint8_t)pick;
     }
+    if (m - k > Scratch<MAXS, MAXL>::kBlock) return METIS_FATAL_SCRATCH;
     {
-        int x = -1;                                          // forward stages 0..x lie entirely below the query
-        for (int i = 0; i < nl; ++i) {
-            const int j = w.lid[i];
-            while (x + 1 < last && w.fe[x + 1] <= j) ++x;
-            // lo: stage of the largest assigned id < j whose stage holds nothing above j
+        int below = -1;                                       // stage of the nearest block item not on `last`
+        for (int t = 0; t < m - k; ++t) {
+            const int j = k + t;
             int lo = 0;
-            {
-                int a = i - 1, u = x;
-                for (;;) {
-                    while (u >= 0 && w.fe[u] == w.fs[u]) --u;
-                    const int pf = (u >= 0) ? (int)w.fe[u] - 1 : -1;
-                    const int pl = (a >= 0) ? (int)w.lid[a] : -1;
-                    if (pf < 0 && pl < 0) break;
-                    if (pf > pl) { lo = u; break; }
-                    const int t = w.lst[a];
-                    const bool above = (t == last) || (w.fe[t] > w.fs[t] && (int)w.fs[t] > j);
-                    if (!above) { lo = t; break; }
-                    --a;
+            if (below >= 0) lo = below;
+            else if (sTop >= 0) {
+                for (int u = sTop;; --u) {
+                    if (u < sTop || topSkip) {
+                        const uint16_t eu = w.fe[u];
+                        if ((eu & (kBroke | kTaken)) == kBroke) {
+                            const int t2 = w.lstk[u];
+                            if (t2 != last) { lo = t2; break; }   // forward intervals all lie below the block
+                        }
+                    }
+                    if (fwd_nonempty(w, u)) { lo = u; break; }
+                    if (u == 0) break;
                 }
             }
-            // hi: first stage above j that holds nothing below j
-            int hi = x + 1;
-            while (hi < last && (w.fe[hi] == w.fs[hi] || (w.flag[hi] & 4))) ++hi;
-            if (hi > last) hi = last;
-            if (lo > hi) return METIS_FATAL_SCRATCH;
             int pick = lo;
             double best = w.capa[lo];
-            for (int t = lo + 1; t <= hi; ++t)
-                if (w.capa[t] > best) { best = w.capa[t]; pick = t; }
+            for (int t2 = lo + 1; t2 <= last; ++t2)
+                if (w.capa[t2] > best) { best = w.capa[t2]; pick = t2; }
             w.capa[pick] -= dlay[j / kH];
-            w.lst[i] = (uint8_t)pick;
-            w.flag[pick] |= 4;
+            w.blk[t] = (uint8_t)pick;
+            if (pick != last) below = pick;
+            w.sub[j] = (uint8_t)pick;
         }
     }
 
-    // ---- majority vote back to real layers (:290-308) ----------------------------------------
-    {
-        int lf = 0, u = 0;
-        for (int r = 0; r < L; ++r) {
-            const int j0 = kH * r, j6 = j0 + kH - 1;
-            while (u < last && (int)w.fe[u] <= j0) ++u;
-            uint8_t own;
-            if (u < last && (int)w.fs[u] <= j0 && j6 < (int)w.fe[u]) {
-                own = (uint8_t)u;
-            } else if (j0 >= m) {
-                own = (uint8_t)last;
-            } else {
-                int st[kH];
-                int uu = u;
-                for (int q = 0; q < kH; ++q) {
-                    const int j = j0 + q;
-                    if (lf < nl && (int)w.lid[lf] == j) st[q] = w.lst[lf++];
-                    else if (j >= m) st[q] = last;
-                    else { while (uu < last && (int)w.fe[uu] <= j) ++uu; st[q] = uu; }
-                }
-                int cand = st[0], votes = 1;                // Boyer-Moore, then exact count
-                for (int q = 1; q < kH; ++q) {
-                    if (votes == 0) { cand = st[q]; votes = 1; }
-                    else if (st[q] == cand) ++votes;
-                    else --votes;
-                }
-                int n = 0;
-                for (int q = 0; q < kH; ++q) n += (st[q] == cand);
-                own = (2 * n > kH) ? (uint8_t)cand : kDropped;   // count > hallucination / 2 (:295)
+    // ---- majority vote back to real layers (:290-308) + first / last / count per stage ---------
+    for (int r = 0; r < L; ++r) {
+        const int j0 = kH * r;
+        int own;
+        if (j0 >= m) {
+            own = last;
+        } else {
+            int st[kH];
+#pragma unroll
+            for (int q = 0; q < kH; ++q) st[q] = (j0 + q >= m) ? last : (int)w.sub[j0 + q];
+            int cand = st[0], votes = 1;                     // Boyer-Moore candidate, then exact count
+#pragma unroll
+            for (int q = 1; q < kH; ++q) {
+                if (votes == 0) { cand = st[q]; votes = 1; }
+                else if (st[q] == cand) ++votes;
+                else --votes;
             }
-            w.owner[r] = own;
+            int n = 0;
+#pragma unroll
+            for (int q = 0; q < kH; ++q) n += (st[q] == cand);
+            own = (2 * n > kH) ? cand : (int)kDropped;       // count > hallucination / 2 (:295)
+        }
+        w.owner[r] = (uint8_t)own;
+        if (own != (int)kDropped) {
+            if (w.cnt[own] == 0) w.first[own] = (uint16_t)r;
+            w.lastl[own] = (uint16_t)r;
+            ++w.cnt[own];
         }
     }
-    for (int s = 0; s < S; ++s) w.cnt[s] = 0;
-    for (int r = 0; r < L; ++r) {
-        const int o = w.owner[r];
-        if (o == kDropped) continue;
-        if (w.cnt[o] == 0) w.fs[o] = (uint16_t)r;
-        w.fe[o] = (uint16_t)r;
-        ++w.cnt[o];
-    }
     for (int s = 0; s < S; ++s)                              // :300-306
-        w.capa[s] = w.cnt[s] ? w.perf[s] - py_sum_range(lc, w.fs[s], (int)w.fe[s] + 1) : w.perf[s];
+        w.capa[s] = w.cnt[s] ? w.perf[s] - py_sum_range(lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
 
     // ---- boundary adjustment (:310-356): at most three committed single-layer moves ---------
     for (int n = 1; n <= 3; ++n) {
@@ -303,9 +402,7 @@ MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
         if (top - 1 >= 0 && w.capa[top - 1] < val) { nb = top - 1; val = w.capa[top - 1]; }
         if (top + 1 < S && w.capa[top + 1] < val) { nb = top + 1; }
         if (nb < 0 || w.cnt[nb] <= 1) break;                 // no-op rounds leave the state unchanged
-        int layer = -1;
-        if (top > nb) { for (int r = L - 1; r >= 0; --r) if (w.owner[r] == nb) { layer = r; break; } }
-        else          { for (int r = 0; r < L; ++r) if (w.owner[r] == nb) { layer = r; break; } }
+        const int layer = (top > nb) ? w.lastl[nb] : w.first[nb];
         const double dl = lc[layer];
         const double ntop = w.capa[top] - dl;
         const double nnb = w.capa[nb] + dl;
@@ -318,6 +415,13 @@ MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
         w.owner[layer] = (uint8_t)top;
         w.capa[top] = ntop;
         w.capa[nb] = nnb;
+        if (top > nb) { int r = layer - 1; while (w.owner[r] != nb) --r; w.lastl[nb] = (uint16_t)r; }
+        else          { int r = layer + 1; while (w.owner[r] != nb) ++r; w.first[nb] = (uint16_t)r; }
+        if (w.cnt[top] == 0) { w.first[top] = (uint16_t)layer; w.lastl[top] = (uint16_t)layer; }
+        else {
+            if (layer < (int)w.first[top]) w.first[top] = (uint16_t)layer;
+            if (layer > (int)w.lastl[top]) w.lastl[top] = (uint16_t)layer;
+        }
         ++w.cnt[top];
         --w.cnt[nb];
     }
@@ -398,42 +502,72 @@ struct PlanEvaluator {
     Scratch<MAXS, MAXL> &w;
     PlanDesc pd;
     int bs_total;         // gbs // batches
+    int nbad;             // stages of the current strategy that violate _is_valid_strategies
     uint32_t aux;
 
-    MB_HD PlanEvaluator(const Tables &t, Scratch<MAXS, MAXL> &s) : T(t), w(s), bs_total(0), aux(0) {}
+    MB_HD PlanEvaluator(const Tables &t, Scratch<MAXS, MAXL> &s) : T(t), w(s), bs_total(0), nbad(0), aux(0) {}
 
     MB_HD int group(int s) const { return 1 << w.gcode[s]; }
     MB_HD int dp_of(int s) const { return (1 << w.gcode[s]) >> w.tpc[s]; }
 
-    // IntraStagePlanGenerator._is_valid_strategies (search_space/plan.py:238-249)
-    // gbs // dp // batches == (gbs // batches) >> log2(dp) because dp is a power of two.
-    MB_HD bool valid() const {
-        for (int s = 0; s < pd.S; ++s) {
-            const int mbs = bs_total >> (w.gcode[s] - w.tpc[s]);
-            if (mbs == 0 || mbs > T.p.max_bs) return false;
-            if ((1 << w.tpc[s]) > T.p.max_tp) return false;
-        }
-        return true;
+    // one stage of IntraStagePlanGenerator._is_valid_strategies (search_space/plan.py:238-249);
+    // gbs // dp // batches == (gbs // batches) >> log2(dp) because dp is a power of two
+    MB_HD bool stage_bad(int g, int t) const {
+        const int mbs = bs_total >> (g - t);
+        return mbs == 0 || mbs > T.p.max_bs || (1 << t) > T.p.max_tp;
     }
 
-    // IntraStagePlanGenerator._next_strategy (search_space/plan.py:251-268)
+    // Start of a plan.  The reference starts from (dp = group, tp = 1) and, while no memory state
+    // exists, always halves the stage with the largest dp (plan.py:252-266).  Every strategy on that
+    // path is invalid (mbs == 0 somewhere) until all dp <= B = 2^floor(log2(gbs // batches)), and no
+    // stage with dp <= B is touched before that, so the first strategy that can be valid is
+    // tp_s = max(1, group_s / B) - jumping there skips only strategies that have no effect.
+    // If that strategy is invalid it stays invalid for the rest of the chain (mbs and tp only grow).
+    // returns 1 ready, 0 plan has no valid strategy, -1 scratch limits exceeded
+    MB_HD int begin(const PlanDesc &plan) {
+        pd = plan;
+        if (pd.S > MAXS || T.p.num_layers > MAXL) return -1;
+        bs_total = T.p.gbs / pd.batches;
+        int lb = 0;
+        while ((2 << lb) <= bs_total) ++lb;
+        nbad = 0;
+        for (int s = 0; s < pd.S; ++s) {
+            const int g = pd.row[s];
+            const int t = g > lb ? g - lb : 0;
+            w.gcode[s] = (uint8_t)g;
+            w.tpc[s] = (uint8_t)t;
+            nbad += stage_bad(g, t) ? 1 : 0;
+        }
+        return nbad == 0 ? 1 : 0;
+    }
+
+    // IntraStagePlanGenerator._next_strategy (search_space/plan.py:251-268); keeps nbad current
     MB_HD bool next_strategy(bool have_state) {
         int pick = -1;
         if (have_state) {
+            double best = 0.0;
             for (int s = 0; s < pd.S; ++s)
-                if (dp_of(s) != 1 && (pick < 0 || w.mstate[s] < w.mstate[pick])) pick = s;
+                if (w.gcode[s] != w.tpc[s] && (pick < 0 || w.mstate[s] < best)) { pick = s; best = w.mstate[s]; }
         } else {                                             // default state 1/dp: largest dp first
-            for (int s = 0; s < pd.S; ++s)
-                if (dp_of(s) != 1 && (pick < 0 || dp_of(s) > dp_of(pick))) pick = s;
+            int best = -1;
+            for (int s = 0; s < pd.S; ++s) {
+                const int ldp = (int)w.gcode[s] - (int)w.tpc[s];
+                if (ldp != 0 && ldp > best) { pick = s; best = ldp; }
+            }
         }
         if (pick < 0) return false;
-        ++w.tpc[pick];
+        const int g = w.gcode[pick], t = w.tpc[pick];
+        nbad += (stage_bad(g, t + 1) ? 1 : 0) - (stage_bad(g, t) ? 1 : 0);
+        w.tpc[pick] = (uint8_t)(t + 1);
         return true;
     }
+
+    MB_HD bool valid() const { return nbad == 0; }
 
     // StagePerformance.get_device_group_memory_capacity, one stage (model/device_group.py:87-101)
     MB_HD double memory_capacity(int a, int b) const {
         const int nt = T.p.num_types;
+        if (nt == 1) return T.type_memory[0] * (double)(b - a);
         const int32_t *end = T.run_end + pd.ns * nt;
         const uint8_t *typ = T.run_type + pd.ns * nt;
         PySum acc;
@@ -461,41 +595,49 @@ struct PlanEvaluator {
         return 0;
     }
 
+    // mixed-type stage of get_intra_stage_compute_performance (model/device_group.py:68-76)
+    MB_HD_NOINLINE int hetero_performance(int a, int b, int dp, int tpc, double &p) {
+        HSplit hs;
+        int rc = partition_data(T, pd.ns, a, b - a, dp, tpc, bs_total, hs, aux);
+        if (rc) return rc;
+        double mx = -INFINITY;
+        for (int r = 0; r < hs.nruns; ++r) {
+            double c;
+            if (hs.plus[r] > 0) {
+                rc = replica_perf_cost(hs.type[r], tpc, hs.base[r] + 1, c);
+                if (rc) return rc;
+                if (c > mx) mx = c;
+            }
+            if (hs.plus[r] < hs.n[r]) {
+                rc = replica_perf_cost(hs.type[r], tpc, hs.base[r], c);
+                if (rc) return rc;
+                if (c > mx) mx = c;
+            }
+        }
+        p = (mx != 0.0) ? 1. / mx : 0.0;
+        return 0;
+    }
+
     // StagePerformance.get_intra_stage_compute_performance (model/device_group.py:54-85) -> w.perf
     MB_HD_NOINLINE int compute_performance() {
         PySum total;
+        const bool one_type = T.p.num_types == 1;
         int a = 0;
         for (int s = 0; s < pd.S; ++s) {
-            const int b = a + group(s);
-            const int dp = dp_of(s), tpc = w.tpc[s];
-            const int ta = type_of_rank(T, pd.ns, a), tb = type_of_rank(T, pd.ns, b - 1);
+            const int g = w.gcode[s], tpc = w.tpc[s];
+            const int b = a + (1 << g);
+            const int ta = one_type ? 0 : type_of_rank(T, pd.ns, a);
+            const int tb = one_type ? 0 : type_of_rank(T, pd.ns, b - 1);
             double p;
             if (ta == tb) {
-                const int bs = T.p.gbs / pd.batches / dp;
+                const int bs = bs_total >> (g - tpc);
                 const int key = key_of(T, ta, tpc, bs);
                 if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; return METIS_FATAL_KEY_EXEC; }
-                const double e = T.exec_full[key];
-                if (e == 0.0) return METIS_FATAL_ZERODIV;
-                p = 1. / e;
+                if (T.exec_full[key] == 0.0) return METIS_FATAL_ZERODIV;
+                p = T.inv_exec[key];                          // 1. / profile_cost
             } else {
-                HSplit hs;
-                int rc = partition_data(T, pd.ns, a, b - a, dp, tpc, bs_total, hs, aux);
+                const int rc = hetero_performance(a, b, 1 << (g - tpc), tpc, p);
                 if (rc) return rc;
-                double mx = -INFINITY;
-                for (int r = 0; r < hs.nruns; ++r) {
-                    double c;
-                    if (hs.plus[r] > 0) {
-                        rc = replica_perf_cost(hs.type[r], tpc, hs.base[r] + 1, c);
-                        if (rc) return rc;
-                        if (c > mx) mx = c;
-                    }
-                    if (hs.plus[r] < hs.n[r]) {
-                        rc = replica_perf_cost(hs.type[r], tpc, hs.base[r], c);
-                        if (rc) return rc;
-                        if (c > mx) mx = c;
-                    }
-                }
-                p = (mx != 0.0) ? 1. / mx : 0.0;
             }
             w.perf[s] = p;
             total.add(p);
@@ -507,34 +649,23 @@ struct PlanEvaluator {
         return 0;
     }
 
-    // LayerLoadBalancer._get_stage_memory_demand, one stage (model/load_balancer.py:29-55, quirk Q6)
-    MB_HD_NOINLINE int memory_demand(int s, int a, int b, double &out) {
-        const int la = w.part[s], lb = w.part[s + 1];
-        const int type0 = T.run_type[pd.ns * T.p.num_types];
-        const int tpc = w.tpc[s];
-        double demand = 0.001;
-        if (type_of_rank(T, pd.ns, a) == type_of_rank(T, pd.ns, b - 1)) {
-            const int bs = T.p.gbs / pd.batches / dp_of(s);
-            const int key = key_of(T, type0, tpc, bs);
-            if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; return METIS_FATAL_KEY_MEMORY; }
-            demand += py_sum_range(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
-        } else {
-            HSplit hs;                                       // whole-cluster device list (quirk Q6)
-            const int rc = partition_data(T, pd.ns, 0, T.p.total_devices, dp_of(s), tpc, bs_total, hs, aux);
-            if (rc) return rc;
-            for (int r = 0; r < hs.nruns; ++r)
-                for (int i = 0; i < hs.n[r]; ++i) {
-                    const int h = hs.base[r] + (i < hs.plus[r] ? 1 : 0);
-                    for (int bit = 30; bit >= 0; --bit) {
-                        const int piece = 1 << bit;
-                        if (!(h & piece)) continue;
-                        const int key = key_of(T, type0, tpc, piece);
-                        if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)piece; return METIS_FATAL_KEY_MEMORY; }
-                        demand += py_sum_range(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
-                    }
+    // mixed-type stage of _get_stage_memory_demand (model/load_balancer.py:45-52, quirk Q6)
+    MB_HD_NOINLINE int hetero_memory_demand(int s, int type0, double &demand) {
+        const int la = w.part[s], lb = w.part[s + 1], tpc = w.tpc[s];
+        HSplit hs;                                           // whole-cluster device list (quirk Q6)
+        const int rc = partition_data(T, pd.ns, 0, T.p.total_devices, dp_of(s), tpc, bs_total, hs, aux);
+        if (rc) return rc;
+        for (int r = 0; r < hs.nruns; ++r)
+            for (int i = 0; i < hs.n[r]; ++i) {
+                const int h = hs.base[r] + (i < hs.plus[r] ? 1 : 0);
+                for (int bit = 30; bit >= 0; --bit) {
+                    const int piece = 1 << bit;
+                    if (!(h & piece)) continue;
+                    const int key = key_of(T, type0, tpc, piece);
+                    if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)piece; return METIS_FATAL_KEY_MEMORY; }
+                    demand += py_sum_range(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
                 }
-        }
-        out = demand;
+            }
         return 0;
     }
 
@@ -585,19 +716,30 @@ struct PlanEvaluator {
     }
 
     // One attempt of LayerLoadBalancer.partition_layer (model/load_balancer.py:127-143) after
-    // balance_run: memory demand, OOM test and, when memory is exceeded, the capacity re-weighting.
-    // returns 1 = partition accepted (w.mstate = memory_state), 2 = retry with the adjusted w.perf,
-    // 0 = (None, -1, None), <0 = fatal (negated code).  After the third failed attempt the reference
-    // still evaluates _adj_compute_performance and discards it; that call is skipped here.
+    // balance_run: memory demand (:29-55), OOM test (:57-63) and, when memory is exceeded, the
+    // capacity re-weighting.  returns 1 = partition accepted (w.mstate = memory_state), 2 = retry
+    // with the adjusted w.perf, 0 = (None, -1, None), <0 = fatal (negated code).  After the third
+    // failed attempt the reference still evaluates _adj_compute_performance and discards it; that
+    // call is skipped here.
     MB_HD_NOINLINE int memory_phase(int attempt) {
         const int S = pd.S;
+        const bool one_type = T.p.num_types == 1;
+        const int type0 = T.run_type[pd.ns * T.p.num_types];
         bool oom = false;
         int a = 0;
         for (int s = 0; s < S; ++s) {
-            const int b = a + group(s);
-            double md;
-            const int rc = memory_demand(s, a, b, md);
-            if (rc) return -rc;
+            const int g = w.gcode[s], tpc = w.tpc[s];
+            const int b = a + (1 << g);
+            double md = 0.001;
+            if (one_type || type_of_rank(T, pd.ns, a) == type_of_rank(T, pd.ns, b - 1)) {
+                const int bs = bs_total >> (g - tpc);
+                const int key = key_of(T, type0, tpc, bs);
+                if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; return -METIS_FATAL_KEY_MEMORY; }
+                md += py_sum_range(T.mem + (size_t)key * T.p.lpad, w.part[s], w.part[s + 1]) * kMemCoef;
+            } else {
+                const int rc = hetero_memory_demand(s, type0, md);
+                if (rc) return -rc;
+            }
             const double st = memory_capacity(a, b) - md;
             w.extra[s] = md;
             w.capa[s] = st;
@@ -670,89 +812,115 @@ struct PlanEvaluator {
         return slow;
     }
 
-    // HeteroCostEstimator.get_cost (model/cost_estimator.py:199-244); returns 0 ok, 1 KeyError
+    // mixed-type stage of _get_execution_cost (model/cost_estimator.py:189-197 with :152-173)
+    MB_HD_NOINLINE int hetero_exec_cost(int a, int b, int dp, int tpc, int la, int lb, double &len) {
+        HSplit hs;
+        uint32_t dummy;
+        if (partition_data(T, pd.ns, a, b - a, dp, tpc, bs_total, hs, dummy)) return 1;
+        len = -INFINITY;
+        for (int r = 0; r < hs.nruns; ++r)
+            for (int v = 0; v < 2; ++v) {
+                const int cntv = v ? hs.plus[r] : hs.n[r] - hs.plus[r];
+                const int h = hs.base[r] + v;
+                if (cntv <= 0 || h == 0) continue;
+                double acc = 0.;
+                for (int bit = 30; bit >= 0; --bit) {
+                    const int piece = 1 << bit;
+                    if (!(h & piece)) continue;
+                    if (piece > T.p.max_bs) return 1;            // :166-167
+                    const int key = key_of(T, hs.type[r], tpc, piece);
+                    if (key < 0) return 1;
+                    acc += py_sum_range(T.lc + (size_t)key * T.p.lpad, la, lb);
+                }
+                if (acc > len) len = acc;
+            }
+        return 0;
+    }
+
+    // _get_fb_sync_cost over the device types of ranks [a, b) (model/cost_estimator.py:57-72, quirk Q9)
+    MB_HD int fb_sync_cost(int a, int b, int tpc, int mbs, double &out) const {
+        const int nt = T.p.num_types;
+        const int32_t *end = T.run_end + pd.ns * nt;
+        const uint8_t *typ = T.run_type + pd.ns * nt;
+        double mx = -INFINITY;
+        int lo = 0;
+        for (int k = 0; k < nt; ++k) {
+            const int hi = end[k];
+            if ((a > lo ? a : lo) < (b < hi ? b : hi)) {
+                const int key = key_of(T, typ[k], tpc, mbs);
+                if (key < 0) return 1;
+                const double v = T.fb_sync[key];
+                if (v == 0.0) return 1;                       // falsy -> KeyError
+                if (v > mx) mx = v;
+            }
+            lo = hi;
+        }
+        out = mx;
+        return 0;
+    }
+
+    // HeteroCostEstimator.get_cost (model/cost_estimator.py:199-244); returns 0 ok, 1 KeyError.
+    // x / tp is evaluated as x * 2^-log2(tp) (same real quotient, same rounding); the remaining
+    // quotients come from the derived tables when the cluster has a single bandwidth value.
     MB_HD_NOINLINE int get_cost(double &cost_out) {
         const int per = T.p.devices_per_node;
         const int Lm = T.p.num_layers;
+        const bool one_type = T.p.num_types == 1;
+        const bool ubw = T.p.uniform_bw != 0;
         const int nstage = pd.label < pd.S ? pd.label : pd.S;  // zip(range(plan.num_stage), strategies)
         PySum lens_sum;
         double max_len = -INFINITY, max_upd = -INFINITY, max_dp = -INFINITY;
         double pp_cost = 0., fb_sync = 0.;
         int a = 0;
         for (int s = 0; s < nstage; ++s) {
-            const int b = a + group(s);
+            const int g = w.gcode[s], tpc = w.tpc[s];
+            const int b = a + (1 << g);
             const int la = w.part[s], lb = w.part[s + 1];
-            const int dp = dp_of(s), tpc = w.tpc[s], tp = 1 << tpc;
-            const int ta = type_of_rank(T, pd.ns, a), tb = type_of_rank(T, pd.ns, b - 1);
-            const int mbs = T.p.gbs / dp / pd.batches;
+            const int ldp = g - tpc;
+            const int mbs = bs_total >> ldp;
+            const double inv_tp = pow2_neg(tpc);              // 1 / tp, exact power of two
+            const int ta = one_type ? 0 : type_of_rank(T, pd.ns, a);
+            const int tb = one_type ? 0 : type_of_rank(T, pd.ns, b - 1);
             double len;
             if (ta == tb) {                                   // _get_execution_cost :175-188
                 const int key = key_of(T, ta, tpc, mbs);
                 if (key < 0) return 1;
                 len = py_sum_range(T.lc + (size_t)key * T.p.lpad, la, lb);
-            } else {                                          // :189-197 with :152-173
-                HSplit hs;
-                uint32_t dummy;
-                if (partition_data(T, pd.ns, a, b - a, dp, tpc, bs_total, hs, dummy)) return 1;
-                len = -INFINITY;
-                for (int r = 0; r < hs.nruns; ++r)
-                    for (int v = 0; v < 2; ++v) {
-                        const int cntv = v ? hs.plus[r] : hs.n[r] - hs.plus[r];
-                        const int h = hs.base[r] + v;
-                        if (cntv <= 0 || h == 0) continue;
-                        double acc = 0.;
-                        for (int bit = 30; bit >= 0; --bit) {
-                            const int piece = 1 << bit;
-                            if (!(h & piece)) continue;
-                            if (piece > T.p.max_bs) return 1;            // :166-167
-                            const int key = key_of(T, hs.type[r], tpc, piece);
-                            if (key < 0) return 1;
-                            acc += py_sum_range(T.lc + (size_t)key * T.p.lpad, la, lb);
-                        }
-                        if (acc > len) len = acc;
-                    }
+            } else if (hetero_exec_cost(a, b, 1 << ldp, tpc, la, lb, len)) {
+                return 1;
             }
             lens_sum.add(len);
             if (len > max_len) max_len = len;
 
-            if (s == nstage - 1) {                            // _get_fb_sync_cost :57-72 (quirk Q9)
-                const int nt = T.p.num_types;
-                const int32_t *end = T.run_end + pd.ns * nt;
-                const uint8_t *typ = T.run_type + pd.ns * nt;
-                double mx = -INFINITY;
-                int lo = 0;
-                for (int k = 0; k < nt; ++k) {
-                    const int hi = end[k];
-                    if ((a > lo ? a : lo) < (b < hi ? b : hi)) {
-                        const int key = key_of(T, typ[k], tpc, mbs);
-                        if (key < 0) return 1;
-                        const double v = T.fb_sync[key];
-                        if (v == 0.0) return 1;               // falsy -> KeyError
-                        if (v > mx) mx = v;
-                    }
-                    lo = hi;
-                }
-                fb_sync = mx * (double)pd.batches;
-            } else {                                          // :224-227
+            if (s == nstage - 1) {
+                double v;
+                if (fb_sync_cost(a, b, tpc, mbs, v)) return 1;
+                fb_sync = v * (double)pd.batches;
+            } else if (ubw) {                                 // :224-227 via the derived tables
+                pp_cost += (lb == Lm - 1) ? T.pp_vocab[mbs * T.p.num_tp + tpc] : T.pp_hidden[mbs];
+            } else {
                 double act;
                 if (lb == Lm - 1)
-                    act = (double)((int64_t)mbs * T.p.sequence_length * T.p.vocab_size) / (double)tp;
+                    act = (double)((int64_t)mbs * T.p.sequence_length * T.p.vocab_size) * inv_tp;
                 else
                     act = (double)((int64_t)mbs * T.p.sequence_length * T.p.hidden_size);
                 const int b2 = b + group(s + 1);
-                const double bw = T.p.uniform_bw ? T.bw_first[0] : bw_of_node_range(a / per, (b2 - 1) / per);
-                pp_cost += act / (bw * 1048576.0);
+                pp_cost += act / (bw_of_node_range(a / per, (b2 - 1) / per) * 1048576.0);
             }
             // get_parameter_size_by_stage (model/activation_parameter.py:40-51)
             int ntr = lb - la;
             double params = 0.0;
-            if (la == 0) { params += T.p.input_params / (double)tp; --ntr; }
-            if (lb == Lm) { params += T.p.output_params / (double)tp; --ntr; }
-            params += T.p.transformer_params / (double)tp * (double)ntr;
-            const double bwd = (T.p.uniform_bw ? T.bw_first[0] : dp_bandwidth(a, dp, tp)) * 1048576.0;
-            const double dpc = (double)(2 * (dp - 1)) / ((double)dp * bwd) * params;    // :37-43
+            if (la == 0) { params += T.p.input_params * inv_tp; --ntr; }
+            if (lb == Lm) { params += T.p.output_params * inv_tp; --ntr; }
+            params += T.p.transformer_params * inv_tp * (double)ntr;
+            double dpc;                                       // :37-43
+            if (ubw) dpc = T.dpk[ldp] * params;
+            else {
+                const int dp = 1 << ldp;
+                dpc = (double)(2 * (dp - 1)) / ((double)dp * (dp_bandwidth(a, dp, 1 << tpc) * 1048576.0)) * params;
+            }
             if (dpc > max_dp) max_dp = dpc;
-            const double upd = T.p.optimizer_time / (double)tp * ((double)(lb - la) / (double)Lm);   // :145-147
+            const double upd = T.p.optimizer_time * inv_tp * T.ratio[lb - la];   // :145-147
             if (upd > max_upd) max_upd = upd;
             a = b;
         }
@@ -762,27 +930,21 @@ struct PlanEvaluator {
         return 0;
     }
 
-    MB_HD bool begin(const PlanDesc &plan) {
-        pd = plan;
-        if (pd.S > MAXS || T.p.num_layers > MAXL) return false;
-        bs_total = T.p.gbs / pd.batches;
-        for (int s = 0; s < pd.S; ++s) { w.gcode[s] = pd.row[s]; w.tpc[s] = 0; }
-        return true;
-    }
-
     // cost_het_cluster.py:31-48 for one inter-stage plan, with IntraStagePlanGenerator.has_next
     // (search_space/plan.py:192-226) inlined.  `only_step` >= 0 stops after emitting that step.
     // Sequential form (replay kernel and tests); the search kernel uses search_loop below.
     template <class Sink>
     MB_HD_NOINLINE void run(const PlanDesc &plan, Sink &sink, int only_step = -1) {
-        if (!begin(plan)) { sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0); return; }
+        const int ok = begin(plan);
+        if (ok < 0) { sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0); return; }
+        if (ok == 0) return;
         bool started = false, have_state = false;
         int nrep = 0, step = 0;
         for (;;) {
             if (nrep == 1) return;                            // plan.py:194-195
             int attempt = 0;
             for (;;) {
-                if (!started) started = true;                 // _initial_strategies :231-236
+                if (!started) started = true;                 // first strategy that can be valid (see begin)
                 else if (!next_strategy(have_state)) return;  // :203-204
                 if (!valid()) continue;
                 sink.partition_call();
@@ -821,7 +983,7 @@ MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &s
     enum { NEED_PLAN = 0, ADVANCE = 1, READY_NEW = 2, READY_RETRY = 3, DONE = 4 };
     PlanEvaluator<MAXS, MAXL> ev(T, w);
     int state = NEED_PLAN, attempt = 0, nrep = 0, step = 0;
-    bool started = false, have_state = false;
+    bool have_state = false;
     for (;;) {
         // ---- F ---------------------------------------------------------------------------------
         sink.phase(0);
@@ -831,17 +993,15 @@ MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &s
             const bool got = warp.fetch(need, plan);
             if (need) {
                 if (!got) state = DONE;
-                else if (!ev.begin(plan)) sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0);
-                else { state = ADVANCE; started = false; have_state = false; nrep = 0; step = 0; }
+                else {
+                    const int ok = ev.begin(plan);
+                    if (ok < 0) sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0);
+                    else if (ok == 1) { state = READY_NEW; attempt = 1; have_state = false; nrep = 0; step = 0; }
+                }
             } else if (state == ADVANCE) {
                 if (nrep == 1) state = NEED_PLAN;                         // plan.py:194-195
-                else {
-                    bool alive = true;
-                    if (!started) started = true;                         // _initial_strategies
-                    else alive = ev.next_strategy(have_state);
-                    if (!alive) state = NEED_PLAN;                        // plan.py:203-204
-                    else if (ev.valid()) { state = READY_NEW; attempt = 1; }
-                }
+                else if (!ev.next_strategy(have_state)) state = NEED_PLAN; // plan.py:203-204
+                else if (ev.valid()) { state = READY_NEW; attempt = 1; }
             }
         }
         if (!warp.any(state == READY_NEW || state == READY_RETRY)) break;

@@ -39,7 +39,7 @@ static int arg_fail(const char *what) {
 
 struct BlobLayout {
     uint32_t total;
-    uint32_t key, lc, mem, exec_full, fb, norm, dlay, tmem, bwf, bwm, runt, rune;
+    uint32_t key, lc, mem, exec_full, fb, norm, derived, tmem, bwf, bwm, runt, rune;
 };
 
 static uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -54,7 +54,7 @@ static BlobLayout make_layout(const MetisProblem &p) {
     l.exec_full = o; o = align16(o + (uint32_t)p.num_keys * 8);
     l.fb = o;        o = align16(o + (uint32_t)p.num_keys * 8);
     l.norm = o;      o = align16(o + (uint32_t)p.norm_len * 8);
-    l.dlay = o;      o = align16(o + (uint32_t)p.norm_len * 8);
+    l.derived = o;   o = align16(o + (uint32_t)derived_layout(p).total * 8);
     l.tmem = o;      o = align16(o + (uint32_t)p.num_types * 8);
     l.bwf = o;       o = align16(o + (uint32_t)p.num_types * 8);
     l.bwm = o;       o = align16(o + (uint32_t)p.num_types * 8);
@@ -73,7 +73,7 @@ __device__ __forceinline__ Tables make_tables(const MetisProblem &p, const BlobL
     T.exec_full = reinterpret_cast<const double *>(base + l.exec_full);
     T.fb_sync = reinterpret_cast<const double *>(base + l.fb);
     T.norm_lc = reinterpret_cast<const double *>(base + l.norm);
-    T.dlay = reinterpret_cast<const double *>(base + l.dlay);
+    bind_derived(T, reinterpret_cast<const double *>(base + l.derived));
     T.type_memory = reinterpret_cast<const double *>(base + l.tmem);
     T.bw_first = reinterpret_cast<const double *>(base + l.bwf);
     T.bw_min = reinterpret_cast<const double *>(base + l.bwm);
@@ -101,9 +101,11 @@ __global__ void pack_tables_kernel(MetisProblem p, BlobLayout l, uint8_t *blob) 
     copy_bytes(blob + l.bwm, p.type_bw_min, (uint32_t)p.num_types * 8, tid, nthr);
     copy_bytes(blob + l.runt, p.ns_run_type, (uint32_t)p.num_node_sequences * p.num_types, tid, nthr);
     copy_bytes(blob + l.rune, p.ns_run_end, (uint32_t)p.num_node_sequences * p.num_types * 4, tid, nthr);
-    double *dlay = reinterpret_cast<double *>(blob + l.dlay);
-    for (uint32_t r = tid; r < (uint32_t)p.norm_len; r += nthr)
-        dlay[r] = p.norm_lc[r] / 7.0;                       // tmp_demand = c_demand / hallucination (:191)
+    // derived tables: each entry is one IEEE operation of the reference, evaluated once per launch
+    double *derived = reinterpret_cast<double *>(blob + l.derived);
+    const DerivedLayout d = derived_layout(p);
+    for (uint32_t i = tid; i < (uint32_t)d.total; i += nthr)
+        derived[i] = derive_entry(p, d, p.norm_lc, p.exec_full, p.type_bw_first, (int)i);
 }
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier --------------------------

@@ -26,14 +26,15 @@ Tables host_tables(const MetisProblem &p, std::vector<double> &dlay) {
     T.exec_full = p.exec_full;
     T.fb_sync = p.fb_sync;
     T.norm_lc = p.norm_lc;
-    dlay.resize(p.norm_len);
-    for (int r = 0; r < p.norm_len; ++r) dlay[r] = p.norm_lc[r] / 7.0;
-    T.dlay = dlay.data();
+    const DerivedLayout d = derived_layout(p);
+    dlay.resize(d.total);
+    for (int i = 0; i < d.total; ++i) dlay[i] = derive_entry(p, d, p.norm_lc, p.exec_full, p.type_bw_first, i);
     T.type_memory = p.type_memory;
     T.bw_first = p.type_bw_first;
     T.bw_min = p.type_bw_min;
     T.run_type = p.ns_run_type;
     T.run_end = p.ns_run_end;
+    bind_derived(T, dlay.data());
     return T;
 }
 

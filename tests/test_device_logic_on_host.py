@@ -113,3 +113,33 @@ def test_units_balancer(units):
         got = hs.host_layer_balance([[float.fromhex(x) for x in c['capa']] for c in cases], lc, L)
         for g, c in zip(got, cases):
             assert g == c['part'], c
+
+
+@pytest.mark.parametrize('name', ['c3_homo64_mpl4', 'c4_het128'])
+def test_full_size_spaces_on_host(name, workload_dir):
+    """8.3e4-plan C3 space (all candidates) and the 4.5e6-plan C4 space (reference-sampled ordinals)."""
+    meta, arr = load_golden(name)
+    w, root, digest = workload_dir(name)
+    assert digest == meta['inputs_sha256']
+    problem, space, (rec, det, summary) = _search(meta, root, 'profile', w.num_layers, w.hidden_size,
+                                                  w.sequence_length, w.vocab_size, w.gbs, w.variance,
+                                                  w.max_permute_len, w.max_tp, w.max_bs)
+    assert space.num_plans == meta['counters']['A']
+    assert summary.fatal_ordinal == 2 ** 64 - 1
+    order = np.lexsort((rec['step'], rec['ordinal']))
+    rec, det = rec[order], det[order]
+    if 'sample' in arr:
+        keep = np.isin(rec['ordinal'].astype(np.int64), arr['sample'])
+        rec, det = rec[keep], det[keep]
+    else:
+        c = meta['counters']
+        assert (summary.num_partition_calls, summary.num_balancer_runs, summary.num_records) == (c['B'], c['runs'], c['C'])
+    assert len(rec) == len(arr['cost'])
+    assert (rec['ordinal'].astype(np.int64) == arr['ordinal']).all() and (rec['step'] == arr['step']).all()
+    assert (rec['cost'].view(np.uint64) == arr['cost'].view(np.uint64)).all()
+    assert (rec['num_repartition'] == arr['nrep']).all()
+    S = arr['nstage'].astype(np.int64)
+    for i in range(0, len(rec), max(1, len(rec) // 2000)):          # partitions of a spread of candidates
+        s = int(S[i])
+        assert det[i, 2 * s:3 * s + 1].tolist() == arr['part'][i, :s + 1].tolist()
+        assert (1 << det[i, :s].astype(np.int64)).tolist() == arr['dp'][i, :s].tolist()

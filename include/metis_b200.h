@@ -116,6 +116,8 @@ typedef struct MetisPlanSpace {
     int64_t num_plans;
     int32_t num_blocks;
     int32_t num_div;
+    int32_t max_stage;            /* largest num_stage of any block (sizes the per-plan task state)  */
+    int32_t reserved;
     const MetisPlanBlock *blocks; /* [device] [num_blocks]                                          */
     const int32_t *batches;       /* [device] [num_div] divisors of gbs, descending (plan.py:120-124) */
     const uint8_t *rows;          /* [device]                                                       */
@@ -161,9 +163,10 @@ int metis_abi_version(void);
  */
 void metis_set_profile_events(void *before_kernel, void *after_kernel);
 
-/* Bytes of device scratch the calls below need for `num_plans` plans (workspace argument);
- * metis_het_detail / metis_homo_cost need metis_het_workspace_bytes(problem, 0). */
-int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans);
+/* Bytes of device scratch metis_het_search needs for a shard of `num_plans` plans whose largest
+ * stage count is `max_stage` (task lists of the round scheduler; large spaces are cut into waves so
+ * this stays below ~4.3 GB).  metis_het_detail / metis_homo_cost need metis_het_workspace_bytes(problem, 0, 1). */
+int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans, int32_t max_stage);
 
 /*
  * Replaces the loop of cost_het_cluster.py:24-48 for the shard's plans.
@@ -172,7 +175,7 @@ int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans
  *   detail       [device] optional, capacity * detail_stride bytes: per record
  *                dp code[num_stage], tp code[num_stage] (log2) then layer_partition[num_stage+1]
  *                (uint8 each); detail_stride >= 3*METIS_MAX_STAGES+1, or NULL
- *   workspace    [device] metis_het_workspace_bytes(plans in shard) bytes
+ *   workspace    [device] metis_het_workspace_bytes(problem, plans in shard, space->max_stage) bytes
  *   summary      [host]   filled asynchronously (use pinned memory)
  */
 int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, const MetisShard *shard,

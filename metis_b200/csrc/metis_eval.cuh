@@ -966,82 +966,113 @@ struct PlanEvaluator {
 };
 
 // ---------------------------------------------------------------------------
-// Warp-synchronous search loop: every lane owns one inter-stage plan at a time and the lanes of a
-// warp move through the phases together, so the expensive phases (balance_run, memory check,
-// cost) execute with all lanes busy:
-//   F  fetch / advance: lanes without a ready strategy fetch the next plan or take chain steps
-//      (search_space/plan.py:192-268) until every lane is ready or out of work (cheap, divergent);
-//   P  stage performance of new strategies (model/device_group.py:54-85);
-//   R  LayerComputeBalancer.run (convergent: the forward scan has the same trip count in all lanes);
-//   M  memory demand / OOM / re-weighting (load_balancer.py:127-143); OOM lanes stay ready for R;
-//   C  cost of accepted partitions (cost_estimator.py:199-244) and record emission.
-// `Warp` supplies any(pred) and fetch(need, PlanDesc&) - a warp ballot / aggregated atomic on the
-// device, trivial on the host (tests/hostsim).
+// Round-based search (the search kernel's schedule).
+//
+// The work per inter-stage plan is heavy-tailed: most plans need one LayerComputeBalancer run, a
+// few per cent need 10-36 *sequential* runs (strategy chain x re-partition attempts).  A "task"
+// is therefore one partition attempt of one plan; every round executes all pending tasks, one
+// task per lane, packed densely into warps, and appends the plans that continue to the list of
+// the next round.  Between rounds only a header, the strategy (tp codes) and - for a re-partition
+// attempt - the re-weighted stage performance persist, in [stage][slot] arrays so that a warp
+// reads and writes them coalesced.
+//   begin_task : plan -> first strategy that can be valid (PlanEvaluator::begin)
+//   run_task   : [P stage performance] -> R LayerComputeBalancer.run -> M memory check /
+//                re-weighting -> C cost + record -> advance along the chain (plan.py:192-268)
+// All lanes of a warp walk these steps together; `Warp::append(cont)` is called convergently.
 // ---------------------------------------------------------------------------
+struct TaskBuffers {
+    uint64_t *hdr;      // [cap]            ordinal | step << 32 | attempt << 48 | nrep << 52 | retry << 56
+    uint8_t *tpc;       // [smax][cap]      log2(tp) per stage
+    double *perf;       // [smax][cap]      re-weighted stage performance (retry tasks only)
+    int64_t cap;
+};
+
+MB_HD uint64_t pack_task(uint32_t ordinal, int step, int attempt, int nrep, bool retry) {
+    return (uint64_t)ordinal | ((uint64_t)(step & 0xFFFF) << 32) | ((uint64_t)(attempt & 0xF) << 48) |
+           ((uint64_t)(nrep & 0xF) << 52) | ((uint64_t)(retry ? 1 : 0) << 56);
+}
+
 template <int MAXS, int MAXL, class Sink, class Warp>
-MB_HD_NOINLINE void search_loop(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &warp) {
-    enum { NEED_PLAN = 0, ADVANCE = 1, READY_NEW = 2, READY_RETRY = 3, DONE = 4 };
+MB_HD void begin_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &warp, const TaskBuffers &out,
+                      bool has, const PlanDesc &plan) {
     PlanEvaluator<MAXS, MAXL> ev(T, w);
-    int state = NEED_PLAN, attempt = 0, nrep = 0, step = 0;
-    bool have_state = false;
-    for (;;) {
-        // ---- F ---------------------------------------------------------------------------------
-        sink.phase(0);
-        while (warp.any(state == NEED_PLAN || state == ADVANCE)) {
-            PlanDesc plan;
-            const bool need = (state == NEED_PLAN);
-            const bool got = warp.fetch(need, plan);
-            if (need) {
-                if (!got) state = DONE;
-                else {
-                    const int ok = ev.begin(plan);
-                    if (ok < 0) sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0);
-                    else if (ok == 1) { state = READY_NEW; attempt = 1; have_state = false; nrep = 0; step = 0; }
-                }
-            } else if (state == ADVANCE) {
-                if (nrep == 1) state = NEED_PLAN;                         // plan.py:194-195
-                else if (!ev.next_strategy(have_state)) state = NEED_PLAN; // plan.py:203-204
-                else if (ev.valid()) { state = READY_NEW; attempt = 1; }
-            }
+    bool cont = false;
+    if (has) {
+        const int ok = ev.begin(plan);
+        if (ok < 0) sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0);
+        cont = ok == 1;
+    }
+    const int64_t pos = warp.append(cont);
+    if (cont) {
+        out.hdr[pos] = pack_task(plan.ordinal, 0, 1, 0, false);
+        for (int s = 0; s < plan.S; ++s) out.tpc[(int64_t)s * out.cap + pos] = w.tpc[s];
+    }
+}
+
+template <int MAXS, int MAXL, class Sink, class Warp>
+MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &warp, const TaskBuffers &in,
+                    const TaskBuffers &out, bool has, int64_t pos, const PlanDesc &plan) {
+    PlanEvaluator<MAXS, MAXL> ev(T, w);
+    int step = 0, attempt = 1, nrep = 0;
+    bool retry = false, cont = false, advance = false, have_state = false, costing = false;
+    sink.phase(1);
+    if (has) {                                               // ---- restore, P ----
+        const uint64_t h = in.hdr[pos];
+        step = (int)((h >> 32) & 0xFFFF);
+        attempt = (int)((h >> 48) & 0xF);
+        nrep = (int)((h >> 52) & 0xF);
+        retry = ((h >> 56) & 1) != 0;
+        ev.pd = plan;
+        ev.bs_total = T.p.gbs / plan.batches;
+        ev.nbad = 0;
+        for (int s = 0; s < plan.S; ++s) {
+            w.gcode[s] = plan.row[s];
+            w.tpc[s] = in.tpc[(int64_t)s * in.cap + pos];
         }
-        if (!warp.any(state == READY_NEW || state == READY_RETRY)) break;
-        // ---- P ---------------------------------------------------------------------------------
-        sink.phase(1);
-        if (state == READY_NEW) {
+        if (retry) {
+            for (int s = 0; s < plan.S; ++s) w.perf[s] = in.perf[(int64_t)s * in.cap + pos];
+        } else {
             sink.partition_call();
             const int rc = ev.compute_performance();
-            if (rc) { sink.fatal(ev.pd.ordinal, rc, ev.aux); state = NEED_PLAN; }
-        }
-        // ---- R ---------------------------------------------------------------------------------
-        const bool ready = (state == READY_NEW || state == READY_RETRY);
-        int result = -1000;
-        sink.phase(2);
-        if (ready) {
-            sink.balancer_run();
-            const int rc = balance_run<MAXS, MAXL>(T, ev.pd.S, w);
-            if (rc) { sink.fatal(ev.pd.ordinal, rc, ev.aux); state = NEED_PLAN; }
-            else result = 0;
-        }
-        // ---- M ---------------------------------------------------------------------------------
-        sink.phase(3);
-        if (ready && result == 0) {
-            const int r = ev.memory_phase(attempt);
-            if (r < 0) { sink.fatal(ev.pd.ordinal, -r, ev.aux); state = NEED_PLAN; }
-            else if (r == 2) { state = READY_RETRY; ++attempt; }
-            else if (r == 0) { have_state = false; state = ADVANCE; }     // memory_state = None (:225)
-            else { have_state = true; nrep = attempt; result = 1; }
-        }
-        // ---- C ---------------------------------------------------------------------------------
-        sink.phase(4);
-        if (ready && result == 1) {
-            double cost;
-            if (ev.get_cost(cost) == 0) sink.emit(ev.pd, step, nrep, cost, w.tpc, w.part);
-            else sink.keyerror();
-            ++step;
-            state = ADVANCE;
+            if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
         }
     }
-    sink.phase(5);
+    sink.phase(2);
+    if (has) {                                               // ---- R ----
+        sink.balancer_run();
+        const int rc = balance_run<MAXS, MAXL>(T, plan.S, w);
+        if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
+    }
+    sink.phase(3);
+    if (has) {                                               // ---- M ----
+        const int r = ev.memory_phase(attempt);
+        if (r < 0) { sink.fatal(plan.ordinal, -r, ev.aux); has = false; }
+        else if (r == 2) { cont = true; retry = true; ++attempt; }
+        else if (r == 0) { have_state = false; advance = true; }     // memory_state = None (plan.py:225)
+        else { have_state = true; nrep = attempt; costing = true; }
+    }
+    sink.phase(4);
+    if (has && costing) {                                    // ---- C ----
+        double cost;
+        if (ev.get_cost(cost) == 0) sink.emit(plan, step, nrep, cost, w.tpc, w.part);
+        else sink.keyerror();
+        ++step;
+        advance = nrep != 1;                                 // plan.py:194-195
+    }
+    sink.phase(0);
+    if (has && advance) {                                    // ---- chain (plan.py:197-206) ----
+        for (;;) {
+            if (!ev.next_strategy(have_state)) break;        // :203-204
+            if (ev.valid()) { cont = true; retry = false; attempt = 1; break; }
+        }
+    }
+    const int64_t opos = warp.append(has && cont);
+    if (has && cont) {
+        out.hdr[opos] = pack_task(plan.ordinal, step, attempt, nrep, retry);
+        for (int s = 0; s < plan.S; ++s) out.tpc[(int64_t)s * out.cap + opos] = w.tpc[s];
+        if (retry)
+            for (int s = 0; s < plan.S; ++s) out.perf[(int64_t)s * out.cap + opos] = w.perf[s];
+    }
 }
 
 // ---------------------------------------------------------------------------

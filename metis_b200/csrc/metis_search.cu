@@ -12,11 +12,14 @@
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no FMA contraction: parity).
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
 #include "metis_eval.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace metis {
 
@@ -226,56 +229,40 @@ struct DeviceSink {
     }
 };
 
-// Warp-level services of search_loop: ballots and an aggregated fetch of plan indices from the
-// launch-wide counter (one atomicAdd per warp per round, popc-ranked inside the warp).
+// Warp-level services of begin_task / run_task: ballot + one aggregated atomicAdd per warp hands
+// out consecutive slots of the next round's task list (so the state stores are coalesced).
 struct DeviceWarp {
-    const MetisPlanSpace &sp;
-    const MetisShard sh;
-    unsigned long long *counter;
-    long long slots;
-    int cur_block;
-    __device__ DeviceWarp(const MetisPlanSpace &s, const MetisShard &h, unsigned long long *c, long long n)
-        : sp(s), sh(h), counter(c), slots(n), cur_block(0) {}
-    __device__ bool any(bool p) const { return __any_sync(0xFFFFFFFFu, p); }
-    __device__ bool fetch(bool need, PlanDesc &pd) {
+    unsigned int *counter;
+    __device__ explicit DeviceWarp(unsigned int *c) : counter(c) {}
+    __device__ int64_t append(bool want) const {
         const unsigned full = 0xFFFFFFFFu;
-        const unsigned m = __ballot_sync(full, need);
-        if (m == 0) return false;
+        const unsigned m = __ballot_sync(full, want);
+        if (m == 0) return -1;
         const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
         base = __shfl_sync(full, base, leader);
-        if (!need) return false;
-        const long long i = (long long)base + __popc(m & ((1u << lane) - 1u));
-        if (i >= slots) return false;
-        const long long ordinal = ((i / sh.tile) * sh.world + sh.rank) * sh.tile + (i % sh.tile);
-        if (ordinal >= sp.num_plans) return false;
-        // plans are handed out in increasing order: walk forward from the block of the previous plan
-        int b = cur_block;
-        while (b + 1 < sp.num_blocks && __ldg(&sp.blocks[b + 1].first_ordinal) <= ordinal) ++b;
-        cur_block = b;
-        const MetisPlanBlock blk = sp.blocks[b];
-        const uint32_t rel = (uint32_t)(ordinal - blk.first_ordinal);
-        const uint32_t row = rel / (uint32_t)sp.num_div;
-        pd.ordinal = (uint32_t)ordinal;
-        pd.ns = blk.ns_idx;
-        pd.S = blk.num_stage;
-        pd.label = blk.label_stage;
-        pd.batches = __ldg(&sp.batches[rel - row * (uint32_t)sp.num_div]);
-        pd.row = sp.rows + blk.rows_offset + (size_t)row * blk.num_stage;
-        return true;
+        return (int64_t)base + __popc(m & ((1u << lane) - 1u));
     }
+};
+
+struct RoundBuffers {
+    TaskBuffers buf[2];
+    unsigned int *counts;      // [3] rotating task counters
+    long long wave;            // plans admitted per wave (= capacity of the task lists)
 };
 
 template <int MAXS, int MAXL>
 __global__ void __launch_bounds__(kThreads)
 het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                   const MetisShard sh, const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob,
-                  const int use_smem, const long long slots, const __grid_constant__ DeviceOut out) {
+                  const int use_smem, const long long slots, const __grid_constant__ DeviceOut out,
+                  const __grid_constant__ RoundBuffers rb) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
     __shared__ double s_cost[kThreads / 32];
     __shared__ uint32_t s_ord[kThreads / 32], s_step[kThreads / 32], s_meta[kThreads / 32];
+    cg::grid_group grid = cg::this_grid();
 
     const uint8_t *base = blob;
     if (use_smem) {
@@ -287,8 +274,50 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
     DeviceSink sink(out);
     {
         Scratch<MAXS, MAXL> w;
-        DeviceWarp warp(sp, sh, &out.counters[5], slots);
-        search_loop<MAXS, MAXL>(T, w, sink, warp);
+        const int lane = threadIdx.x & 31;
+        const long long gwarp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+        const long long nwarps = (long long)gridDim.x * (kThreads / 32);
+        unsigned int round = 0;                              // global round counter (rotates the 3 counters)
+        for (long long wave0 = 0; wave0 < slots; wave0 += rb.wave) {
+            const long long wave1 = wave0 + rb.wave < slots ? wave0 + rb.wave : slots;
+            // ---- admission: every plan of the wave -> first strategy that can be valid ----------
+            sink.phase(0);
+            {
+                DeviceWarp warp(&rb.counts[(round + 1) % 3]);
+                if (blockIdx.x == 0 && threadIdx.x == 0) rb.counts[(round + 2) % 3] = 0;
+                for (long long b0 = wave0 + gwarp * 32; b0 < wave1; b0 += nwarps * 32) {
+                    const long long i = b0 + lane;
+                    PlanDesc pd;
+                    bool has = false;
+                    if (i < wave1) {
+                        const long long ordinal = ((i / sh.tile) * sh.world + sh.rank) * sh.tile + (i % sh.tile);
+                        has = decode_plan(sp, ordinal, pd);
+                    }
+                    begin_task<MAXS, MAXL>(T, w, sink, warp, rb.buf[(round + 1) & 1], has, pd);
+                }
+            }
+            grid.sync();
+            ++round;
+            // ---- rounds: one partition attempt per pending plan --------------------------------
+            for (;;) {
+                const unsigned int n = *(volatile unsigned int *)&rb.counts[round % 3];
+                if (n == 0) break;
+                DeviceWarp warp(&rb.counts[(round + 1) % 3]);
+                if (blockIdx.x == 0 && threadIdx.x == 0) rb.counts[(round + 2) % 3] = 0;
+                const TaskBuffers &in = rb.buf[round & 1], &nxt = rb.buf[(round + 1) & 1];
+                for (long long b0 = gwarp * 32; b0 < (long long)n; b0 += nwarps * 32) {
+                    const long long pos = b0 + lane;
+                    PlanDesc pd;
+                    bool has = false;
+                    if (pos < (long long)n) has = decode_plan(sp, (uint32_t)in.hdr[pos], pd);
+                    run_task<MAXS, MAXL>(T, w, sink, warp, in, nxt, has, pos, pd);
+                }
+                grid.sync();
+                ++round;
+            }
+            // counts[round % 3] is 0 here and becomes this wave's successor "previous" counter; the
+            // admission of the next wave appends to counts[(round+1) % 3], which was zeroed one round ago
+        }
     }
 
 #ifdef METIS_PROFILE_PHASES
@@ -473,18 +502,37 @@ static int64_t shard_plan_slots(int64_t num_plans, const MetisShard *sh) {
     return rounds * tile;
 }
 
-int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans) {
+constexpr int64_t kFixedWs = 4096;                 // summary + counters + round counters
+constexpr int64_t kMaxBlocks = 4096;               // per-block best records
+constexpr int64_t kRoundBudget = 4LL << 30;        // bytes of task-list storage before the space is cut into waves
+
+static int64_t task_slot_bytes(int max_stage) { return 8 + (int64_t)max_stage + 8 * (int64_t)max_stage; }
+
+static int64_t wave_size(int64_t slots, int max_stage) {
+    int64_t cap = kRoundBudget / (2 * task_slot_bytes(max_stage));
+    cap &= ~(int64_t)127;
+    if (cap < 65536) cap = 65536;
+    if (cap > slots) cap = (slots + 127) & ~(int64_t)127;
+    return cap < 128 ? 128 : cap;
+}
+
+int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans, int32_t max_stage) {
     if (check_problem(problem)) return METIS_E_ARG;
+    if (max_stage < 1) max_stage = 1;
+    if (max_stage > METIS_MAX_STAGES) max_stage = METIS_MAX_STAGES;
     const BlobLayout lay = make_layout(*problem);
-    const int64_t nblocks = (num_plans + kThreads - 1) / kThreads + 64;
-    return 4096 + (int64_t)align16(lay.total) + nblocks * (int64_t)sizeof(MetisRecord) + 256;
+    const int64_t cap = wave_size(num_plans, max_stage);
+    return 256 + kFixedWs + (int64_t)align16(lay.total) + kMaxBlocks * (int64_t)sizeof(MetisRecord) +
+           2 * cap * task_slot_bytes(max_stage) + 1024;
 }
 
 struct Workspace {
     MetisSearchSummary *summary;
     unsigned long long *counters;
+    unsigned int *round_counts;
     uint8_t *blob;
     MetisRecord *block_best;
+    uint8_t *tasks;
 };
 
 static Workspace carve(void *ws, const BlobLayout &lay) {
@@ -494,9 +542,20 @@ static Workspace carve(void *ws, const BlobLayout &lay) {
     Workspace w;
     w.summary = reinterpret_cast<MetisSearchSummary *>(b);
     w.counters = reinterpret_cast<unsigned long long *>(b + 1024);
-    w.blob = b + 2048;
-    w.block_best = reinterpret_cast<MetisRecord *>(b + 2048 + align16(lay.total));
+    w.round_counts = reinterpret_cast<unsigned int *>(b + 2048);
+    w.blob = b + kFixedWs;
+    w.block_best = reinterpret_cast<MetisRecord *>(b + kFixedWs + align16(lay.total));
+    w.tasks = reinterpret_cast<uint8_t *>(w.block_best + kMaxBlocks);
     return w;
+}
+
+static TaskBuffers carve_tasks(uint8_t *&p, int64_t cap, int max_stage) {
+    TaskBuffers t;
+    t.cap = cap;
+    t.hdr = reinterpret_cast<uint64_t *>(p);   p += cap * 8;
+    t.perf = reinterpret_cast<double *>(p);    p += cap * 8 * (int64_t)max_stage;
+    t.tpc = p;                                 p += cap * (int64_t)max_stage;
+    return t;
 }
 
 int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, const MetisShard *shard,
@@ -508,19 +567,18 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     if (shard->world < 1 || shard->rank < 0 || shard->rank >= shard->world || shard->tile < 32 || shard->tile % 32)
         return arg_fail("bad shard (tile must be a positive multiple of 32)");
     if (space->num_plans > 0xFFFFFFF0LL) return arg_fail("more than 2^32 plans");
+    if (space->max_stage < 1 || space->max_stage > METIS_MAX_STAGES) return arg_fail("max_stage out of range (METIS_MAX_STAGES)");
     if (detail && detail_stride < 3 * METIS_MAX_STAGES + 1) return arg_fail("detail_stride too small");
     if (capacity < 0 || (capacity > 0 && !records)) return arg_fail("records/capacity mismatch");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const BlobLayout lay = make_layout(*problem);
     const int64_t slots = shard_plan_slots(space->num_plans, shard);
-    const int64_t nblocks = (slots + kThreads - 1) / kThreads;
-    const int64_t need = 4096 + (int64_t)align16(lay.total) + (nblocks + 1) * (int64_t)sizeof(MetisRecord);
+    const int64_t need = metis_het_workspace_bytes(problem, slots, space->max_stage);
     if (workspace_bytes < need) { snprintf(g_err, sizeof(g_err), "workspace too small: need %lld", (long long)need); return METIS_E_CAPACITY; }
-    if (nblocks > 0x7FFFFFFFLL) return arg_fail("too many blocks");
     const Workspace ws = carve(workspace, lay);
 
     cudaError_t e;
-    e = cudaMemsetAsync(ws.counters, 0, 16 * sizeof(unsigned long long), stream);
+    e = cudaMemsetAsync(ws.counters, 0, 2048, stream);       // counters + round counters
     if (e != cudaSuccess) return cuda_fail(e, "memset counters");
     e = cudaMemsetAsync(ws.counters + 4, 0xFF, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset fatal key");
@@ -528,8 +586,8 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "pack_tables_kernel");
 
-    const int use_smem = lay.total <= (uint32_t)kSmemBlobMax;
-    const size_t dyn = use_smem ? lay.total : 0;
+    int use_smem = lay.total <= (uint32_t)kSmemBlobMax;
+    size_t dyn = use_smem ? lay.total : 0;
     auto kern = het_search_kernel<kMaxS, kMaxL>;
     if (dyn > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -538,24 +596,37 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     DeviceOut out;
     out.records = records; out.capacity = capacity; out.detail = detail; out.detail_stride = detail_stride;
     out.counters = ws.counters; out.block_best = ws.block_best;
-    // persistent grid: one wave of resident blocks, plans are fetched from a launch-wide counter
+    RoundBuffers rb;
+    uint8_t *tp = ws.tasks;
+    rb.wave = wave_size(slots, space->max_stage);
+    rb.buf[0] = carve_tasks(tp, rb.wave, space->max_stage);
+    rb.buf[1] = carve_tasks(tp, rb.wave, space->max_stage);
+    rb.counts = ws.round_counts;
+    // cooperative persistent grid: every block is resident, rounds are separated by grid.sync()
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, dyn);
     if (e != cudaSuccess || per_sm < 1 || sms < 1) return cuda_fail(e, "occupancy query");
-    const int64_t resident = (int64_t)sms * per_sm;
-    const int64_t grid = nblocks < resident ? nblocks : resident;
-    if (nblocks > 0) {
+    int64_t grid = (int64_t)sms * per_sm;
+    const int64_t useful = (slots + kThreads - 1) / kThreads;
+    if (grid > useful) grid = useful;
+    if (grid > kMaxBlocks) grid = kMaxBlocks;
+    if (slots > 0) {
+        MetisProblem p_arg = *problem;
+        MetisPlanSpace s_arg = *space;
+        MetisShard sh_arg = *shard;
+        BlobLayout lay_arg = lay;
+        const uint8_t *blob_arg = ws.blob;
+        long long slots_arg = slots;
+        void *args[] = {&p_arg, &s_arg, &sh_arg, &lay_arg, &blob_arg, &use_smem, &slots_arg, &out, &rb};
         if (g_ev_before) cudaEventRecord(g_ev_before, stream);
-        kern<<<(unsigned)grid, kThreads, dyn, stream>>>(*problem, *space, *shard, lay, ws.blob, use_smem,
-                                                        (long long)slots, out);
-        e = cudaGetLastError();
+        e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(kThreads), args, dyn, stream);
         if (g_ev_after) cudaEventRecord(g_ev_after, stream);
         g_ev_before = g_ev_after = nullptr;
-        if (e != cudaSuccess) return cuda_fail(e, "het_search_kernel");
+        if (e != cudaSuccess) return cuda_fail(e, "het_search_kernel (cooperative launch)");
     }
-    het_finalize_kernel<<<1, 256, 0, stream>>>(ws.block_best, (int)(nblocks > 0 ? grid : 0), ws.counters, ws.summary);
+    het_finalize_kernel<<<1, 256, 0, stream>>>(ws.block_best, (int)(slots > 0 ? grid : 0), ws.counters, ws.summary);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "het_finalize_kernel");
     e = cudaMemcpyAsync(summary, ws.summary, sizeof(MetisSearchSummary), cudaMemcpyDeviceToHost, stream);
@@ -571,7 +642,7 @@ int metis_het_detail(const MetisProblem *problem, const MetisPlanSpace *space, c
     if (detail_stride < 3 * METIS_MAX_STAGES + 1) return arg_fail("detail_stride too small");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const BlobLayout lay = make_layout(*problem);
-    if (workspace_bytes < 4096 + (int64_t)align16(lay.total)) return METIS_E_CAPACITY;
+    if (workspace_bytes < 256 + kFixedWs + (int64_t)align16(lay.total)) return METIS_E_CAPACITY;
     const Workspace ws = carve(workspace, lay);
     pack_tables_kernel<<<8, 256, 0, stream>>>(*problem, lay, ws.blob);
     if (n > 0) {
@@ -592,7 +663,7 @@ int metis_homo_cost(const MetisProblem *problem, int32_t type_id, const int32_t 
     if (type_id < 0 || type_id >= problem->num_types) return arg_fail("type_id out of range");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const BlobLayout lay = make_layout(*problem);
-    if (workspace_bytes < 4096 + (int64_t)align16(lay.total)) return METIS_E_CAPACITY;
+    if (workspace_bytes < 256 + kFixedWs + (int64_t)align16(lay.total)) return METIS_E_CAPACITY;
     const Workspace ws = carve(workspace, lay);
     pack_tables_kernel<<<8, 256, 0, stream>>>(*problem, lay, ws.blob);
     if (n > 0) {

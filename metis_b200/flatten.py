@@ -221,6 +221,7 @@ class FlatPlanSpace:
         s.num_plans = self.num_plans
         s.num_blocks = len(self.blocks)
         s.num_div = len(self.batches)
+        s.max_stage = int(self.blocks['num_stage'].max()) if len(self.blocks) else 1
         s.blocks = ptr_of('blocks')
         s.batches = ptr_of('batches')
         s.rows = ptr_of('rows')

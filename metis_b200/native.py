@@ -46,6 +46,7 @@ class MetisPlanBlock(C.Structure):
 
 class MetisPlanSpace(C.Structure):
     _fields_ = [('num_plans', C.c_int64), ('num_blocks', C.c_int32), ('num_div', C.c_int32),
+                ('max_stage', C.c_int32), ('reserved', C.c_int32),
                 ('blocks', C.c_void_p), ('batches', C.c_void_p), ('rows', C.c_void_p)]
 
 
@@ -97,7 +98,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.metis_set_profile_events.restype = None
     lib.metis_set_profile_events.argtypes = [C.c_void_p, C.c_void_p]
     lib.metis_het_workspace_bytes.restype = C.c_int64
-    lib.metis_het_workspace_bytes.argtypes = [C.POINTER(MetisProblem), C.c_int64]
+    lib.metis_het_workspace_bytes.argtypes = [C.POINTER(MetisProblem), C.c_int64, C.c_int32]
     lib.metis_het_search.restype = C.c_int
     lib.metis_het_search.argtypes = [C.POINTER(MetisProblem), C.POINTER(MetisPlanSpace), C.POINTER(MetisShard),
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,

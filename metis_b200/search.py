@@ -59,7 +59,7 @@ class DeviceProblem:
         self.s_struct = self.space.as_struct(lambda n: self._dev[n].data_ptr())
 
     def workspace_bytes(self, num_plans: int) -> int:
-        n = self.lib.metis_het_workspace_bytes(C.byref(self.p_struct), num_plans)
+        n = self.lib.metis_het_workspace_bytes(C.byref(self.p_struct), num_plans, self.s_struct.max_stage)
         if n < 0:
             native.check(int(n), 'metis_het_workspace_bytes')
         return int(n)
@@ -257,7 +257,7 @@ def homo_costs(problem: flatten.FlatProblem, type_id: int, plans: np.ndarray, de
         tens = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.uint8).reshape(-1).copy()).to(dev)
                 for k, v in problem.arrays.items()}
         p = problem.as_struct(lambda n: tens[n].data_ptr())
-        ws = torch.empty(int(lib.metis_het_workspace_bytes(C.byref(p), 0)), dtype=torch.uint8, device=dev)
+        ws = torch.empty(int(lib.metis_het_workspace_bytes(C.byref(p), 0, 1)), dtype=torch.uint8, device=dev)
         n = len(plans)
         d_plans = torch.from_numpy(np.ascontiguousarray(plans, dtype=np.int32).reshape(-1)).to(dev)
         cost = torch.zeros(max(n, 1), dtype=torch.float64, device=dev)

@@ -118,22 +118,35 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
             PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> ev(T, w);
             ev.run(pd, sink);
         }
-    } else {                              // the search kernel's state machine with a one-lane "warp"
+    } else {                              // the search kernel's round schedule with one-lane "warps"
         struct HostWarp {
-            const MetisPlanSpace *sp; const MetisShard *sh; int64_t next, slots;
-            bool any(bool p) const { return p; }
-            bool fetch(bool need, PlanDesc &pd) {
-                if (!need) return false;
-                while (next < slots) {
-                    const int64_t i = next++;
-                    const int64_t ordinal = ((i / sh->tile) * sh->world + sh->rank) * sh->tile + (i % sh->tile);
-                    if (ordinal >= sp->num_plans) return false;
-                    if (decode(*sp, ordinal, pd)) return true;
-                }
-                return false;
+            int64_t *count;
+            int64_t append(bool want) const { return want ? (*count)++ : -1; }
+        };
+        const int smax = sp->max_stage > 0 ? sp->max_stage : METIS_MAX_STAGES;
+        const int64_t cap = rounds * tile > 0 ? rounds * tile : 1;
+        std::vector<uint64_t> hdr[2] = {std::vector<uint64_t>(cap), std::vector<uint64_t>(cap)};
+        std::vector<uint8_t> tpc[2] = {std::vector<uint8_t>(cap * smax), std::vector<uint8_t>(cap * smax)};
+        std::vector<double> perf[2] = {std::vector<double>(cap * smax), std::vector<double>(cap * smax)};
+        TaskBuffers buf[2];
+        for (int k = 0; k < 2; ++k) buf[k] = TaskBuffers{hdr[k].data(), tpc[k].data(), perf[k].data(), cap};
+        int64_t n = 0;
+        HostWarp warp{&n};
+        for (int64_t i = 0; i < rounds * tile; ++i) {
+            const int64_t ordinal = ((i / tile) * world + sh->rank) * tile + (i % tile);
+            PlanDesc pd;
+            const bool has = decode(*sp, ordinal, pd);
+            begin_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, warp, buf[0], has, pd);
+        }
+        for (int r = 0; n > 0; ++r) {
+            const int64_t cur = n;
+            n = 0;
+            for (int64_t pos = 0; pos < cur; ++pos) {
+                PlanDesc pd;
+                const bool has = decode(*sp, (uint32_t)buf[r & 1].hdr[pos], pd);
+                run_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, warp, buf[r & 1], buf[(r + 1) & 1], has, pos, pd);
             }
-        } warp{sp, sh, 0, rounds * tile};
-        search_loop<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, warp);
+        }
     }
     return 0;
 }

@@ -150,7 +150,8 @@ typedef struct MetisShard {
     int32_t rank;                 /* 0 <= rank < world                                              */
     int32_t world;
     int32_t tile;                 /* plans per interleave tile (multiple of 32)                     */
-    int32_t reserved;
+    int32_t reserved;             /* tuning: rounds with fewer than reserved x (resident warps) pending
+                                     tasks run one task per warp; 0 = default                        */
 } MetisShard;
 
 const char *metis_last_error(void);

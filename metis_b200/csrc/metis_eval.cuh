@@ -113,6 +113,23 @@ struct PlanDesc {
     const uint8_t *row;  // log2(group size) per stage
 };
 
+// Execution policies.  `Serial`: one thread owns the task (host, replay kernel, and the throughput
+// mode of the search kernel where the 32 lanes of a warp hold 32 different tasks).  A cooperative
+// policy (metis_search.cu: WarpLanes) has all lanes of a warp work on ONE task whose scratch lives in
+// shared memory: loops over independent elements are strided over the lanes (lane()/width(), then
+// sync()), everything else is executed redundantly by every lane on identical data.
+struct Serial {
+    static constexpr bool kUniform = false;
+    MB_HD int lane() const { return 0; }
+    MB_HD int width() const { return 1; }
+    MB_HD void sync() const {}
+};
+struct SerialUniform : Serial {           // tests: the code paths of the cooperative mode, one lane
+    static constexpr bool kUniform = true;
+};
+
+constexpr uint64_t kOnes = 0x0101010101010101ULL;
+
 constexpr uint16_t kBroke = 0x8000;   // stage closed because a sub-layer did not fit (that sub-layer is skipped)
 constexpr uint16_t kTaken = 0x4000;   // that skipped sub-layer was taken by the backward pass
 constexpr uint16_t kPos = 0x3FFF;
@@ -129,13 +146,14 @@ struct Scratch {
     uint16_t fe[MAXS];     // end of the stage's forward interval in sub-layers | kBroke | kTaken
     uint16_t first[MAXS], lastl[MAXS], cnt[MAXS];   // real layers owned by each stage
     uint16_t part[MAXS + 1];
+    uint16_t rs[MAXS + 1]; // first rank of each stage (prefix sum of the group sizes)
     uint8_t gcode[MAXS];   // log2(device group size)
     uint8_t tpc[MAXS];     // log2(tp)
     uint8_t lstk[MAXS];    // stage on which the skipped sub-layer of stage s was placed
     uint8_t got[MAXS];     // stage received a leftover sub-layer
     uint8_t blk[kBlock];   // stage of each leftover of the middle block
     uint8_t owner[MAXL];   // stage owning each real layer after the majority vote
-    uint8_t sub[MAXL * kH + 8];   // stage of each sub-layer below the backward tail
+    uint64_t subw[MAXL];   // per real layer: byte q = stage of sub-layer 7r+q (below the backward tail)
 };
 
 // ---------------------------------------------------------------------------
@@ -222,8 +240,22 @@ MB_HD bool fwd_nonempty(const Scratch<MAXS, MAXL> &w, int s) {
     return (int)(w.fe[s] & kPos) > fwd_start(w, s);
 }
 
-template <int MAXS, int MAXL>
-MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
+MB_HD void sub_store(uint64_t *subw, int j, int stage) {
+    reinterpret_cast<uint8_t *>(subw)[(j / kH) * 8 + (j % kH)] = (uint8_t)stage;
+}
+
+// number of bytes of x (bytes 0..6) equal to c
+MB_HD int swar_count(uint64_t x, int c) {
+    const uint64_t y = x ^ ((uint64_t)c * kOnes);
+    const uint64_t lo7 = 0x7F7F7F7F7F7F7F7FULL;
+    const uint64_t t = ~((((y & lo7) + lo7) | y) | lo7) & 0x0080808080808080ULL;   // 0x80 where a byte of y is 0
+    int n = 0;
+    for (uint64_t v = t; v; v &= v - 1) ++n;
+    return n;
+}
+
+template <int MAXS, int MAXL, class X>
+MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x) {
     const int L = T.p.num_layers;
     if (T.p.norm_len < L) return METIS_FATAL_INDEX;       // expand_lc_demand[layer_id] IndexError (:219/:238)
     const double *dlay = T.dlay;
@@ -232,7 +264,8 @@ MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
     const int lim = (N - 1 - kH) > 0 ? (N - 1 - kH) : 0;   // :218
     const int last = S - 1;
 
-    for (int s = 0; s < S; ++s) { w.capa[s] = w.perf[s]; w.got[s] = 0; w.cnt[s] = 0; }
+    for (int s = x.lane(); s < S; s += x.width()) { w.capa[s] = w.perf[s]; w.got[s] = 0; w.cnt[s] = 0; }
+    x.sync();
 
     // ---- forward pass (:216-231): flat scan, layer by layer, 7 sub-layers each -----------------
     int k = 0, sTop = -1;
@@ -240,16 +273,25 @@ MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
     if (S > 1) {
         int s = 0, j = 0;
         double c = w.capa[0];
+        uint8_t *subb = reinterpret_cast<uint8_t *>(w.subw);
         for (int r = 0; r + 1 < L; ++r) {
             const double d = dlay[r];
             const int nsub = (r == L - 2) ? kH - 1 : kH;     // the last 8 sub-layers are reserved
+            if (X::kUniform && nsub == kH && s < last && c > 9.0 * d) {
+                // whole layer fits with room to spare: the seven compare-and-subtract steps all take
+                // the "fits" branch (c - 7d > d even after rounding), so only the subtractions remain
+                c -= d; c -= d; c -= d; c -= d; c -= d; c -= d; c -= d;
+                w.subw[r] = (uint64_t)s * kOnes;
+                j += kH;
+                continue;
+            }
 #pragma unroll
             for (int q = 0; q < kH; ++q) {
                 if (q < nsub) {
                     if (s < last) {
                         if (c > d) {
                             c -= d;
-                            w.sub[j] = (uint8_t)s;
+                            subb[r * 8 + q] = (uint8_t)s;
                         } else {                                 // sub-layer j does not fit: skipped, stage closes
                             w.capa[s] = c;
                             w.fe[s] = (uint16_t)(j | kBroke);
@@ -326,7 +368,7 @@ MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
         w.capa[pick] -= dlay[j / kH];
         w.lstk[s] = (uint8_t)pick;
         w.got[pick] = 1;
-        w.sub[j] = (uint8_t)pick;
+        sub_store(w.subw, j, pick);
     }
     if (m - k > Scratch<MAXS, MAXL>::kBlock) return METIS_FATAL_SCRATCH;
     {
@@ -355,41 +397,51 @@ MB_HD_NOINLINE int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
             w.capa[pick] -= dlay[j / kH];
             w.blk[t] = (uint8_t)pick;
             if (pick != last) below = pick;
-            w.sub[j] = (uint8_t)pick;
+            sub_store(w.subw, j, pick);
         }
     }
 
-    // ---- majority vote back to real layers (:290-308) + first / last / count per stage ---------
-    for (int r = 0; r < L; ++r) {
-        const int j0 = kH * r;
+    // ---- majority vote back to real layers (:290-308) ------------------------------------------
+    // A stage holding >= 4 of a layer's 7 sub-layers holds the middle one or one of the first
+    // three, so at most four candidates are counted (SWAR byte compare on the packed layer word).
+    x.sync();
+    for (int r = x.lane(); r < L; r += x.width()) {
+        const int nlow = m - kH * r;                         // sub-layers of r below the backward tail
         int own;
-        if (j0 >= m) {
+        if (nlow <= 0) {
             own = last;
         } else {
-            int st[kH];
-#pragma unroll
-            for (int q = 0; q < kH; ++q) st[q] = (j0 + q >= m) ? last : (int)w.sub[j0 + q];
-            int cand = st[0], votes = 1;                     // Boyer-Moore candidate, then exact count
-#pragma unroll
-            for (int q = 1; q < kH; ++q) {
-                if (votes == 0) { cand = st[q]; votes = 1; }
-                else if (st[q] == cand) ++votes;
-                else --votes;
+            uint64_t v = w.subw[r];
+            if (nlow < kH) {
+                const uint64_t mask = (1ULL << (8 * nlow)) - 1ULL;
+                v = (v & mask) | (((uint64_t)last * kOnes) & ~mask);
             }
-            int n = 0;
-#pragma unroll
-            for (int q = 0; q < kH; ++q) n += (st[q] == cand);
-            own = (2 * n > kH) ? cand : (int)kDropped;       // count > hallucination / 2 (:295)
+            v |= 0xFF00000000000000ULL;
+            const int c3 = (int)((v >> 24) & 0xFF);
+            own = kDropped;
+            if (swar_count(v, c3) * 2 > kH) own = c3;         // count > hallucination / 2 (:295)
+            else {
+                const int c0 = (int)(v & 0xFF), c1 = (int)((v >> 8) & 0xFF), c2 = (int)((v >> 16) & 0xFF);
+                if (swar_count(v, c0) * 2 > kH) own = c0;
+                else if (c1 != c0 && swar_count(v, c1) * 2 > kH) own = c1;
+                else if (c2 != c1 && c2 != c0 && swar_count(v, c2) * 2 > kH) own = c2;
+            }
         }
         w.owner[r] = (uint8_t)own;
+    }
+    x.sync();
+    for (int r = 0; r < L; ++r) {                            // first / last / count of layers per stage
+        const int own = w.owner[r];
         if (own != (int)kDropped) {
             if (w.cnt[own] == 0) w.first[own] = (uint16_t)r;
             w.lastl[own] = (uint16_t)r;
             ++w.cnt[own];
         }
     }
-    for (int s = 0; s < S; ++s)                              // :300-306
+    x.sync();
+    for (int s = x.lane(); s < S; s += x.width())            // :300-306
         w.capa[s] = w.cnt[s] ? w.perf[s] - py_sum_range(lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
+    x.sync();
 
     // ---- boundary adjustment (:310-356): at most three committed single-layer moves ---------
     for (int n = 1; n <= 3; ++n) {
@@ -496,16 +548,18 @@ MB_HD_NOINLINE int partition_data(const Tables &T, int ns, int rank_lo, int coun
 //   void fatal(uint32_t ordinal, int code, uint32_t aux);
 //   void emit(const PlanDesc&, int step, int nrep, double cost, const uint8_t *tpc, const uint16_t *part);
 
-template <int MAXS, int MAXL>
+template <int MAXS, int MAXL, class X = Serial>
 struct PlanEvaluator {
     const Tables &T;
     Scratch<MAXS, MAXL> &w;
+    X x;
     PlanDesc pd;
     int bs_total;         // gbs // batches
     int nbad;             // stages of the current strategy that violate _is_valid_strategies
     uint32_t aux;
 
-    MB_HD PlanEvaluator(const Tables &t, Scratch<MAXS, MAXL> &s) : T(t), w(s), bs_total(0), nbad(0), aux(0) {}
+    MB_HD PlanEvaluator(const Tables &t, Scratch<MAXS, MAXL> &s, const X &lanes = X())
+        : T(t), w(s), x(lanes), bs_total(0), nbad(0), aux(0) {}
 
     MB_HD int group(int s) const { return 1 << w.gcode[s]; }
     MB_HD int dp_of(int s) const { return (1 << w.gcode[s]) >> w.tpc[s]; }
@@ -531,10 +585,10 @@ struct PlanEvaluator {
         int lb = 0;
         while ((2 << lb) <= bs_total) ++lb;
         nbad = 0;
+        set_groups(pd.row);
         for (int s = 0; s < pd.S; ++s) {
             const int g = pd.row[s];
             const int t = g > lb ? g - lb : 0;
-            w.gcode[s] = (uint8_t)g;
             w.tpc[s] = (uint8_t)t;
             nbad += stage_bad(g, t) ? 1 : 0;
         }
@@ -618,34 +672,60 @@ struct PlanEvaluator {
         return 0;
     }
 
-    // StagePerformance.get_intra_stage_compute_performance (model/device_group.py:54-85) -> w.perf
-    MB_HD_NOINLINE int compute_performance() {
-        PySum total;
-        const bool one_type = T.p.num_types == 1;
+    // start rank of stage s (prefix sum of the group sizes, filled by set_groups)
+    MB_HD int rank_start(int s) const { return w.rs[s]; }
+
+    MB_HD void set_groups(const uint8_t *row) {
         int a = 0;
-        for (int s = 0; s < pd.S; ++s) {
+        for (int s = 0; s < pd.S; ++s) { w.gcode[s] = row[s]; w.rs[s] = (uint16_t)a; a += 1 << row[s]; }
+        w.rs[pd.S] = (uint16_t)a;
+    }
+
+    // StagePerformance.get_intra_stage_compute_performance (model/device_group.py:54-85) -> w.perf
+    MB_HD int compute_performance() {
+        const bool one_type = T.p.num_types == 1;
+        int fail = 0;
+        for (int s = x.lane(); s < pd.S; s += x.width()) {
             const int g = w.gcode[s], tpc = w.tpc[s];
-            const int b = a + (1 << g);
-            const int ta = one_type ? 0 : type_of_rank(T, pd.ns, a);
-            const int tb = one_type ? 0 : type_of_rank(T, pd.ns, b - 1);
-            double p;
-            if (ta == tb) {
+            double p = 0.0;
+            if (one_type) {
                 const int bs = bs_total >> (g - tpc);
-                const int key = key_of(T, ta, tpc, bs);
-                if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; return METIS_FATAL_KEY_EXEC; }
-                if (T.exec_full[key] == 0.0) return METIS_FATAL_ZERODIV;
-                p = T.inv_exec[key];                          // 1. / profile_cost
+                const int key = key_of(T, 0, tpc, bs);
+                if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; fail = METIS_FATAL_KEY_EXEC; }
+                else if (T.exec_full[key] == 0.0) fail = METIS_FATAL_ZERODIV;
+                else p = T.inv_exec[key];                     // 1. / profile_cost
             } else {
-                const int rc = hetero_performance(a, b, 1 << (g - tpc), tpc, p);
-                if (rc) return rc;
+                const int a = rank_start(s), b = a + (1 << g);
+                const int ta = type_of_rank(T, pd.ns, a), tb = type_of_rank(T, pd.ns, b - 1);
+                if (ta == tb) {
+                    const int bs = bs_total >> (g - tpc);
+                    const int key = key_of(T, ta, tpc, bs);
+                    if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; fail = METIS_FATAL_KEY_EXEC; }
+                    else if (T.exec_full[key] == 0.0) fail = METIS_FATAL_ZERODIV;
+                    else p = T.inv_exec[key];
+                } else {
+                    const int rc = hetero_performance(a, b, 1 << (g - tpc), tpc, p);
+                    if (rc) fail = rc;
+                }
             }
             w.perf[s] = p;
-            total.add(p);
-            a = b;
+            w.extra[s] = fail ? (double)fail + (double)aux * 256.0 : 0.0;   // per-stage error mailbox (cooperative mode)
+        }
+        x.sync();
+        PySum total;
+        for (int s = 0; s < pd.S; ++s) {                     // first failing stage in stage order, like the reference
+            if (w.extra[s] != 0.0) {
+                const uint64_t code = (uint64_t)w.extra[s];
+                aux = (uint32_t)(code >> 8);
+                return (int)(code & 0xFF);
+            }
+            total.add(w.perf[s]);
         }
         const double tot = total.result();
         if (tot == 0.0) return METIS_FATAL_ZERODIV;
-        for (int s = 0; s < pd.S; ++s) w.perf[s] = w.perf[s] / tot;
+        x.sync();
+        for (int s = x.lane(); s < pd.S; s += x.width()) w.perf[s] = w.perf[s] / tot;
+        x.sync();
         return 0;
     }
 
@@ -673,6 +753,7 @@ struct PlanEvaluator {
     // in: w.perf (c_capa), w.extra (m_demand); out: w.perf; returns 1 = None, 0 ok, <0 fatal (negated code)
     MB_HD_NOINLINE int adjust_performance() {
         const int S = pd.S;
+        x.sync();
         double need = 0.;
         PySum avail_sum;
         int a = 0;
@@ -712,6 +793,7 @@ struct PlanEvaluator {
             if (++guard > 4096) return -METIS_FATAL_HANG;
         }
         for (int s = 0; s < S; ++s) w.perf[s] = w.extra[s] + w.mstate[s];
+        x.sync();
         return 0;
     }
 
@@ -721,33 +803,41 @@ struct PlanEvaluator {
     // with the adjusted w.perf, 0 = (None, -1, None), <0 = fatal (negated code).  After the third
     // failed attempt the reference still evaluates _adj_compute_performance and discards it; that
     // call is skipped here.
-    MB_HD_NOINLINE int memory_phase(int attempt) {
+    MB_HD int memory_phase(int attempt) {
         const int S = pd.S;
         const bool one_type = T.p.num_types == 1;
         const int type0 = T.run_type[pd.ns * T.p.num_types];
-        bool oom = false;
-        int a = 0;
-        for (int s = 0; s < S; ++s) {
+        for (int s = x.lane(); s < S; s += x.width()) {
             const int g = w.gcode[s], tpc = w.tpc[s];
-            const int b = a + (1 << g);
-            double md = 0.001;
+            const int a = one_type ? 0 : rank_start(s), b = a + (1 << g);
+            double md = 0.001, err = 0.0;
             if (one_type || type_of_rank(T, pd.ns, a) == type_of_rank(T, pd.ns, b - 1)) {
                 const int bs = bs_total >> (g - tpc);
                 const int key = key_of(T, type0, tpc, bs);
-                if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; return -METIS_FATAL_KEY_MEMORY; }
-                md += py_sum_range(T.mem + (size_t)key * T.p.lpad, w.part[s], w.part[s + 1]) * kMemCoef;
+                if (key < 0) err = (double)METIS_FATAL_KEY_MEMORY + (double)(((uint32_t)tpc << 16) | (uint32_t)bs) * 256.0;
+                else md += py_sum_range(T.mem + (size_t)key * T.p.lpad, w.part[s], w.part[s + 1]) * kMemCoef;
             } else {
                 const int rc = hetero_memory_demand(s, type0, md);
-                if (rc) return -rc;
+                if (rc) err = (double)rc + (double)aux * 256.0;
             }
-            const double st = memory_capacity(a, b) - md;
             w.extra[s] = md;
-            w.capa[s] = st;
-            if (st < 0) oom = true;
-            a = b;
+            w.capa[s] = one_type ? T.type_memory[0] * (double)(1 << g) - md : memory_capacity(a, b) - md;
+            w.mstate[s] = err;
+        }
+        x.sync();
+        bool oom = false;
+        for (int s = 0; s < S; ++s) {
+            if (w.mstate[s] != 0.0) {
+                const uint64_t code = (uint64_t)w.mstate[s];
+                aux = (uint32_t)(code >> 8);
+                return -(int)(code & 0xFF);
+            }
+            if (w.capa[s] < 0) oom = true;
         }
         if (!oom) {
-            for (int s = 0; s < S; ++s) w.mstate[s] = w.capa[s];
+            x.sync();
+            for (int s = x.lane(); s < S; s += x.width()) w.mstate[s] = w.capa[s];
+            x.sync();
             return 1;
         }
         if (attempt >= 3) return 0;
@@ -762,7 +852,7 @@ struct PlanEvaluator {
     MB_HD_NOINLINE int partition_layer(Sink &sink) {
         for (int attempt = 1; attempt <= 3; ++attempt) {
             sink.balancer_run();
-            const int rc = balance_run<MAXS, MAXL>(T, pd.S, w);
+            const int rc = balance_run<MAXS, MAXL>(T, pd.S, w, x);
             if (rc) return -rc;
             const int r = memory_phase(attempt);
             if (r == 1) return attempt;
@@ -862,12 +952,33 @@ struct PlanEvaluator {
     // HeteroCostEstimator.get_cost (model/cost_estimator.py:199-244); returns 0 ok, 1 KeyError.
     // x / tp is evaluated as x * 2^-log2(tp) (same real quotient, same rounding); the remaining
     // quotients come from the derived tables when the cluster has a single bandwidth value.
-    MB_HD_NOINLINE int get_cost(double &cost_out) {
+    MB_HD int get_cost(double &cost_out) {
         const int per = T.p.devices_per_node;
         const int Lm = T.p.num_layers;
         const bool one_type = T.p.num_types == 1;
         const bool ubw = T.p.uniform_bw != 0;
         const int nstage = pd.label < pd.S ? pd.label : pd.S;  // zip(range(plan.num_stage), strategies)
+        // execution time of every stage first (independent range sums; w.capa[s] = time, w.extra[s] = error flag)
+        x.sync();
+        for (int s = x.lane(); s < nstage; s += x.width()) {
+            const int g = w.gcode[s], tpc = w.tpc[s];
+            const int a = one_type ? 0 : rank_start(s), b = a + (1 << g);
+            const int la = w.part[s], lb = w.part[s + 1];
+            const int ldp = g - tpc;
+            const int ta = one_type ? 0 : type_of_rank(T, pd.ns, a);
+            const int tb = one_type ? 0 : type_of_rank(T, pd.ns, b - 1);
+            double len = 0.0, err = 0.0;
+            if (ta == tb) {                                   // _get_execution_cost :175-188
+                const int key = key_of(T, ta, tpc, bs_total >> ldp);
+                if (key < 0) err = 1.0;
+                else len = py_sum_range(T.lc + (size_t)key * T.p.lpad, la, lb);
+            } else if (hetero_exec_cost(a, b, 1 << ldp, tpc, la, lb, len)) {
+                err = 1.0;
+            }
+            w.capa[s] = len;
+            w.extra[s] = err;
+        }
+        x.sync();
         PySum lens_sum;
         double max_len = -INFINITY, max_upd = -INFINITY, max_dp = -INFINITY;
         double pp_cost = 0., fb_sync = 0.;
@@ -879,16 +990,8 @@ struct PlanEvaluator {
             const int ldp = g - tpc;
             const int mbs = bs_total >> ldp;
             const double inv_tp = pow2_neg(tpc);              // 1 / tp, exact power of two
-            const int ta = one_type ? 0 : type_of_rank(T, pd.ns, a);
-            const int tb = one_type ? 0 : type_of_rank(T, pd.ns, b - 1);
-            double len;
-            if (ta == tb) {                                   // _get_execution_cost :175-188
-                const int key = key_of(T, ta, tpc, mbs);
-                if (key < 0) return 1;
-                len = py_sum_range(T.lc + (size_t)key * T.p.lpad, la, lb);
-            } else if (hetero_exec_cost(a, b, 1 << ldp, tpc, la, lb, len)) {
-                return 1;
-            }
+            if (w.extra[s] != 0.0) return 1;                  // KeyError raised while costing stage s
+            const double len = w.capa[s];
             lens_sum.add(len);
             if (len > max_len) max_len = len;
 
@@ -995,7 +1098,7 @@ MB_HD uint64_t pack_task(uint32_t ordinal, int step, int attempt, int nrep, bool
 template <int MAXS, int MAXL, class Sink, class Warp>
 MB_HD void begin_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &warp, const TaskBuffers &out,
                       bool has, const PlanDesc &plan) {
-    PlanEvaluator<MAXS, MAXL> ev(T, w);
+    PlanEvaluator<MAXS, MAXL, Serial> ev(T, w);
     bool cont = false;
     if (has) {
         const int ok = ev.begin(plan);
@@ -1009,10 +1112,10 @@ MB_HD void begin_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp 
     }
 }
 
-template <int MAXS, int MAXL, class Sink, class Warp>
-MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &warp, const TaskBuffers &in,
-                    const TaskBuffers &out, bool has, int64_t pos, const PlanDesc &plan) {
-    PlanEvaluator<MAXS, MAXL> ev(T, w);
+template <int MAXS, int MAXL, class X, class Sink, class Warp>
+MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sink &sink, Warp &warp,
+                    const TaskBuffers &in, const TaskBuffers &out, bool has, int64_t pos, const PlanDesc &plan) {
+    PlanEvaluator<MAXS, MAXL, X> ev(T, w, lanes);
     int step = 0, attempt = 1, nrep = 0;
     bool retry = false, cont = false, advance = false, have_state = false, costing = false;
     sink.phase(1);
@@ -1025,13 +1128,13 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &w
         ev.pd = plan;
         ev.bs_total = T.p.gbs / plan.batches;
         ev.nbad = 0;
-        for (int s = 0; s < plan.S; ++s) {
-            w.gcode[s] = plan.row[s];
+        ev.set_groups(plan.row);
+        for (int s = lanes.lane(); s < plan.S; s += lanes.width()) {
             w.tpc[s] = in.tpc[(int64_t)s * in.cap + pos];
+            if (retry) w.perf[s] = in.perf[(int64_t)s * in.cap + pos];
         }
-        if (retry) {
-            for (int s = 0; s < plan.S; ++s) w.perf[s] = in.perf[(int64_t)s * in.cap + pos];
-        } else {
+        lanes.sync();
+        if (!retry) {
             sink.partition_call();
             const int rc = ev.compute_performance();
             if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
@@ -1040,7 +1143,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &w
     sink.phase(2);
     if (has) {                                               // ---- R ----
         sink.balancer_run();
-        const int rc = balance_run<MAXS, MAXL>(T, plan.S, w);
+        const int rc = balance_run<MAXS, MAXL>(T, plan.S, w, lanes);
         if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
     }
     sink.phase(3);
@@ -1069,9 +1172,11 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &w
     const int64_t opos = warp.append(has && cont);
     if (has && cont) {
         out.hdr[opos] = pack_task(plan.ordinal, step, attempt, nrep, retry);
-        for (int s = 0; s < plan.S; ++s) out.tpc[(int64_t)s * out.cap + opos] = w.tpc[s];
-        if (retry)
-            for (int s = 0; s < plan.S; ++s) out.perf[(int64_t)s * out.cap + opos] = w.perf[s];
+        lanes.sync();
+        for (int s = lanes.lane(); s < plan.S; s += lanes.width()) {
+            out.tpc[(int64_t)s * out.cap + opos] = w.tpc[s];
+            if (retry) out.perf[(int64_t)s * out.cap + opos] = w.perf[s];
+        }
     }
 }
 

@@ -188,12 +188,14 @@ struct DeviceSink {
     unsigned int n_part, n_run, n_key;
     double best_cost;
     uint32_t best_ord, best_step, best_meta;
+    bool leader;                    // cooperative mode: only lane 0 of the warp produces side effects
     __device__ DeviceSink(const DeviceOut &out)
         : o(out), n_part(0), n_run(0), n_key(0), best_cost(INFINITY), best_ord(0xFFFFFFFFu), best_step(0xFFFFu),
-          best_meta(0) {}
+          best_meta(0), leader(true) {}
 #ifdef METIS_PROFILE_PHASES
     long long t_last = 0; int cur = -1; long long acc[6] = {0, 0, 0, 0, 0, 0};
     __device__ void phase(int k) {
+        if (!leader) return;
         const long long now = clock64();
         if (cur >= 0) acc[cur] += now - t_last;
         cur = k; t_last = now;
@@ -201,15 +203,17 @@ struct DeviceSink {
 #else
     __device__ void phase(int) {}
 #endif
-    __device__ void partition_call() { ++n_part; }
-    __device__ void balancer_run() { ++n_run; }
-    __device__ void keyerror() { ++n_key; }
+    __device__ void partition_call() { n_part += leader ? 1u : 0u; }
+    __device__ void balancer_run() { n_run += leader ? 1u : 0u; }
+    __device__ void keyerror() { n_key += leader ? 1u : 0u; }
     __device__ void fatal(uint32_t ordinal, int code, uint32_t aux) {
+        if (!leader) return;
         const unsigned long long key = ((unsigned long long)ordinal << 32) | ((unsigned long long)(code & 0xFF) << 24) |
                                        (unsigned long long)(((aux >> 16) & 0xFF) << 16) | (aux & 0xFFFF);
         atomicMin(&o.counters[4], key);
     }
     __device__ void emit(const PlanDesc &pd, int step, int nrep, double cost, const uint8_t *tpc, const uint16_t *part) {
+        if (!leader) return;
         const unsigned long long slot = atomicAdd(&o.counters[0], 1ULL);
         if ((long long)slot < o.capacity) {
             MetisRecord r;
@@ -246,18 +250,40 @@ struct DeviceWarp {
     }
 };
 
+// Lane policy of the cooperative (latency) mode, see metis_eval.cuh `Serial`.
+struct WarpLanes {
+    static constexpr bool kUniform = true;
+    __device__ int lane() const { return threadIdx.x & 31; }
+    __device__ int width() const { return 32; }
+    __device__ void sync() const { __syncwarp(); }
+};
+
+// Cooperative mode: the 32 lanes of a warp execute ONE task redundantly on shared-memory scratch
+// (identical data => identical control flow, no divergence); lane 0 appends for the warp.
+struct UniformWarp {
+    unsigned int *counter;
+    __device__ explicit UniformWarp(unsigned int *c) : counter(c) {}
+    __device__ int64_t append(bool want) const {
+        unsigned int base = 0;
+        if (want && (threadIdx.x & 31) == 0) base = atomicAdd(counter, 1u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        return want ? (int64_t)base : -1;
+    }
+};
+
 struct RoundBuffers {
     TaskBuffers buf[2];
     unsigned int *counts;      // [3] rotating task counters
     long long wave;            // plans admitted per wave (= capacity of the task lists)
+    long long coop_below;      // rounds with fewer pending tasks run one task per warp (latency mode)
 };
 
 template <int MAXS, int MAXL>
 __global__ void __launch_bounds__(kThreads)
 het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                   const MetisShard sh, const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob,
-                  const int use_smem, const long long slots, const __grid_constant__ DeviceOut out,
-                  const __grid_constant__ RoundBuffers rb) {
+                  const int use_smem, const unsigned int scratch_off, const long long slots,
+                  const __grid_constant__ DeviceOut out, const __grid_constant__ RoundBuffers rb) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
     __shared__ double s_cost[kThreads / 32];
@@ -274,6 +300,7 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
     DeviceSink sink(out);
     {
         Scratch<MAXS, MAXL> w;
+        Scratch<MAXS, MAXL> *wsh = reinterpret_cast<Scratch<MAXS, MAXL> *>(smem + scratch_off) + (threadIdx.x >> 5);
         const int lane = threadIdx.x & 31;
         const long long gwarp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
         const long long nwarps = (long long)gridDim.x * (kThreads / 32);
@@ -305,12 +332,25 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                 DeviceWarp warp(&rb.counts[(round + 1) % 3]);
                 if (blockIdx.x == 0 && threadIdx.x == 0) rb.counts[(round + 2) % 3] = 0;
                 const TaskBuffers &in = rb.buf[round & 1], &nxt = rb.buf[(round + 1) & 1];
-                for (long long b0 = gwarp * 32; b0 < (long long)n; b0 += nwarps * 32) {
-                    const long long pos = b0 + lane;
-                    PlanDesc pd;
-                    bool has = false;
-                    if (pos < (long long)n) has = decode_plan(sp, (uint32_t)in.hdr[pos], pd);
-                    run_task<MAXS, MAXL>(T, w, sink, warp, in, nxt, has, pos, pd);
+                if ((long long)n >= rb.coop_below) {
+                    // throughput mode: one task per lane, 32 tasks per warp in lockstep
+                    for (long long b0 = gwarp * 32; b0 < (long long)n; b0 += nwarps * 32) {
+                        const long long pos = b0 + lane;
+                        PlanDesc pd;
+                        bool has = false;
+                        if (pos < (long long)n) has = decode_plan(sp, (uint32_t)in.hdr[pos], pd);
+                        run_task<MAXS, MAXL>(T, w, Serial(), sink, warp, in, nxt, has, pos, pd);
+                    }
+                } else {
+                    // latency mode: one task per warp on shared-memory scratch
+                    UniformWarp uwarp(&rb.counts[(round + 1) % 3]);
+                    sink.leader = lane == 0;
+                    for (long long pos = gwarp; pos < (long long)n; pos += nwarps) {
+                        PlanDesc pd;
+                        const bool has = decode_plan(sp, (uint32_t)in.hdr[pos], pd);
+                        run_task<MAXS, MAXL>(T, *wsh, WarpLanes(), sink, uwarp, in, nxt, has, pos, pd);
+                    }
+                    sink.leader = true;
                 }
                 grid.sync();
                 ++round;
@@ -463,7 +503,7 @@ layer_balance_kernel(const double *__restrict__ capa, const int32_t *__restrict_
     uint16_t *out = partition + i * (stride + 1);
     if (S < 1 || S > MAXS || num_layers > MAXL) { out[0] = 0xFFFF; return; }
     for (int s = 0; s < S; ++s) w.perf[s] = capa[i * stride + s];
-    const int rc = balance_run<MAXS, MAXL>(T, S, w);
+    const int rc = balance_run<MAXS, MAXL>(T, S, w, Serial());
     if (rc) { out[0] = 0xFFFF; return; }
     for (int s = 0; s <= S; ++s) out[s] = w.part[s];
 }
@@ -587,7 +627,8 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     if (e != cudaSuccess) return cuda_fail(e, "pack_tables_kernel");
 
     int use_smem = lay.total <= (uint32_t)kSmemBlobMax;
-    size_t dyn = use_smem ? lay.total : 0;
+    unsigned int scratch_off = use_smem ? ((lay.total + 127u) & ~127u) : 0u;
+    size_t dyn = scratch_off + (kThreads / 32) * sizeof(Scratch<kMaxS, kMaxL>);
     auto kern = het_search_kernel<kMaxS, kMaxL>;
     if (dyn > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -619,7 +660,8 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
         BlobLayout lay_arg = lay;
         const uint8_t *blob_arg = ws.blob;
         long long slots_arg = slots;
-        void *args[] = {&p_arg, &s_arg, &sh_arg, &lay_arg, &blob_arg, &use_smem, &slots_arg, &out, &rb};
+        rb.coop_below = (long long)(shard->reserved > 0 ? shard->reserved : 6) * grid * (kThreads / 32);
+        void *args[] = {&p_arg, &s_arg, &sh_arg, &lay_arg, &blob_arg, &use_smem, &scratch_off, &slots_arg, &out, &rb};
         if (g_ev_before) cudaEventRecord(g_ev_before, stream);
         e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(kThreads), args, dyn, stream);
         if (g_ev_after) cudaEventRecord(g_ev_after, stream);

@@ -144,7 +144,10 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
             for (int64_t pos = 0; pos < cur; ++pos) {
                 PlanDesc pd;
                 const bool has = decode(*sp, (uint32_t)buf[r & 1].hdr[pos], pd);
-                run_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, warp, buf[r & 1], buf[(r + 1) & 1], has, pos, pd);
+                if (mode == 2)
+                    run_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, SerialUniform(), sink, warp, buf[r & 1], buf[(r + 1) & 1], has, pos, pd);
+                else
+                    run_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, Serial(), sink, warp, buf[r & 1], buf[(r + 1) & 1], has, pos, pd);
             }
         }
     }
@@ -181,7 +184,7 @@ int hostsim_layer_balance(const double *capa, const int32_t *num_stage, int64_t 
         const int S = num_stage[i];
         uint16_t *out = partition + i * (stride + 1);
         for (int s = 0; s < S; ++s) w.perf[s] = capa[i * stride + s];
-        const int rc = balance_run<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, S, w);
+        const int rc = balance_run<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, S, w, Serial());
         if (rc) { out[0] = 0xFFFF; continue; }
         for (int s = 0; s <= S; ++s) out[s] = w.part[s];
     }

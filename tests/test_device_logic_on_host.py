@@ -49,7 +49,7 @@ def test_c1_het():
     assert summary.best.cost == 621.8881853975784 and summary.best.ordinal == 7
 
 
-@pytest.mark.parametrize('mode', [0, 1], ids=['sequential_run', 'search_loop'])
+@pytest.mark.parametrize('mode', [0, 1, 2], ids=['sequential_run', 'rounds', 'rounds_uniform_paths'])
 @pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight'])
 def test_synthetic(name, mode, workload_dir):
     meta, arr = load_golden(name)

@@ -30,6 +30,7 @@ space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.g
 dp = search.DeviceProblem(problem, space, 'cuda:0')
 dp.lib = native._lib
 s = search.HetSearcher(dp, want_records=False)
+s.shard.reserved = int(os.environ.get('METIS_COOP', '0'))
 for _ in range(3):
     s.launch()
 torch.cuda.synchronize()

@@ -111,7 +111,14 @@ struct PlanDesc {
     int label;         // InterStagePlan.num_stage as emitted (quirk Q1)
     int batches;
     const uint8_t *row;  // log2(group size) per stage
+    uint64_t geo;        // packed geometry (pack_geo) carried through the task lists
 };
+
+// rows byte offset (32) | S-1 (8) | label-1 (8) | ns (8) | divisor index (8)
+MB_HD uint64_t pack_geo(int64_t row_offset, int S, int label, int ns, int div) {
+    return (uint64_t)(row_offset & 0xFFFFFFFFLL) | ((uint64_t)((S - 1) & 0xFF) << 32) | ((uint64_t)((label - 1) & 0xFF) << 40) |
+           ((uint64_t)(ns & 0xFF) << 48) | ((uint64_t)(div & 0xFF) << 56);
+}
 
 // Execution policies.  `Serial`: one thread owns the task (host, replay kernel, and the throughput
 // mode of the search kernel where the 32 lanes of a warp hold 32 different tasks).  A cooperative
@@ -123,6 +130,9 @@ struct Serial {
     MB_HD int lane() const { return 0; }
     MB_HD int width() const { return 1; }
     MB_HD void sync() const {}
+    // combine per-lane partial results: largest v, lowest index among equals / largest v
+    MB_HD void argmax_first(double &, int &) const {}
+    MB_HD double max_all(double v) const { return v; }
 };
 struct SerialUniform : Serial {           // tests: the code paths of the cooperative mode, one lane
     static constexpr bool kUniform = true;
@@ -445,10 +455,12 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
 
     // ---- boundary adjustment (:310-356): at most three committed single-layer moves ---------
     for (int n = 1; n <= 3; ++n) {
-        int top = 0;
-        double maxc = w.capa[0];
-        for (int t = 1; t < S; ++t)
+        int top = 0x7FFFFFFF;
+        double maxc = -INFINITY;
+        for (int t = x.lane(); t < S; t += x.width())        // stable: lowest index among equal maxima (:329-331)
             if (w.capa[t] > maxc) { maxc = w.capa[t]; top = t; }
+        x.argmax_first(maxc, top);
+        if (top == 0x7FFFFFFF) top = 0;
         int nb = -1;
         double val = INFINITY;
         if (top - 1 >= 0 && w.capa[top - 1] < val) { nb = top - 1; val = w.capa[top - 1]; }
@@ -459,11 +471,13 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         const double ntop = w.capa[top] - dl;
         const double nnb = w.capa[nb] + dl;
         double newmax = -INFINITY;
-        for (int t = 0; t < S; ++t) {
+        for (int t = x.lane(); t < S; t += x.width()) {
             const double v = (t == top) ? ntop : (t == nb) ? nnb : w.capa[t];
             if (v > newmax) newmax = v;
         }
+        newmax = x.max_all(newmax);
         if (newmax > maxc) break;                            // :352 (not committed)
+        x.sync();
         w.owner[layer] = (uint8_t)top;
         w.capa[top] = ntop;
         w.capa[nb] = nnb;
@@ -476,6 +490,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         }
         ++w.cnt[top];
         --w.cnt[nb];
+        x.sync();
     }
 
     w.part[0] = 0;                                           // :358-364
@@ -1085,6 +1100,7 @@ struct PlanEvaluator {
 // ---------------------------------------------------------------------------
 struct TaskBuffers {
     uint64_t *hdr;      // [cap]            ordinal | step << 32 | attempt << 48 | nrep << 52 | retry << 56
+    uint64_t *geo;      // [cap]            plan geometry (pack_geo)
     uint8_t *tpc;       // [smax][cap]      log2(tp) per stage
     double *perf;       // [smax][cap]      re-weighted stage performance (retry tasks only)
     int64_t cap;
@@ -1108,6 +1124,7 @@ MB_HD void begin_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp 
     const int64_t pos = warp.append(cont);
     if (cont) {
         out.hdr[pos] = pack_task(plan.ordinal, 0, 1, 0, false);
+        out.geo[pos] = plan.geo;
         for (int s = 0; s < plan.S; ++s) out.tpc[(int64_t)s * out.cap + pos] = w.tpc[s];
     }
 }
@@ -1172,6 +1189,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
     const int64_t opos = warp.append(has && cont);
     if (has && cont) {
         out.hdr[opos] = pack_task(plan.ordinal, step, attempt, nrep, retry);
+        out.geo[opos] = plan.geo;
         lanes.sync();
         for (int s = lanes.lane(); s < plan.S; s += lanes.width()) {
             out.tpc[(int64_t)s * out.cap + opos] = w.tpc[s];

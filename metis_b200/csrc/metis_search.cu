@@ -163,8 +163,21 @@ __device__ __forceinline__ bool decode_plan(const MetisPlanSpace &sp, int64_t or
     pd.S = b.num_stage;
     pd.label = b.label_stage;
     pd.batches = __ldg(&sp.batches[div]);
-    pd.row = sp.rows + b.rows_offset + row * b.num_stage;
+    const int64_t off = b.rows_offset + row * b.num_stage;
+    pd.row = sp.rows + off;
+    pd.geo = pack_geo(off, b.num_stage, b.label_stage, b.ns_idx, div);
     return true;
+}
+
+// task list entry -> plan (no block search: the geometry word was stored at admission)
+__device__ __forceinline__ void decode_task(const MetisPlanSpace &sp, uint64_t hdr, uint64_t geo, PlanDesc &pd) {
+    pd.ordinal = (uint32_t)hdr;
+    pd.geo = geo;
+    pd.row = sp.rows + (geo & 0xFFFFFFFFULL);
+    pd.S = (int)((geo >> 32) & 0xFF) + 1;
+    pd.label = (int)((geo >> 40) & 0xFF) + 1;
+    pd.ns = (int)((geo >> 48) & 0xFF);
+    pd.batches = __ldg(&sp.batches[(geo >> 56) & 0xFF]);
 }
 
 __device__ __forceinline__ bool rec_less(double c0, uint32_t o0, uint32_t s0, double c1, uint32_t o1, uint32_t s1) {
@@ -256,6 +269,22 @@ struct WarpLanes {
     __device__ int lane() const { return threadIdx.x & 31; }
     __device__ int width() const { return 32; }
     __device__ void sync() const { __syncwarp(); }
+    __device__ void argmax_first(double &v, int &i) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double v2 = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+            const int i2 = __shfl_xor_sync(0xFFFFFFFFu, i, d);
+            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+        }
+    }
+    __device__ double max_all(double v) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double v2 = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+            if (v2 > v) v = v2;
+        }
+        return v;
+    }
 };
 
 // Cooperative mode: the 32 lanes of a warp execute ONE task redundantly on shared-memory scratch
@@ -276,10 +305,11 @@ struct RoundBuffers {
     unsigned int *counts;      // [3] rotating task counters
     long long wave;            // plans admitted per wave (= capacity of the task lists)
     long long coop_below;      // rounds with fewer pending tasks run one task per warp (latency mode)
+    unsigned long long *trace; // profiling builds: (tasks, globaltimer ns) per round, 512 entries
 };
 
 template <int MAXS, int MAXL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? 6 : 4))
 het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                   const MetisShard sh, const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob,
                   const int use_smem, const unsigned int scratch_off, const long long slots,
@@ -328,6 +358,14 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
             // ---- rounds: one partition attempt per pending plan --------------------------------
             for (;;) {
                 const unsigned int n = *(volatile unsigned int *)&rb.counts[round % 3];
+#ifdef METIS_PROFILE_PHASES
+                if (blockIdx.x == 0 && threadIdx.x == 0 && round < 512) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    rb.trace[2 * round] = n;
+                    rb.trace[2 * round + 1] = t;
+                }
+#endif
                 if (n == 0) break;
                 DeviceWarp warp(&rb.counts[(round + 1) % 3]);
                 if (blockIdx.x == 0 && threadIdx.x == 0) rb.counts[(round + 2) % 3] = 0;
@@ -338,7 +376,7 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                         const long long pos = b0 + lane;
                         PlanDesc pd;
                         bool has = false;
-                        if (pos < (long long)n) has = decode_plan(sp, (uint32_t)in.hdr[pos], pd);
+                        if (pos < (long long)n) { decode_task(sp, in.hdr[pos], in.geo[pos], pd); has = true; }
                         run_task<MAXS, MAXL>(T, w, Serial(), sink, warp, in, nxt, has, pos, pd);
                     }
                 } else {
@@ -347,7 +385,8 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                     sink.leader = lane == 0;
                     for (long long pos = gwarp; pos < (long long)n; pos += nwarps) {
                         PlanDesc pd;
-                        const bool has = decode_plan(sp, (uint32_t)in.hdr[pos], pd);
+                        decode_task(sp, in.hdr[pos], in.geo[pos], pd);
+                        const bool has = true;
                         run_task<MAXS, MAXL>(T, *wsh, WarpLanes(), sink, uwarp, in, nxt, has, pos, pd);
                     }
                     sink.leader = true;
@@ -542,11 +581,11 @@ static int64_t shard_plan_slots(int64_t num_plans, const MetisShard *sh) {
     return rounds * tile;
 }
 
-constexpr int64_t kFixedWs = 4096;                 // summary + counters + round counters
+constexpr int64_t kFixedWs = 16384;                // summary + counters + round counters + round trace
 constexpr int64_t kMaxBlocks = 4096;               // per-block best records
 constexpr int64_t kRoundBudget = 4LL << 30;        // bytes of task-list storage before the space is cut into waves
 
-static int64_t task_slot_bytes(int max_stage) { return 8 + (int64_t)max_stage + 8 * (int64_t)max_stage; }
+static int64_t task_slot_bytes(int max_stage) { return 16 + (int64_t)max_stage + 8 * (int64_t)max_stage; }
 
 static int64_t wave_size(int64_t slots, int max_stage) {
     int64_t cap = kRoundBudget / (2 * task_slot_bytes(max_stage));
@@ -593,6 +632,7 @@ static TaskBuffers carve_tasks(uint8_t *&p, int64_t cap, int max_stage) {
     TaskBuffers t;
     t.cap = cap;
     t.hdr = reinterpret_cast<uint64_t *>(p);   p += cap * 8;
+    t.geo = reinterpret_cast<uint64_t *>(p);   p += cap * 8;
     t.perf = reinterpret_cast<double *>(p);    p += cap * 8 * (int64_t)max_stage;
     t.tpc = p;                                 p += cap * (int64_t)max_stage;
     return t;
@@ -608,6 +648,7 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
         return arg_fail("bad shard (tile must be a positive multiple of 32)");
     if (space->num_plans > 0xFFFFFFF0LL) return arg_fail("more than 2^32 plans");
     if (space->max_stage < 1 || space->max_stage > METIS_MAX_STAGES) return arg_fail("max_stage out of range (METIS_MAX_STAGES)");
+    if (space->num_div < 1 || space->num_div > 256) return arg_fail("more than 256 divisors of gbs");
     if (detail && detail_stride < 3 * METIS_MAX_STAGES + 1) return arg_fail("detail_stride too small");
     if (capacity < 0 || (capacity > 0 && !records)) return arg_fail("records/capacity mismatch");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -618,7 +659,7 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     const Workspace ws = carve(workspace, lay);
 
     cudaError_t e;
-    e = cudaMemsetAsync(ws.counters, 0, 2048, stream);       // counters + round counters
+    e = cudaMemsetAsync(ws.counters, 0, kFixedWs - 1024, stream);   // counters, round counters, trace
     if (e != cudaSuccess) return cuda_fail(e, "memset counters");
     e = cudaMemsetAsync(ws.counters + 4, 0xFF, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset fatal key");
@@ -628,8 +669,10 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
 
     int use_smem = lay.total <= (uint32_t)kSmemBlobMax;
     unsigned int scratch_off = use_smem ? ((lay.total + 127u) & ~127u) : 0u;
-    size_t dyn = scratch_off + (kThreads / 32) * sizeof(Scratch<kMaxS, kMaxL>);
-    auto kern = het_search_kernel<kMaxS, kMaxL>;
+    // two instantiations: the small one (S <= 64, L <= 128) halves the per-warp scratch -> more resident warps
+    const bool small = space->max_stage <= 64 && problem->num_layers <= 128;
+    size_t dyn = scratch_off + (kThreads / 32) * (small ? sizeof(Scratch<64, 128>) : sizeof(Scratch<kMaxS, kMaxL>));
+    auto kern = small ? het_search_kernel<64, 128> : het_search_kernel<kMaxS, kMaxL>;
     if (dyn > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
@@ -643,6 +686,7 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     rb.buf[0] = carve_tasks(tp, rb.wave, space->max_stage);
     rb.buf[1] = carve_tasks(tp, rb.wave, space->max_stage);
     rb.counts = ws.round_counts;
+    rb.trace = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(ws.summary) + 4096);
     // cooperative persistent grid: every block is resident, rounds are separated by grid.sync()
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);

@@ -52,6 +52,8 @@ bool decode(const MetisPlanSpace &sp, int64_t ordinal, PlanDesc &pd) {
     pd.label = blk.label_stage;
     pd.batches = sp.batches[rel - row * sp.num_div];
     pd.row = sp.rows + blk.rows_offset + row * blk.num_stage;
+    pd.geo = pack_geo(blk.rows_offset + row * blk.num_stage, blk.num_stage, blk.label_stage, blk.ns_idx,
+                      (int)(rel - row * sp.num_div));
     return true;
 }
 
@@ -126,10 +128,11 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
         const int smax = sp->max_stage > 0 ? sp->max_stage : METIS_MAX_STAGES;
         const int64_t cap = rounds * tile > 0 ? rounds * tile : 1;
         std::vector<uint64_t> hdr[2] = {std::vector<uint64_t>(cap), std::vector<uint64_t>(cap)};
+        std::vector<uint64_t> geo[2] = {std::vector<uint64_t>(cap), std::vector<uint64_t>(cap)};
         std::vector<uint8_t> tpc[2] = {std::vector<uint8_t>(cap * smax), std::vector<uint8_t>(cap * smax)};
         std::vector<double> perf[2] = {std::vector<double>(cap * smax), std::vector<double>(cap * smax)};
         TaskBuffers buf[2];
-        for (int k = 0; k < 2; ++k) buf[k] = TaskBuffers{hdr[k].data(), tpc[k].data(), perf[k].data(), cap};
+        for (int k = 0; k < 2; ++k) buf[k] = TaskBuffers{hdr[k].data(), geo[k].data(), tpc[k].data(), perf[k].data(), cap};
         int64_t n = 0;
         HostWarp warp{&n};
         for (int64_t i = 0; i < rounds * tile; ++i) {
@@ -142,8 +145,16 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
             const int64_t cur = n;
             n = 0;
             for (int64_t pos = 0; pos < cur; ++pos) {
-                PlanDesc pd;
-                const bool has = decode(*sp, (uint32_t)buf[r & 1].hdr[pos], pd);
+                PlanDesc pd;                                  // rebuilt from the geometry word like the kernel does
+                const uint64_t g = buf[r & 1].geo[pos];
+                pd.ordinal = (uint32_t)buf[r & 1].hdr[pos];
+                pd.geo = g;
+                pd.row = sp->rows + (g & 0xFFFFFFFFULL);
+                pd.S = (int)((g >> 32) & 0xFF) + 1;
+                pd.label = (int)((g >> 40) & 0xFF) + 1;
+                pd.ns = (int)((g >> 48) & 0xFF);
+                pd.batches = sp->batches[(g >> 56) & 0xFF];
+                const bool has = true;
                 if (mode == 2)
                     run_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, SerialUniform(), sink, warp, buf[r & 1], buf[(r + 1) & 1], has, pos, pd);
                 else

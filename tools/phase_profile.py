@@ -40,5 +40,16 @@ sm = s.summary()
 cyc = list(sm.reserved)[:5]
 tot = sum(cyc) or 1
 print(f'{name}: {a.elapsed_time(b):.2f} ms, plans {space.num_plans}, B {sm.num_partition_calls}, runs {sm.num_balancer_runs}, C {sm.num_records}')
+import numpy as np  # noqa: E402
+base = (s.workspace.data_ptr() + 127) & ~127
+off = base - s.workspace.data_ptr()
+trace = s.workspace[off + 4096: off + 4096 + 512 * 16].cpu().numpy().view(np.uint64).reshape(-1, 2)
+rows = [(int(n), int(t)) for n, t in trace if t]
+if rows:
+    t0 = rows[0][1]
+    print('  round: tasks  start_us  (duration_us)')
+    for i, (n, t) in enumerate(rows):
+        dur = (rows[i + 1][1] - t) / 1e3 if i + 1 < len(rows) else 0.0
+        print(f'  {i + 1:3d}: {n:7d} {(t - t0) / 1e3:9.1f}  ({dur:8.1f})')
 for k, n in zip(cyc, ['F fetch/advance', 'P performance', 'R balance_run', 'M memory/adjust', 'C cost/emit']):
     print(f'  {n:18s} {100.0 * k / tot:6.2f} %   {k / 1e6:10.1f} Mcycles (summed over warps)')

@@ -126,7 +126,14 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
             int64_t append(bool want) const { return want ? (*count)++ : -1; }
         };
         const int smax = sp->max_stage > 0 ? sp->max_stage : METIS_MAX_STAGES;
-        const int64_t cap = rounds * tile > 0 ? rounds * tile : 1;
+        int64_t cap = 1;                  // count the admitted plans first so the lists are sized exactly
+        for (int64_t i = 0; i < rounds * tile; ++i) {
+            const int64_t ordinal = ((i / tile) * world + sh->rank) * tile + (i % tile);
+            PlanDesc pd;
+            if (!decode(*sp, ordinal, pd)) continue;
+            PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> ev(T, w);
+            if (ev.begin(pd) == 1) ++cap;
+        }
         std::vector<uint64_t> hdr[2] = {std::vector<uint64_t>(cap), std::vector<uint64_t>(cap)};
         std::vector<uint64_t> geo[2] = {std::vector<uint64_t>(cap), std::vector<uint64_t>(cap)};
         std::vector<uint8_t> tpc[2] = {std::vector<uint8_t>(cap * smax), std::vector<uint8_t>(cap * smax)};

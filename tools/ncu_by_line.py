@@ -1,0 +1,62 @@
+#!/usr/bin/env python3
+"""Developer tool: attribute `Instructions Executed` / stall samples of an ncu report to CUDA source
+lines (ncu's CSV source page is SASS-only; nvdisasm -g supplies the SASS offset -> file:line map).
+
+  python tools/ncu_by_line.py gpurun_out/<report>.ncu-rep [kernel-substring] [top-N]
+"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+rep = sys.argv[1]
+kern = sys.argv[2] if len(sys.argv) > 2 else 'het_search_kernelILi64'
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 45
+repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+lib = os.path.join(repo, 'metis_b200', 'libmetis_b200.so')
+tmp = tempfile.mkdtemp()
+subprocess.run(['cuobjdump', '-xelf', 'all', lib], cwd=tmp, capture_output=True)
+cubin = [f for f in os.listdir(tmp) if f.startswith('metis_search.') and f.endswith('.cubin')][0]
+dis = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+line_of = {}
+cur = None
+inside = False
+for ln in dis.splitlines():
+    if ln.startswith('//---') and '.text.' in ln:
+        inside = kern in ln
+        continue
+    if not inside:
+        continue
+    m = re.match(r'\s*//## File "(.*)", line (\d+)', ln)
+    if m:
+        cur = (os.path.basename(m.group(1)), int(m.group(2)))
+        continue
+    m = re.match(r'\s*/\*([0-9a-f]{4,})\*/', ln)
+    if m:
+        line_of[int(m.group(1), 16)] = cur
+csvtxt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
+                        capture_output=True, text=True).stdout
+rows = list(csv.reader(csvtxt.splitlines()))
+hdr = rows[1]
+ia, iex, ith, ism = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('Thread Instructions Executed'), hdr.index('# Samples')
+base = int(rows[2][ia], 16)
+agg = collections.defaultdict(lambda: [0, 0, 0])
+tot = [0, 0, 0]
+for r in rows[2:]:
+    off = int(r[ia], 16) - base
+    key = line_of.get(off, ('?', 0))
+    for k, idx in enumerate((iex, ith, ism)):
+        agg[key][k] += int(r[idx]); tot[k] += int(r[idx])
+src = {}
+def text(key):
+    f, n = key
+    path = os.path.join(repo, 'metis_b200', 'csrc', f)
+    if f not in src and os.path.exists(path):
+        src[f] = open(path).read().splitlines()
+    return src[f][n - 1].strip()[:90] if f in src and 0 < n <= len(src[f]) else ''
+print(f'total warp-inst {tot[0]/1e9:.3f}e9, thread/inst {tot[1]/max(tot[0],1):.2f}, samples {tot[2]}')
+for key, (ex, th, sm) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    print(f'{100*ex/tot[0]:5.1f}% inst {100*sm/max(tot[2],1):5.1f}% smp  {key[0]}:{key[1]:<5d} {text(key)}')

@@ -162,7 +162,7 @@ struct Scratch {
     uint8_t lstk[MAXS];    // stage on which the skipped sub-layer of stage s was placed
     uint8_t got[MAXS];     // stage received a leftover sub-layer
     uint8_t blk[kBlock];   // stage of each leftover of the middle block
-    uint8_t owner[MAXL];   // stage owning each real layer after the majority vote
+    uint64_t ownerw[MAXL / 8 + 1];   // byte r = stage owning real layer r after the vote (kDropped = none)
     uint64_t subw[MAXL];   // per real layer: byte q = stage of sub-layer 7r+q (below the backward tail)
 };
 
@@ -254,15 +254,37 @@ MB_HD void sub_store(uint64_t *subw, int j, int stage) {
     reinterpret_cast<uint8_t *>(subw)[(j / kH) * 8 + (j % kH)] = (uint8_t)stage;
 }
 
-// number of bytes of x (bytes 0..6) equal to c
-MB_HD int swar_count(uint64_t x, int c) {
+MB_HD int popc64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+MB_HD int ctz64(uint64_t v) {            // v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+MB_HD int clz64(uint64_t v) {            // v != 0
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+
+// 0x80 in every byte of x that equals c
+MB_HD uint64_t swar_eq(uint64_t x, int c) {
     const uint64_t y = x ^ ((uint64_t)c * kOnes);
     const uint64_t lo7 = 0x7F7F7F7F7F7F7F7FULL;
-    const uint64_t t = ~((((y & lo7) + lo7) | y) | lo7) & 0x0080808080808080ULL;   // 0x80 where a byte of y is 0
-    int n = 0;
-    for (uint64_t v = t; v; v &= v - 1) ++n;
-    return n;
+    return ~((((y & lo7) + lo7) | y) | lo7);
 }
+
+// number of bytes of x (bytes 0..6) equal to c
+MB_HD int swar_count(uint64_t x, int c) { return popc64(swar_eq(x, c) & 0x0080808080808080ULL); }
 
 template <int MAXS, int MAXL, class X>
 MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x) {
@@ -287,12 +309,34 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         for (int r = 0; r + 1 < L; ++r) {
             const double d = dlay[r];
             const int nsub = (r == L - 2) ? kH - 1 : kH;     // the last 8 sub-layers are reserved
-            if (X::kUniform && nsub == kH && s < last && c > 9.0 * d) {
-                // whole layer fits with room to spare: the seven compare-and-subtract steps all take
-                // the "fits" branch (c - 7d > d even after rounding), so only the subtractions remain
-                c -= d; c -= d; c -= d; c -= d; c -= d; c -= d; c -= d;
-                w.subw[r] = (uint64_t)s * kOnes;
-                j += kH;
+            if (X::kUniform) {
+                // one task per warp: every lane runs this scalar loop on the same data
+                if (s >= last) break;
+                if (nsub == kH && c > 9.0 * d) {
+                    // whole layer fits with room to spare: all seven compare-and-subtract steps take the
+                    // "fits" branch (c - 7d > d even after rounding), so only the subtractions remain
+                    c -= d; c -= d; c -= d; c -= d; c -= d; c -= d; c -= d;
+                    w.subw[r] = (uint64_t)s * kOnes;
+                    j += kH;
+                    continue;
+                }
+                uint64_t word = 0;
+                int q = 0;
+                while (q < nsub && s < last) {
+                    int k = 0;
+                    while (q + k < nsub && c > d) { c -= d; ++k; }       // sub-layers that fit on stage s
+                    if (k) word |= (((uint64_t)s * kOnes) & ((k == 8 ? 0 : (1ULL << (8 * k))) - 1ULL)) << (8 * q);
+                    q += k;
+                    if (q < nsub) {                                      // sub-layer q does not fit: skipped
+                        w.capa[s] = c;
+                        w.fe[s] = (uint16_t)((j + q) | kBroke);
+                        ++s;
+                        c = w.capa[s];
+                        ++q;
+                    }
+                }
+                w.subw[r] = word;
+                j += nsub;
                 continue;
             }
 #pragma unroll
@@ -437,15 +481,35 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
                 else if (c2 != c1 && c2 != c0 && swar_count(v, c2) * 2 > kH) own = c2;
             }
         }
-        w.owner[r] = (uint8_t)own;
+        reinterpret_cast<uint8_t *>(w.ownerw)[r] = (uint8_t)own;
     }
     x.sync();
-    for (int r = 0; r < L; ++r) {                            // first / last / count of layers per stage
-        const int own = w.owner[r];
-        if (own != (int)kDropped) {
-            if (w.cnt[own] == 0) w.first[own] = (uint16_t)r;
-            w.lastl[own] = (uint16_t)r;
-            ++w.cnt[own];
+    uint8_t *owner = reinterpret_cast<uint8_t *>(w.ownerw);
+    if (X::kUniform) {
+        // first / last / count of the layers of each stage: one lane per stage scans the owner bytes
+        const int nw = (L + 7) / 8;
+        for (int r = L + x.lane(); r < nw * 8; r += x.width()) owner[r] = kDropped;   // pad the last word
+        x.sync();
+        for (int s = x.lane(); s < S; s += x.width()) {
+            int n = 0, fi = 0, la = 0;
+            for (int k = 0; k < nw; ++k) {
+                const uint64_t z = swar_eq(w.ownerw[k], s) & 0x8080808080808080ULL;
+                if (z) {
+                    if (n == 0) fi = 8 * k + (ctz64(z) >> 3);
+                    la = 8 * k + ((63 - clz64(z)) >> 3);
+                    n += popc64(z);
+                }
+            }
+            w.cnt[s] = (uint16_t)n; w.first[s] = (uint16_t)fi; w.lastl[s] = (uint16_t)la;
+        }
+    } else {
+        for (int r = 0; r < L; ++r) {                        // first / last / count of layers per stage
+            const int own = owner[r];
+            if (own != (int)kDropped) {
+                if (w.cnt[own] == 0) w.first[own] = (uint16_t)r;
+                w.lastl[own] = (uint16_t)r;
+                ++w.cnt[own];
+            }
         }
     }
     x.sync();
@@ -478,11 +542,11 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         newmax = x.max_all(newmax);
         if (newmax > maxc) break;                            // :352 (not committed)
         x.sync();
-        w.owner[layer] = (uint8_t)top;
+        owner[layer] = (uint8_t)top;
         w.capa[top] = ntop;
         w.capa[nb] = nnb;
-        if (top > nb) { int r = layer - 1; while (w.owner[r] != nb) --r; w.lastl[nb] = (uint16_t)r; }
-        else          { int r = layer + 1; while (w.owner[r] != nb) ++r; w.first[nb] = (uint16_t)r; }
+        if (top > nb) { int r = layer - 1; while (owner[r] != nb) --r; w.lastl[nb] = (uint16_t)r; }
+        else          { int r = layer + 1; while (owner[r] != nb) ++r; w.first[nb] = (uint16_t)r; }
         if (w.cnt[top] == 0) { w.first[top] = (uint16_t)layer; w.lastl[top] = (uint16_t)layer; }
         else {
             if (layer < (int)w.first[top]) w.first[top] = (uint16_t)layer;

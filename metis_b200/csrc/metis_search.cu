@@ -331,6 +331,7 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
     {
         Scratch<MAXS, MAXL> w;
         Scratch<MAXS, MAXL> *wsh = reinterpret_cast<Scratch<MAXS, MAXL> *>(smem + scratch_off) + (threadIdx.x >> 5);
+        asm volatile("" : "+l"(wsh));        // opaque: keep the pointer in a register instead of re-deriving it at every use
         const int lane = threadIdx.x & 31;
         const long long gwarp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
         const long long nwarps = (long long)gridDim.x * (kThreads / 32);

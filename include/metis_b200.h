@@ -220,6 +220,17 @@ int metis_layer_balance(const double *capa, const int32_t *num_stage, int64_t n,
 int64_t metis_enum_device_groups(int32_t num_stages, int32_t num_gpus, double variance,
                                  int32_t max_permute_len, uint8_t *out, int64_t capacity_rows);
 
+/*
+ * The same for every stage count first_stage..last_stage in one call, one host thread per stage count
+ * (what InterStagePlanGenerator regenerates block by block, search_space/plan.py:130-142).  Tables are
+ * written back to back into `out` (stage count s: rows_per_stage[s-first_stage] rows of s bytes).
+ * Returns the total bytes (call with out == NULL to size the buffer; a second call with the buffer
+ * recomputes the tables) or METIS_E_CAPACITY.
+ */
+int64_t metis_enum_device_group_tables(int32_t first_stage, int32_t last_stage, int32_t num_gpus,
+                                       double variance, int32_t max_permute_len, int64_t *rows_per_stage,
+                                       uint8_t *out, int64_t capacity_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,10 +7,15 @@
 // prefix-shift order of Williams' algorithm (search_space/utils.py:56-88).  `dg_idx` in the
 // reference is the position in this list, so the order is part of the contract.
 //
+// Structure: (1) list the compositions, (2) merge each one and count its permutations in closed
+// form (n! / prod mult!), (3) prefix-sum the counts into row offsets, (4) generate the
+// permutations of disjoint composition ranges on several host threads straight into the output.
 // This is enumeration (integer tuples) - the candidate evaluation itself only runs on the GPU.
 #include <stdint.h>
+#include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "../../include/metis_b200.h"
@@ -25,63 +30,14 @@ int group_sum(const Group &g) {
     return s;
 }
 
-int ilog2(int v) {
-    int c = 0;
+uint8_t ilog2(int v) {
+    uint8_t c = 0;
     while ((1 << c) < v) ++c;
     return c;
 }
 
-struct RowWriter {
-    uint8_t *out;
-    int64_t capacity;
-    int64_t count;
-    int stages;
-    bool overflow;
-    void push(const std::vector<const Group *> &perm) {
-        if (out) {
-            if (count >= capacity) { overflow = true; ++count; return; }
-            uint8_t *dst = out + count * stages;
-            int k = 0;
-            for (const Group *g : perm)
-                for (int v : *g) dst[k++] = (uint8_t)ilog2(v);
-        }
-        ++count;
-    }
-};
-
-// multiset permutations of `items` (search_space/utils.py:72-88), visiting order preserved
-void williams(std::vector<Group> items, RowWriter &w) {
-    std::sort(items.begin(), items.end());                 // utils.py:57 (tuple comparison == lexicographic)
-    const int n = (int)items.size();
-    std::vector<int> nxt(n, -1);
-    int head = 0;
-    for (int k = 1; k < n; ++k) { nxt[k] = head; head = k; }   // prepend => non-increasing chain
-    std::vector<const Group *> perm(n);
-    auto visit = [&]() {
-        int h = head, k = 0;
-        while (h != -1) { perm[k++] = &items[h]; h = nxt[h]; }
-        w.push(perm);
-    };
-    auto nth = [&](int h, int k) {
-        while (k > 0 && nxt[h] != -1) { h = nxt[h]; --k; }
-        return h;
-    };
-    int i = nth(head, n - 2), j = nth(head, n - 1);
-    visit();
-    while (nxt[j] != -1 || items[j] < items[head]) {
-        int s = (nxt[j] != -1 && !(items[i] < items[nxt[j]])) ? j : i;
-        const int t = nxt[s];
-        nxt[s] = nxt[t];
-        nxt[t] = head;
-        if (items[t] < items[head]) i = t;
-        j = nxt[i];
-        head = t;
-        visit();
-    }
-}
-
-// permute() of search_space/device_group.py:7-55
-void merge_and_permute(const std::vector<int> &comp, int max_permute_len, RowWriter &w) {
+// permute() of search_space/device_group.py:7-55 without the final permutations: the merged groups
+std::vector<Group> merge_groups(const std::vector<int> &comp, int max_permute_len) {
     std::vector<Group> groups;
     groups.reserve(comp.size());
     for (int v : comp) groups.push_back(Group{v});
@@ -113,37 +69,89 @@ void merge_and_permute(const std::vector<int> &comp, int max_permute_len, RowWri
         if (num_reduce == (int)groups.size() - max_permute_len) break;   // :48-50
         num_reduce = (int)groups.size() - max_permute_len;
     }
-    williams(groups, w);
+    std::sort(groups.begin(), groups.end());               // utils.py:57 (tuple comparison == lexicographic)
+    return groups;
+}
+
+// number of distinct permutations of a sorted multiset: n! / prod(multiplicity!)
+int64_t multiset_permutation_count(const std::vector<Group> &sorted_items) {
+    int64_t total = 1, placed = 0;
+    size_t i = 0;
+    while (i < sorted_items.size()) {
+        size_t j = i;
+        while (j < sorted_items.size() && sorted_items[j] == sorted_items[i]) ++j;
+        for (int64_t k = 1; k <= (int64_t)(j - i); ++k) total = total * (placed + k) / k;   // *= C(placed+k, k)
+        placed += (int64_t)(j - i);
+        i = j;
+    }
+    return total;
+}
+
+// multiset permutations of the sorted groups (search_space/utils.py:72-88), visiting order preserved;
+// rows (log2 codes, `stages` bytes each) are written consecutively starting at dst
+void williams_rows(const std::vector<Group> &items, int stages, uint8_t *dst) {
+    const int n = (int)items.size();
+    std::vector<int> rank(n), nxt(n, -1), off(n), len(n);
+    std::vector<uint8_t> codes;
+    for (int k = 0; k < n; ++k) {
+        rank[k] = (k > 0 && items[k] == items[k - 1]) ? rank[k - 1] : k;   // equal tuples compare equal
+        off[k] = (int)codes.size();
+        len[k] = (int)items[k].size();
+        for (int v : items[k]) codes.push_back(ilog2(v));
+    }
+    int head = 0;
+    for (int k = 1; k < n; ++k) { nxt[k] = head; head = k; }              // prepend => non-increasing chain
+    auto visit = [&]() {
+        uint8_t *p = dst;
+        for (int h = head; h != -1; h = nxt[h]) { memcpy(p, codes.data() + off[h], (size_t)len[h]); p += len[h]; }
+        dst += stages;
+    };
+    auto nth = [&](int h, int k) {
+        while (k > 0 && nxt[h] != -1) { h = nxt[h]; --k; }
+        return h;
+    };
+    int i = nth(head, n - 2), j = nth(head, n - 1);
+    visit();
+    while (nxt[j] != -1 || rank[j] < rank[head]) {
+        const int s = (nxt[j] != -1 && rank[i] >= rank[nxt[j]]) ? j : i;
+        const int t = nxt[s];
+        nxt[s] = nxt[t];
+        nxt[t] = head;
+        if (rank[t] < rank[head]) i = t;
+        j = nxt[i];
+        head = t;
+        visit();
+    }
 }
 
 // gen_dgroups_recursive (:58-81): non-decreasing compositions, lexicographic in shape index
-void compositions(int stages, int gpus, const std::vector<int> &shapes, int max_permute_len, RowWriter &w) {
+void list_compositions(int stages, int gpus, const std::vector<int> &shapes, std::vector<std::vector<int>> &out) {
     if (shapes.empty()) return;
     std::vector<int> sol;
     sol.reserve(stages);
     const int lo = shapes.front(), hi = shapes.back();
-    // iterative DFS keeps the reference's visiting order: for i in range(prev, len(shapes))
     struct Frame { int next_idx; int sum; };
     std::vector<Frame> stack;
     stack.push_back({0, 0});
     while (!stack.empty()) {
-        Frame &f = stack.back();
         const int depth = (int)stack.size() - 1;              // elements already chosen
         if (depth == stages) {
-            if (f.sum == gpus) merge_and_permute(sol, max_permute_len, w);
+            if (stack.back().sum == gpus) out.push_back(sol);
             stack.pop_back();
             if (!sol.empty()) sol.pop_back();
             continue;
         }
         bool descended = false;
-        while (f.next_idx < (int)shapes.size()) {
+        while (stack.back().next_idx < (int)shapes.size()) {
+            Frame &f = stack.back();
             const int i = f.next_idx++;
             const int g = shapes[i];
             if (g + f.sum > gpus) { f.next_idx = (int)shapes.size(); break; }   // :73-74
             const int remaining = stages - depth - 1, rest = gpus - f.sum - g;
             if (hi * remaining < rest || lo * remaining > rest) continue;       // :61-66 pruning
+            const int sum = f.sum + g;
             sol.push_back(g);
-            stack.push_back({i, f.sum + g});
+            stack.push_back({i, sum});
             descended = true;
             break;
         }
@@ -154,18 +162,86 @@ void compositions(int stages, int gpus, const std::vector<int> &shapes, int max_
     }
 }
 
-}  // namespace
+// One stage count: prepare (compositions, merged groups, row offsets), then fill rows.
+struct StageTable {
+    int stages = 0;
+    std::vector<std::vector<Group>> merged;
+    std::vector<int64_t> offset;          // row offset of each composition, size merged.size()+1
+    int64_t rows() const { return offset.empty() ? 0 : offset.back(); }
+};
 
-extern "C" int64_t metis_enum_device_groups(int32_t num_stages, int32_t num_gpus, double variance,
-                                            int32_t max_permute_len, uint8_t *out, int64_t capacity_rows) {
-    if (num_stages < 1 || num_gpus < 1 || max_permute_len < 1) return METIS_E_ARG;
+StageTable prepare_stage(int num_stages, int num_gpus, double variance, int max_permute_len) {
+    StageTable t;
+    t.stages = num_stages;
     const int share = std::max(num_gpus / num_stages, num_stages / num_gpus);   // :96-98
     const double floor_share = (double)share * variance;
     std::vector<int> shapes;
     for (int s = 1; s <= num_gpus; s <<= 1)
         if ((double)s >= floor_share) shapes.push_back(s);
-    RowWriter w{out, capacity_rows, 0, num_stages, false};
-    compositions(num_stages, num_gpus, shapes, max_permute_len, w);
-    if (w.overflow) return METIS_E_CAPACITY;
-    return w.count;
+    std::vector<std::vector<int>> comps;
+    list_compositions(num_stages, num_gpus, shapes, comps);
+    t.merged.resize(comps.size());
+    t.offset.assign(comps.size() + 1, 0);
+    for (size_t c = 0; c < comps.size(); ++c) {
+        t.merged[c] = merge_groups(comps[c], max_permute_len);
+        t.offset[c + 1] = t.offset[c] + multiset_permutation_count(t.merged[c]);
+    }
+    return t;
+}
+
+void fill_stage(const StageTable &t, uint8_t *out) {
+    for (size_t c = 0; c < t.merged.size(); ++c) williams_rows(t.merged[c], t.stages, out + t.offset[c] * t.stages);
+}
+
+template <class F>
+void parallel_for(int n, F body) {
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (nthreads > 32) nthreads = 32;
+    if (nthreads < 2 || n < 2) { for (int i = 0; i < n; ++i) body(i); return; }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; ++t)
+        pool.emplace_back([=]() { for (int i = (int)t; i < n; i += (int)nthreads) body(i); });
+    for (auto &th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" int64_t metis_enum_device_groups(int32_t num_stages, int32_t num_gpus, double variance,
+                                            int32_t max_permute_len, uint8_t *out, int64_t capacity_rows) {
+    if (num_stages < 1 || num_gpus < 1 || max_permute_len < 1) return METIS_E_ARG;
+    const StageTable t = prepare_stage(num_stages, num_gpus, variance, max_permute_len);
+    if (!out) return t.rows();
+    if (t.rows() > capacity_rows) return METIS_E_CAPACITY;
+    fill_stage(t, out);
+    return t.rows();
+}
+
+extern "C" int64_t metis_enum_device_group_tables(int32_t first_stage, int32_t last_stage, int32_t num_gpus,
+                                                  double variance, int32_t max_permute_len, int64_t *rows_per_stage,
+                                                  uint8_t *out, int64_t capacity_bytes) {
+    if (first_stage < 1 || last_stage < first_stage || num_gpus < 1 || max_permute_len < 1 || !rows_per_stage)
+        return METIS_E_ARG;
+    const int n = last_stage - first_stage + 1;
+    // the sizing call (out == NULL) and the filling call that follows it share the prepared tables
+    struct Prepared { int first, last, gpus, mpl; double variance; std::vector<StageTable> tables; };
+    static thread_local Prepared cache{0, 0, 0, 0, 0.0, {}};
+    const bool hit = cache.first == first_stage && cache.last == last_stage && cache.gpus == num_gpus &&
+                     cache.mpl == max_permute_len && cache.variance == variance && (int)cache.tables.size() == n;
+    if (!hit) {
+        cache = Prepared{first_stage, last_stage, num_gpus, max_permute_len, variance, std::vector<StageTable>(n)};
+        std::vector<StageTable> &fresh = cache.tables;
+        parallel_for(n, [&](int i) { fresh[i] = prepare_stage(first_stage + i, num_gpus, variance, max_permute_len); });
+    }
+    std::vector<StageTable> &tables = cache.tables;
+    std::vector<int64_t> byte_off(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        rows_per_stage[i] = tables[i].rows();
+        byte_off[i + 1] = byte_off[i] + tables[i].rows() * (first_stage + i);
+    }
+    if (!out) return byte_off[n];
+    if (byte_off[n] > capacity_bytes) return METIS_E_CAPACITY;
+    parallel_for(n, [&](int i) { fill_stage(tables[i], out + byte_off[i]); });
+    const int64_t total_bytes = byte_off[n];
+    cache = Prepared{0, 0, 0, 0, 0.0, {}};                 // release the prepared tables
+    return total_bytes;
 }

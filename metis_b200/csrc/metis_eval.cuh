@@ -133,6 +133,7 @@ struct Serial {
     // combine per-lane partial results: largest v, lowest index among equals / largest v
     MB_HD void argmax_first(double &, int &) const {}
     MB_HD double max_all(double v) const { return v; }
+    MB_HD void mark(int) const {}              // profiling hook (cooperative mode, profiling build)
 };
 struct SerialUniform : Serial {           // tests: the code paths of the cooperative mode, one lane
     static constexpr bool kUniform = true;
@@ -299,6 +300,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     for (int s = x.lane(); s < S; s += x.width()) { w.capa[s] = w.perf[s]; w.got[s] = 0; w.cnt[s] = 0; }
     x.sync();
 
+    x.mark(10);
     // ---- forward pass (:216-231): flat scan, layer by layer, 7 sub-layers each -----------------
     int k = 0, sTop = -1;
     bool topSkip = false;
@@ -370,6 +372,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         }
     }
 
+    x.mark(11);
     // ---- backward pass (:233-249): last stage takes a contiguous tail [m, N) -----------------
     int m;
     {
@@ -395,6 +398,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         w.capa[last] = c;
     }
 
+    x.mark(12);
     // ---- leftovers (:251-287), ascending: first the skipped sub-layers, then the middle block --
     // get_proper_stage: lo = stage of the largest assigned id below j whose stage holds nothing
     // above j, hi = stage of the smallest assigned id above j whose stage holds nothing below j.
@@ -455,6 +459,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         }
     }
 
+    x.mark(13);
     // ---- majority vote back to real layers (:290-308) ------------------------------------------
     // A stage holding >= 4 of a layer's 7 sub-layers holds the middle one or one of the first
     // three, so at most four candidates are counted (SWAR byte compare on the packed layer word).
@@ -484,6 +489,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         reinterpret_cast<uint8_t *>(w.ownerw)[r] = (uint8_t)own;
     }
     x.sync();
+    x.mark(14);
     uint8_t *owner = reinterpret_cast<uint8_t *>(w.ownerw);
     if (X::kUniform) {
         // first / last / count of the layers of each stage: one lane per stage scans the owner bytes
@@ -517,6 +523,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         w.capa[s] = w.cnt[s] ? w.perf[s] - py_sum_range(lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
     x.sync();
 
+    x.mark(15);
     // ---- boundary adjustment (:310-356): at most three committed single-layer moves ---------
     for (int n = 1; n <= 3; ++n) {
         int top = 0x7FFFFFFF;
@@ -557,6 +564,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         x.sync();
     }
 
+    x.mark(16);
     w.part[0] = 0;                                           // :358-364
     for (int s = 0; s < S; ++s) w.part[s + 1] = (uint16_t)(w.part[s] + w.cnt[s]);
     return METIS_FATAL_NONE;
@@ -920,6 +928,7 @@ struct PlanEvaluator {
             return 1;
         }
         if (attempt >= 3) return 0;
+        x.mark(21);
         const int rc = adjust_performance();
         if (rc < 0) return rc;
         return rc == 1 ? 0 : 2;
@@ -1199,6 +1208,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
     PlanEvaluator<MAXS, MAXL, X> ev(T, w, lanes);
     int step = 0, attempt = 1, nrep = 0;
     bool retry = false, cont = false, advance = false, have_state = false, costing = false;
+    lanes.mark(1);
     sink.phase(1);
     if (has) {                                               // ---- restore, P ----
         const uint64_t h = in.hdr[pos];
@@ -1215,6 +1225,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
             if (retry) w.perf[s] = in.perf[(int64_t)s * in.cap + pos];
         }
         lanes.sync();
+        lanes.mark(2);
         if (!retry) {
             sink.partition_call();
             const int rc = ev.compute_performance();
@@ -1227,6 +1238,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
         const int rc = balance_run<MAXS, MAXL>(T, plan.S, w, lanes);
         if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
     }
+    lanes.mark(20);
     sink.phase(3);
     if (has) {                                               // ---- M ----
         const int r = ev.memory_phase(attempt);
@@ -1235,6 +1247,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
         else if (r == 0) { have_state = false; advance = true; }     // memory_state = None (plan.py:225)
         else { have_state = true; nrep = attempt; costing = true; }
     }
+    lanes.mark(22);
     sink.phase(4);
     if (has && costing) {                                    // ---- C ----
         double cost;
@@ -1243,6 +1256,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
         ++step;
         advance = nrep != 1;                                 // plan.py:194-195
     }
+    lanes.mark(23);
     sink.phase(0);
     if (has && advance) {                                    // ---- chain (plan.py:197-206) ----
         for (;;) {
@@ -1250,6 +1264,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
             if (ev.valid()) { cont = true; retry = false; attempt = 1; break; }
         }
     }
+    lanes.mark(24);
     const int64_t opos = warp.append(has && cont);
     if (has && cont) {
         out.hdr[opos] = pack_task(plan.ordinal, step, attempt, nrep, retry);
@@ -1260,6 +1275,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
             if (retry) out.perf[(int64_t)s * out.cap + opos] = w.perf[s];
         }
     }
+    lanes.mark(0);
 }
 
 // ---------------------------------------------------------------------------

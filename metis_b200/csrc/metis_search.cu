@@ -264,8 +264,23 @@ struct DeviceWarp {
 };
 
 // Lane policy of the cooperative (latency) mode, see metis_eval.cuh `Serial`.
+#ifdef METIS_PROFILE_PHASES
+__device__ long long g_mark_acc[32];
+#endif
 struct WarpLanes {
     static constexpr bool kUniform = true;
+#ifdef METIS_PROFILE_PHASES
+    mutable long long t_last = 0;
+    mutable int cur = 0;
+    __device__ void mark(int id) const {
+        if ((threadIdx.x & 31) != 0) return;
+        const long long now = clock64();
+        if (t_last) atomicAdd((unsigned long long *)&g_mark_acc[cur & 31], (unsigned long long)(now - t_last));
+        cur = id; t_last = now;
+    }
+#else
+    __device__ void mark(int) const {}
+#endif
     __device__ int lane() const { return threadIdx.x & 31; }
     __device__ int width() const { return 32; }
     __device__ void sync() const { __syncwarp(); }
@@ -383,12 +398,13 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                 } else {
                     // latency mode: one task per warp on shared-memory scratch
                     UniformWarp uwarp(&rb.counts[(round + 1) % 3]);
+                    WarpLanes lanes_coop;
                     sink.leader = lane == 0;
                     for (long long pos = gwarp; pos < (long long)n; pos += nwarps) {
                         PlanDesc pd;
                         decode_task(sp, in.hdr[pos], in.geo[pos], pd);
                         const bool has = true;
-                        run_task<MAXS, MAXL>(T, *wsh, WarpLanes(), sink, uwarp, in, nxt, has, pos, pd);
+                        run_task<MAXS, MAXL>(T, *wsh, lanes_coop, sink, uwarp, in, nxt, has, pos, pd);
                     }
                     sink.leader = true;
                 }
@@ -571,6 +587,14 @@ extern "C" {
 
 const char *metis_last_error(void) { return g_err; }
 int metis_abi_version(void) { return METIS_ABI_VERSION; }
+#ifdef METIS_PROFILE_PHASES
+int metis_debug_marks(long long *out32, int reset) {
+    long long zero[32] = {0};
+    if (out32) cudaMemcpyFromSymbol(out32, g_mark_acc, sizeof(zero));
+    if (reset) cudaMemcpyToSymbol(g_mark_acc, zero, sizeof(zero));
+    return 0;
+}
+#endif
 void metis_set_profile_events(void *before_kernel, void *after_kernel) {
     g_ev_before = static_cast<cudaEvent_t>(before_kernel);
     g_ev_after = static_cast<cudaEvent_t>(after_kernel);

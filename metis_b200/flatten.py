@@ -207,6 +207,31 @@ def enumerate_device_groups(num_stages: int, num_gpus: int, variance, max_permut
     return out
 
 
+def enumerate_device_group_tables(first_stage: int, last_stage: int, num_gpus: int, variance, max_permute_len: int,
+                                  lib=None) -> Dict[int, np.ndarray]:
+    """All row tables for stage counts first_stage..last_stage in one threaded library call."""
+    lib = lib or native.load_library()
+    n = last_stage - first_stage + 1
+    counts = np.zeros(n, dtype=np.int64)
+    total = lib.metis_enum_device_group_tables(first_stage, last_stage, num_gpus, float(variance), max_permute_len,
+                                               counts.ctypes.data, None, 0)
+    if total < 0:
+        raise native.MetisNativeError(f'metis_enum_device_group_tables failed ({total})')
+    blob = np.empty(max(int(total), 1), dtype=np.uint8)
+    got = lib.metis_enum_device_group_tables(first_stage, last_stage, num_gpus, float(variance), max_permute_len,
+                                             counts.ctypes.data, blob.ctypes.data, int(total))
+    if got != total:
+        raise native.MetisNativeError('metis_enum_device_group_tables: inconsistent size')
+    out: Dict[int, np.ndarray] = {}
+    off = 0
+    for i in range(n):
+        stages = first_stage + i
+        size = int(counts[i]) * stages
+        out[stages] = blob[off:off + size].reshape(int(counts[i]), stages)
+        off += size
+    return out
+
+
 @dataclass
 class FlatPlanSpace:
     """Numpy twin of MetisPlanSpace."""
@@ -243,7 +268,8 @@ def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_la
     """Block structure of InterStagePlanGenerator.__next__ (search_space/plan.py:153-175),
     including the mislabelled num_stage=1 block of every later node sequence (quirk Q1)."""
     cap = min(num_devices, num_layers)
-    cache: Dict[int, np.ndarray] = {}
+    lib = lib or native.load_library()
+    cache: Dict[int, np.ndarray] = enumerate_device_group_tables(1, cap + 1, num_devices, variance, max_permute_len, lib)
 
     def rows_of(stages: int) -> np.ndarray:
         if stages not in cache:

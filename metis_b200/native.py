@@ -74,7 +74,8 @@ BLOCK_DTYPE = [('first_ordinal', '<i8'), ('rows_offset', '<i8'), ('num_rows', '<
                ('label_stage', '<i2'), ('num_stage', '<i2'), ('reserved', '<i2', (3,))]
 
 SYMBOLS = ['metis_last_error', 'metis_abi_version', 'metis_set_profile_events', 'metis_het_workspace_bytes', 'metis_het_search',
-           'metis_het_detail', 'metis_homo_cost', 'metis_layer_balance', 'metis_enum_device_groups']
+           'metis_het_detail', 'metis_homo_cost', 'metis_layer_balance', 'metis_enum_device_groups',
+           'metis_enum_device_group_tables']
 
 _lib = None
 
@@ -114,6 +115,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.metis_enum_device_groups.restype = C.c_int64
     lib.metis_enum_device_groups.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_int64]
+    lib.metis_enum_device_group_tables.restype = C.c_int64
+    lib.metis_enum_device_group_tables.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p,
+                                                   C.c_void_p, C.c_int64]
     if lib.metis_abi_version() != 1:
         raise MetisNativeError('libmetis_b200.so ABI version mismatch; rebuild')
     if path == LIB_PATH:

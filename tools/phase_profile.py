@@ -34,11 +34,18 @@ s.shard.reserved = int(os.environ.get('METIS_COOP', '0'))
 for _ in range(3):
     s.launch()
 torch.cuda.synchronize()
+import ctypes
+marks = (ctypes.c_longlong * 32)()
+native._lib.metis_debug_marks(None, 1)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record(); s.launch(); b.record(); torch.cuda.synchronize()
 sm = s.summary()
 cyc = list(sm.reserved)[:5]
 tot = sum(cyc) or 1
+native._lib.metis_debug_marks(marks, 0)
+names = {0: 'between tasks', 1: 'restore', 2: 'P perf', 10: 'R fwd', 11: 'R bwd', 12: 'R leftovers', 13: 'R vote', 14: 'R cnt+capa', 15: 'R adjust', 16: 'R part', 20: 'M demand', 21: 'M reweight', 22: 'C cost', 23: 'chain', 24: 'save'}
+mt = sum(marks) or 1
+print('  cooperative-mode marks (leader-lane cycles): ' + ', '.join(f'{names.get(i, i)} {100.0 * marks[i] / mt:.1f}%' for i in range(32) if marks[i]))
 print(f'{name}: {a.elapsed_time(b):.2f} ms, plans {space.num_plans}, B {sm.num_partition_calls}, runs {sm.num_balancer_runs}, C {sm.num_records}')
 import numpy as np  # noqa: E402
 base = (s.workspace.data_ptr() + 127) & ~127

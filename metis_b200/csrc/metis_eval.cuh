@@ -133,6 +133,7 @@ struct Serial {
     // combine per-lane partial results: largest v, lowest index among equals / largest v
     MB_HD void argmax_first(double &, int &) const {}
     MB_HD double max_all(double v) const { return v; }
+    MB_HD bool any(bool p) const { return p; }
     MB_HD void mark(int) const {}              // profiling hook (cooperative mode, profiling build)
 };
 struct SerialUniform : Serial {           // tests: the code paths of the cooperative mode, one lane
@@ -402,31 +403,44 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     // ---- leftovers (:251-287), ascending: first the skipped sub-layers, then the middle block --
     // get_proper_stage: lo = stage of the largest assigned id below j whose stage holds nothing
     // above j, hi = stage of the smallest assigned id above j whose stage holds nothing below j.
-    for (int s = 0; s < last; ++s) {
-        const uint16_t e = w.fe[s];
-        if ((e & (kBroke | kTaken)) != kBroke) continue;
-        const int j = e & kPos;
-        int lo = 0;
-        for (int u = s;; --u) {
-            if (u < s) {                                      // skipped sub-layer of stage u (already placed)
-                const int t = w.lstk[u];
-                const bool above = (t == last) || (fwd_nonempty(w, t) && fwd_start(w, t) > j);
-                if (!above) { lo = t; break; }
+    {
+        int start = 0;                                        // first sub-layer of stage s's forward interval
+        for (int s = 0; s < last; ++s) {
+            const uint16_t e = w.fe[s];
+            const int pos = e & kPos;
+            const int next_start = pos + ((e & kBroke) ? 1 : 0);
+            if ((e & (kBroke | kTaken)) != kBroke) { start = next_start; continue; }
+            const int j = pos;
+            int lo = 0;
+            if (pos > start) {
+                lo = s;                                       // common case: stage s itself ends right below j
+            } else {
+                for (int u = s;; --u) {
+                    if (u < s) {                              // skipped sub-layer of stage u (already placed)
+                        const int t = w.lstk[u];
+                        const bool above = (t == last) || (fwd_nonempty(w, t) && fwd_start(w, t) > j);
+                        if (!above) { lo = t; break; }
+                    }
+                    if (fwd_nonempty(w, u)) { lo = u; break; }
+                    if (u == 0) break;
+                }
             }
-            if (fwd_nonempty(w, u)) { lo = u; break; }
-            if (u == 0) break;
+            int hi = s + 1;
+            if (hi < last && !((int)(w.fe[hi] & kPos) > next_start && !w.got[hi])) {
+                ++hi;                                         // stage s+1 is empty or already holds a leftover
+                while (hi < last && (!fwd_nonempty(w, hi) || w.got[hi])) ++hi;
+            }
+            if (lo > hi) return METIS_FATAL_SCRATCH;
+            int pick = lo;
+            double best = w.capa[lo];
+            for (int t = lo + 1; t <= hi; ++t)
+                if (w.capa[t] > best) { best = w.capa[t]; pick = t; }
+            w.capa[pick] -= dlay[j / kH];
+            w.lstk[s] = (uint8_t)pick;
+            w.got[pick] = 1;
+            sub_store(w.subw, j, pick);
+            start = next_start;
         }
-        int hi = s + 1;
-        while (hi < last && (!fwd_nonempty(w, hi) || w.got[hi])) ++hi;
-        if (lo > hi) return METIS_FATAL_SCRATCH;
-        int pick = lo;
-        double best = w.capa[lo];
-        for (int t = lo + 1; t <= hi; ++t)
-            if (w.capa[t] > best) { best = w.capa[t]; pick = t; }
-        w.capa[pick] -= dlay[j / kH];
-        w.lstk[s] = (uint8_t)pick;
-        w.got[pick] = 1;
-        sub_store(w.subw, j, pick);
     }
     if (m - k > Scratch<MAXS, MAXL>::kBlock) return METIS_FATAL_SCRATCH;
     {
@@ -840,13 +854,13 @@ struct PlanEvaluator {
     // in: w.perf (c_capa), w.extra (m_demand); out: w.perf; returns 1 = None, 0 ok, <0 fatal (negated code)
     MB_HD_NOINLINE int adjust_performance() {
         const int S = pd.S;
+        const bool one_type = T.p.num_types == 1;
+        double *ratio = reinterpret_cast<double *>(w.subw);      // free after the vote (MAXL >= MAXS)
         x.sync();
-        double need = 0.;
-        PySum avail_sum;
-        int a = 0;
-        for (int s = 0; s < S; ++s) {
-            const int b = a + group(s);
-            const double c = w.perf[s], mc = memory_capacity(a, b), md = w.extra[s];
+        for (int s = x.lane(); s < S; s += x.width()) {          // independent per stage (:80-89)
+            const int a = one_type ? 0 : rank_start(s), b = a + group(s);
+            const double c = w.perf[s], md = w.extra[s];
+            const double mc = one_type ? T.type_memory[0] * (double)group(s) : memory_capacity(a, b);
             double av, adj;
             if (mc > md) {
                 adj = c;
@@ -854,24 +868,35 @@ struct PlanEvaluator {
             } else {
                 av = 0.0;
                 adj = c * (mc / md) * 0.9;
-                need += (c - adj);
             }
             w.capa[s] = av;           // available_compute_capacity
             w.mstate[s] = adj;        // adj_sc_capa
-            avail_sum.add(av);
-            a = b;
+        }
+        x.sync();
+        double need = 0.;
+        PySum avail_sum;
+        for (int s = 0; s < S; ++s) {                            // order-dependent accumulations (:89-91)
+            const int a = one_type ? 0 : rank_start(s);
+            const double mc = one_type ? T.type_memory[0] * (double)group(s) : memory_capacity(a, a + group(s));
+            if (!(mc > w.extra[s])) need += (w.perf[s] - w.mstate[s]);
+            avail_sum.add(w.capa[s]);
         }
         if (avail_sum.result() < need) return 1;
-        for (int s = 0; s < S; ++s) w.extra[s] = 0.;
+        x.sync();
+        for (int s = x.lane(); s < S; s += x.width()) w.extra[s] = 0.;
+        x.sync();
         int guard = 0;
         while (need > 0.01) {
             PySum tot;
             for (int s = 0; s < S; ++s) tot.add(w.capa[s] > 0.001 ? w.perf[s] : 0.0);
             const double tmp_total = tot.result();
-            for (int s = 0; s < S; ++s) {
+            x.sync();
+            for (int s = x.lane(); s < S; s += x.width())        // c_capa_ratio list (:98), before the updates
+                ratio[s] = w.capa[s] > 0.001 ? w.perf[s] / tmp_total : 0.0;
+            x.sync();
+            for (int s = 0; s < S; ++s) {                        // :100-104, sequential: `need` changes as it goes
                 const double av = w.capa[s];
-                const double ratio = av > 0.001 ? w.perf[s] / tmp_total : 0.0;
-                const double want = need * ratio;
+                const double want = need * ratio[s];
                 const double give = want > av ? av : want;
                 w.extra[s] += give;
                 w.capa[s] -= give;
@@ -879,7 +904,8 @@ struct PlanEvaluator {
             }
             if (++guard > 4096) return -METIS_FATAL_HANG;
         }
-        for (int s = 0; s < S; ++s) w.perf[s] = w.extra[s] + w.mstate[s];
+        x.sync();
+        for (int s = x.lane(); s < S; s += x.width()) w.perf[s] = w.extra[s] + w.mstate[s];
         x.sync();
         return 0;
     }
@@ -1067,37 +1093,33 @@ struct PlanEvaluator {
             w.extra[s] = err;
         }
         x.sync();
-        PySum lens_sum;
+        bool bad = false;
+        for (int s = x.lane(); s < nstage; s += x.width()) bad = bad || (w.extra[s] != 0.0);
+        if (x.any(bad)) return 1;                             // KeyError raised while costing a stage
+        double *ppterm = reinterpret_cast<double *>(w.subw);  // free after the vote (MAXL >= MAXS)
         double max_len = -INFINITY, max_upd = -INFINITY, max_dp = -INFINITY;
-        double pp_cost = 0., fb_sync = 0.;
-        int a = 0;
-        for (int s = 0; s < nstage; ++s) {
+        for (int s = x.lane(); s < nstage; s += x.width()) {  // independent per-stage terms
             const int g = w.gcode[s], tpc = w.tpc[s];
-            const int b = a + (1 << g);
             const int la = w.part[s], lb = w.part[s + 1];
             const int ldp = g - tpc;
             const int mbs = bs_total >> ldp;
             const double inv_tp = pow2_neg(tpc);              // 1 / tp, exact power of two
-            if (w.extra[s] != 0.0) return 1;                  // KeyError raised while costing stage s
-            const double len = w.capa[s];
-            lens_sum.add(len);
-            if (len > max_len) max_len = len;
-
-            if (s == nstage - 1) {
-                double v;
-                if (fb_sync_cost(a, b, tpc, mbs, v)) return 1;
-                fb_sync = v * (double)pd.batches;
-            } else if (ubw) {                                 // :224-227 via the derived tables
-                pp_cost += (lb == Lm - 1) ? T.pp_vocab[mbs * T.p.num_tp + tpc] : T.pp_hidden[mbs];
-            } else {
-                double act;
-                if (lb == Lm - 1)
-                    act = (double)((int64_t)mbs * T.p.sequence_length * T.p.vocab_size) * inv_tp;
-                else
-                    act = (double)((int64_t)mbs * T.p.sequence_length * T.p.hidden_size);
-                const int b2 = b + group(s + 1);
-                pp_cost += act / (bw_of_node_range(a / per, (b2 - 1) / per) * 1048576.0);
+            if (w.capa[s] > max_len) max_len = w.capa[s];
+            double pp = 0.0;
+            if (s < nstage - 1) {
+                if (ubw) {                                    // :224-227 via the derived tables
+                    pp = (lb == Lm - 1) ? T.pp_vocab[mbs * T.p.num_tp + tpc] : T.pp_hidden[mbs];
+                } else {
+                    double act;
+                    if (lb == Lm - 1)
+                        act = (double)((int64_t)mbs * T.p.sequence_length * T.p.vocab_size) * inv_tp;
+                    else
+                        act = (double)((int64_t)mbs * T.p.sequence_length * T.p.hidden_size);
+                    const int a = rank_start(s), b2 = rank_start(s + 2);
+                    pp = act / (bw_of_node_range(a / per, (b2 - 1) / per) * 1048576.0);
+                }
             }
+            ppterm[s] = pp;
             // get_parameter_size_by_stage (model/activation_parameter.py:40-51)
             int ntr = lb - la;
             double params = 0.0;
@@ -1108,12 +1130,28 @@ struct PlanEvaluator {
             if (ubw) dpc = T.dpk[ldp] * params;
             else {
                 const int dp = 1 << ldp;
-                dpc = (double)(2 * (dp - 1)) / ((double)dp * (dp_bandwidth(a, dp, 1 << tpc) * 1048576.0)) * params;
+                dpc = (double)(2 * (dp - 1)) / ((double)dp * (dp_bandwidth(rank_start(s), dp, 1 << tpc) * 1048576.0)) * params;
             }
             if (dpc > max_dp) max_dp = dpc;
             const double upd = T.p.optimizer_time * inv_tp * T.ratio[lb - la];   // :145-147
             if (upd > max_upd) max_upd = upd;
-            a = b;
+        }
+        max_len = x.max_all(max_len);
+        max_upd = x.max_all(max_upd);
+        max_dp = x.max_all(max_dp);
+        x.sync();
+        PySum lens_sum;                                       // order-dependent sums, stage order
+        double pp_cost = 0., fb_sync = 0.;
+        for (int s = 0; s < nstage; ++s) {
+            lens_sum.add(w.capa[s]);
+            if (s < nstage - 1) pp_cost += ppterm[s];
+        }
+        {
+            const int s = nstage - 1;                         // _get_fb_sync_cost of the last costed stage
+            const int a = one_type ? 0 : rank_start(s), b = a + group(s);
+            double v;
+            if (fb_sync_cost(a, b, w.tpc[s], bs_total >> (w.gcode[s] - w.tpc[s]), v)) return 1;
+            fb_sync = v * (double)pd.batches;
         }
         const double exec = ((double)(pd.batches - 1) * max_len) + lens_sum.result();   // :235-236
         const double bg = T.p.batch_generator * (double)pd.batches;

@@ -284,6 +284,7 @@ struct WarpLanes {
     __device__ int lane() const { return threadIdx.x & 31; }
     __device__ int width() const { return 32; }
     __device__ void sync() const { __syncwarp(); }
+    __device__ bool any(bool p) const { return __any_sync(0xFFFFFFFFu, p); }
     __device__ void argmax_first(double &v, int &i) const {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -357,7 +358,7 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
             sink.phase(0);
             {
                 DeviceWarp warp(&rb.counts[(round + 1) % 3]);
-                if (blockIdx.x == 0 && threadIdx.x == 0) rb.counts[(round + 2) % 3] = 0;
+                if (blockIdx.x == 0 && threadIdx.x == 0) { rb.counts[(round + 2) % 3] = 0; rb.counts[4 + (round + 2) % 3] = 0; rb.counts[4 + (round + 1) % 3] = 0; }
                 for (long long b0 = wave0 + gwarp * 32; b0 < wave1; b0 += nwarps * 32) {
                     const long long i = b0 + lane;
                     PlanDesc pd;
@@ -384,7 +385,7 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
 #endif
                 if (n == 0) break;
                 DeviceWarp warp(&rb.counts[(round + 1) % 3]);
-                if (blockIdx.x == 0 && threadIdx.x == 0) rb.counts[(round + 2) % 3] = 0;
+                if (blockIdx.x == 0 && threadIdx.x == 0) { rb.counts[(round + 2) % 3] = 0; rb.counts[4 + (round + 2) % 3] = 0; }
                 const TaskBuffers &in = rb.buf[round & 1], &nxt = rb.buf[(round + 1) & 1];
                 if ((long long)n >= rb.coop_below) {
                     // throughput mode: one task per lane, 32 tasks per warp in lockstep
@@ -400,7 +401,11 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                     UniformWarp uwarp(&rb.counts[(round + 1) % 3]);
                     WarpLanes lanes_coop;
                     sink.leader = lane == 0;
-                    for (long long pos = gwarp; pos < (long long)n; pos += nwarps) {
+                    for (;;) {                                    // tasks differ in length (re-weighting): fetch dynamically
+                        unsigned int fetched = 0;
+                        if (lane == 0) fetched = atomicAdd(&rb.counts[4 + round % 3], 1u);
+                        const long long pos = __shfl_sync(0xFFFFFFFFu, fetched, 0);
+                        if (pos >= (long long)n) break;
                         PlanDesc pd;
                         decode_task(sp, in.hdr[pos], in.geo[pos], pd);
                         const bool has = true;

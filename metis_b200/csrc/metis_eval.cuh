@@ -1270,20 +1270,26 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
             if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
         }
     }
-    sink.phase(2);
-    if (has) {                                               // ---- R ----
-        sink.balancer_run();
-        const int rc = balance_run<MAXS, MAXL>(T, plan.S, w, lanes);
-        if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
-    }
-    lanes.mark(20);
-    sink.phase(3);
-    if (has) {                                               // ---- M ----
-        const int r = ev.memory_phase(attempt);
-        if (r < 0) { sink.fatal(plan.ordinal, -r, ev.aux); has = false; }
-        else if (r == 2) { cont = true; retry = true; ++attempt; }
-        else if (r == 0) { have_state = false; advance = true; }     // memory_state = None (plan.py:225)
-        else { have_state = true; nrep = attempt; costing = true; }
+    // In the cooperative mode a re-partition attempt follows immediately (same warp, state in shared
+    // memory); in the throughput mode it becomes a task of the next round so the warp stays converged.
+    for (;;) {
+        sink.phase(2);
+        if (has) {                                           // ---- R ----
+            sink.balancer_run();
+            const int rc = balance_run<MAXS, MAXL>(T, plan.S, w, lanes);
+            if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
+        }
+        lanes.mark(20);
+        sink.phase(3);
+        bool again = false;
+        if (has) {                                           // ---- M ----
+            const int r = ev.memory_phase(attempt);
+            if (r < 0) { sink.fatal(plan.ordinal, -r, ev.aux); has = false; }
+            else if (r == 2) { retry = true; ++attempt; if (X::kUniform) again = true; else cont = true; }
+            else if (r == 0) { have_state = false; advance = true; }     // memory_state = None (plan.py:225)
+            else { have_state = true; nrep = attempt; costing = true; }
+        }
+        if (!again) break;
     }
     lanes.mark(22);
     sink.phase(4);

@@ -23,7 +23,14 @@ namespace cg = cooperative_groups;
 
 namespace metis {
 
-constexpr int kThreads = 128;
+// block shape measured on B200 (profiles/): 256 threads, >= 3 blocks/SM (80 registers) beat 128 x 6 and 256 x 4
+#ifndef METIS_THREADS
+#define METIS_THREADS 256
+#endif
+#ifndef METIS_MIN_BLOCKS
+#define METIS_MIN_BLOCKS 3
+#endif
+constexpr int kThreads = METIS_THREADS;
 constexpr int kMaxS = METIS_MAX_STAGES;
 constexpr int kMaxL = METIS_MAX_LAYERS;
 constexpr int kSmemBlobMax = 160 * 1024;
@@ -325,7 +332,7 @@ struct RoundBuffers {
 };
 
 template <int MAXS, int MAXL>
-__global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? 6 : 4))
+__global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? METIS_MIN_BLOCKS : (METIS_MIN_BLOCKS * 2 + 2) / 3))
 het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                   const MetisShard sh, const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob,
                   const int use_smem, const unsigned int scratch_off, const long long slots,
@@ -347,7 +354,9 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
     {
         Scratch<MAXS, MAXL> w;
         Scratch<MAXS, MAXL> *wsh = reinterpret_cast<Scratch<MAXS, MAXL> *>(smem + scratch_off) + (threadIdx.x >> 5);
+#ifndef METIS_NO_OPAQUE
         asm volatile("" : "+l"(wsh));        // opaque: keep the pointer in a register instead of re-deriving it at every use
+#endif
         const int lane = threadIdx.x & 31;
         const long long gwarp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
         const long long nwarps = (long long)gridDim.x * (kThreads / 32);

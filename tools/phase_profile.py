@@ -15,7 +15,7 @@ from metis_b200.utils import ModelConfig  # noqa: E402
 from metis_b200.workloads import WORKLOADS, materialize, profile_file_order  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else 'c3_homo64_mpl6'
-prof = os.path.join(os.path.dirname(native.LIB_PATH), 'libmetis_b200_prof.so')
+prof = os.path.join(os.path.dirname(native.LIB_PATH), os.environ.get('METIS_LIB', 'libmetis_b200_prof.so'))
 native._lib = native.load_library(prof)
 w = WORKLOADS[name]
 tmp = tempfile.mkdtemp()

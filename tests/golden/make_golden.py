@@ -307,6 +307,30 @@ def golden_c1(procs: int):
     print(f'c1_homo: yielded={yielded} costed={len(costs)} best={min(c for _, c in costs)!r}', file=sys.stderr)
 
 
+def golden_homo_workload(w: Workload):
+    """cost_homo_cluster() of the reference on a synthetic single-type workload."""
+    with tempfile.TemporaryDirectory() as root:
+        digest = materialize(w, root)
+        order = profile_file_order(w)
+        argv = w.cli_args(root)
+        ref = import_reference()
+        sys.path.insert(0, REF)
+        import cost_homo_cluster as homo_mod
+        args, cluster, profile_data, device_types, model_config, volume = build_objects(ref, argv, order)
+        estimator = ref['cost_estimator'].HomoCostEstimator(profile_data, model_config, volume, cluster)
+        homo_mod.device_types = device_types
+        yielded = sum(1 for _ in ref['plan'].UniformPlanGenerator(cluster.get_total_num_devices(),
+                                                                  args.max_profiled_tp_degree, args.gbs))
+        with contextlib.redirect_stdout(io.StringIO()):
+            costs = homo_mod.cost_homo_cluster(args, cluster, estimator)
+        arr = {'plan': np.array([[p.dp, p.pp, p.tp, p.mbs, p.gbs] for p, _ in costs], dtype=np.int32).reshape(-1, 5),
+               'cost': np.array([c for _, c in costs], dtype=np.float64)}
+        meta = {'workload': w.name, 'inputs_sha256': digest, 'file_order': order, 'yielded': yielded,
+                'costed': len(costs)}
+        save(w.name + '_homo', meta, arr)
+        print(f'{w.name}_homo: yielded={yielded} costed={len(costs)}', file=sys.stderr)
+
+
 def golden_units():
     """Unit-level vectors from reference functions on seeded random inputs."""
     ref = import_reference()
@@ -380,6 +404,8 @@ def main():
             golden_units()
         elif name == 'c1':
             golden_c1(ns.procs)
+        elif name.endswith(':homo'):
+            golden_homo_workload(WORKLOADS[name.split(':')[0]])
         elif name.endswith(':sample'):
             golden_het_workload(WORKLOADS[name.split(':')[0]], ns.procs, sample_n=20000)
         else:

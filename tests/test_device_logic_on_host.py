@@ -50,7 +50,8 @@ def test_c1_het():
 
 
 @pytest.mark.parametrize('mode', [0, 1, 2], ids=['sequential_run', 'rounds', 'rounds_uniform_paths'])
-@pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight'])
+@pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight', 'sweep_n8_t1', 'sweep_n16_t2_v0',
+                                  'long_profile'])
 def test_synthetic(name, mode, workload_dir):
     meta, arr = load_golden(name)
     w, root, _ = workload_dir(name)
@@ -115,7 +116,7 @@ def test_units_balancer(units):
             assert g == c['part'], c
 
 
-@pytest.mark.parametrize('name', ['c3_homo64_mpl4', 'c4_het128'])
+@pytest.mark.parametrize('name', ['c3_homo64_mpl4', 'c4_het128', 'sweep_n32_t4'])
 def test_full_size_spaces_on_host(name, workload_dir):
     """8.3e4-plan C3 space (all candidates) and the 4.5e6-plan C4 space (reference-sampled ordinals)."""
     meta, arr = load_golden(name)
@@ -143,3 +144,26 @@ def test_full_size_spaces_on_host(name, workload_dir):
         s = int(S[i])
         assert det[i, 2 * s:3 * s + 1].tolist() == arr['part'][i, :s + 1].tolist()
         assert (1 << det[i, :s].astype(np.int64)).tolist() == arr['dp'][i, :s].tolist()
+
+
+@pytest.mark.parametrize('name,root_kind', [('c1', 'c1'), ('c3_homo64_mpl4', 'syn'), ('sweep_n8_t1', 'syn')])
+def test_homo_cost_on_host(name, root_kind, workload_dir):
+    """HomoCostEstimator.get_cost (device code, host build) against the reference's costs."""
+    from metis_b200 import api
+    from metis_b200.arguments import parse_args
+    if root_kind == 'c1':
+        meta, arr = load_golden('c1_homo')
+        root, sub, L, hid, seq, voc, gbs, max_tp = C1_DIR, 'profile_data_samples', 10, 4096, 1024, 51200, 128, 4
+    else:
+        meta, arr = load_golden(name + '_homo')
+        w, root, _ = workload_dir(name)
+        sub, L, hid, seq, voc, gbs, max_tp = 'profile', w.num_layers, w.hidden_size, w.sequence_length, w.vocab_size, w.gbs, w.max_tp
+    cluster, profile, types, cfg = hs.load_inputs(root, sub, meta['file_order'], L, hid, seq, voc)
+    plans = np.array([[p.dp, p.pp, p.tp, p.mbs, p.gbs] for p in api.UniformPlanGenerator(cluster.get_total_num_devices(), max_tp, gbs)
+                      if p.gbs == gbs], dtype=np.int32)
+    problem = flatten.build_problem(profile, cluster, cfg, gbs, int(plans[:, 2].max()), int(plans[:, 3].max()),
+                                    [tuple(dict.fromkeys(t.name for t in cluster.get_device_types()))])
+    cost, status = hs.host_homo_cost(problem, problem.type_names.index(types[0]), plans)
+    keep = status != 1
+    assert plans[keep].tolist() == arr['plan'].tolist()
+    assert cost[keep].tolist() == arr['cost'].tolist()

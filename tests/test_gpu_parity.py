@@ -111,7 +111,8 @@ def test_c1_het_and_homo_vs_golden_and_oracle():
     assert min(c for _, c in hom) == 621.8881853975784
 
 
-@pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight'])
+@pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight', 'sweep_n8_t1', 'sweep_n16_t2_v0',
+                                  'sweep_n32_t4', 'long_profile'])
 def test_synthetic_vs_golden(name, workload_dir):
     _gpu()
     meta, arr = load_golden(name)
@@ -166,6 +167,23 @@ def test_c4_sampled_vs_golden(workload_dir):
     # checksum-style property at full size: the summary's best is the argmin of all records
     i = int(np.lexsort((out.records['step'], out.records['ordinal'], out.records['cost']))[0])
     assert out.best[:3] == (float(out.records['cost'][i]), int(out.records['ordinal'][i]), int(out.records['step'][i]))
+
+
+@pytest.mark.parametrize('name', ['c3_homo64_mpl4', 'sweep_n8_t1'])
+def test_homo_synthetic_vs_golden(name, workload_dir):
+    _gpu()
+    from metis_b200 import api
+    from metis_b200.arguments import parse_args
+    meta, arr = load_golden(name + '_homo')
+    w, root, digest = workload_dir(name)
+    assert digest == meta['inputs_sha256']
+    cluster, profile, types, cfg = _inputs(root, 'profile', meta['file_order'], w.num_layers, w.hidden_size,
+                                           w.sequence_length, w.vocab_size)
+    args = parse_args(['--gbs', str(w.gbs), '--max_profiled_tp_degree', str(w.max_tp), '--num_layers', str(w.num_layers)])
+    volume = api.GPTActivationAndParam(cfg, profile['model']['parameters'])
+    hom = api.cost_homo_cluster(args, cluster, api.HomoCostEstimator(profile, cfg, volume, cluster), types[0], 'cuda:0')
+    assert [[p.dp, p.pp, p.tp, p.mbs, p.gbs] for p, _ in hom] == arr['plan'].tolist()
+    assert [c for _, c in hom] == arr['cost'].tolist()
 
 
 def test_fatal_keyerror_like_reference(workload_dir):

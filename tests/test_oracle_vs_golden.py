@@ -71,7 +71,8 @@ def test_c1_homo_kat2():
     assert [c for _, c in out] == arr['cost'].tolist()
 
 
-@pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight'])
+@pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight', 'sweep_n8_t1', 'sweep_n16_t2_v0',
+                                  'long_profile'])
 def test_synthetic_het(name, workload_dir):
     meta, arr = load_golden(name)
     w, root, digest = workload_dir(name)
@@ -120,3 +121,16 @@ def test_units_adjust(units):
                                              [float.fromhex(x) for x in case['md']])
         want = None if case['out'] is None else [float.fromhex(x) for x in case['out']]
         assert out == want
+
+
+@pytest.mark.parametrize('name', ['c3_homo64_mpl4', 'sweep_n8_t1'])
+def test_synthetic_homo(name, workload_dir):
+    meta, arr = load_golden(name + '_homo')
+    w, root, digest = workload_dir(name)
+    assert digest == meta['inputs_sha256']
+    cluster, profile, types, model = _oracle_inputs(root, 'profile', meta['file_order'], w.num_layers,
+                                                    w.hidden_size, w.sequence_length, w.vocab_size)
+    out, counters = orc.homo_search(profile, cluster, model, types[0], w.gbs, w.max_tp)
+    assert counters['yielded'] == meta['yielded'] and counters['costed'] == meta['costed']
+    assert [list(p) for p, _ in out] == arr['plan'].tolist()
+    assert [c for _, c in out] == arr['cost'].tolist()

@@ -186,6 +186,30 @@ MB_HD double py_sum_range(const double *x, int a, int b) {
     return f;
 }
 
+// The same, kept out of line and rolled: the cooperative mode is instruction-fetch bound
+// (profiles/: stall_no_instruction is its top stall), so it trades unrolling for code size.
+MB_HD_NOINLINE double py_sum_range_compact(const double *x, int a, int b) {
+    if (a >= b) return 0.0;
+    double f = 0.0 + x[a];
+    double c = 0.0;
+#pragma unroll 1
+    for (int i = a + 1; i < b; ++i) {
+        const double v = x[i];
+        const double t = f + v;
+        if (fabs(f) >= fabs(v)) c += (f - t) + v;
+        else c += (v - t) + f;
+        f = t;
+    }
+    if (c != 0.0 && isfinite(c)) f += c;
+    return f;
+}
+
+template <class X>
+MB_HD double sum_range(const double *x, int a, int b) {
+    if constexpr (X::kUniform) return py_sum_range_compact(x, a, b);
+    else return py_sum_range(x, a, b);
+}
+
 // Running form of the same sum for values produced on the fly.
 struct PySum {
     double f, c;
@@ -220,6 +244,7 @@ MB_HD int type_of_rank(const Tables &T, int ns, int rank) {
     const int nt = T.p.num_types;
     const int32_t *end = T.run_end + ns * nt;
     const uint8_t *typ = T.run_type + ns * nt;
+#pragma unroll 1
     for (int k = 0; k < nt; ++k)
         if (rank < end[k]) return typ[k];
     return typ[nt - 1];
@@ -298,6 +323,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     const int lim = (N - 1 - kH) > 0 ? (N - 1 - kH) : 0;   // :218
     const int last = S - 1;
 
+#pragma unroll (X::kUniform ? 1 : 0)
     for (int s = x.lane(); s < S; s += x.width()) { w.capa[s] = w.perf[s]; w.got[s] = 0; w.cnt[s] = 0; }
     x.sync();
 
@@ -309,6 +335,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         int s = 0, j = 0;
         double c = w.capa[0];
         uint8_t *subb = reinterpret_cast<uint8_t *>(w.subw);
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int r = 0; r + 1 < L; ++r) {
             const double d = dlay[r];
             const int nsub = (r == L - 2) ? kH - 1 : kH;     // the last 8 sub-layers are reserved
@@ -325,8 +352,10 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
                 }
                 uint64_t word = 0;
                 int q = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
                 while (q < nsub && s < last) {
                     int k = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
                     while (q + k < nsub && c > d) { c -= d; ++k; }       // sub-layers that fit on stage s
                     if (k) word |= (((uint64_t)s * kOnes) & ((k == 8 ? 0 : (1ULL << (8 * k))) - 1ULL)) << (8 * q);
                     q += k;
@@ -363,6 +392,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         if (s < last) {                                          // ran into the reserved tail
             w.capa[s] = c;
             w.fe[s] = (uint16_t)lim;
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int t = s + 1; t < last; ++t) w.fe[t] = (uint16_t)lim;
             k = lim;
             sTop = s;
@@ -379,13 +409,16 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     {
         double c = w.capa[last];
         const double dl = dlay[L - 1];
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int i = 0; i < kH; ++i) c -= dl;               // unconditional while len < hallucination (:237-241)
         m = N - kH;
         int sp = S - 2;
+#pragma unroll (X::kUniform ? 1 : 0)
         while (m > 0) {
             const int j = m - 1;
             bool un = (j >= k);
             if (!un) {                                       // below k only skipped sub-layers are unassigned
+#pragma unroll (X::kUniform ? 1 : 0)
                 while (sp >= 0 && (!(w.fe[sp] & kBroke) || (int)(w.fe[sp] & kPos) > j)) --sp;
                 un = (sp >= 0 && (int)(w.fe[sp] & kPos) == j);
             }
@@ -405,6 +438,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     // above j, hi = stage of the smallest assigned id above j whose stage holds nothing below j.
     {
         int start = 0;                                        // first sub-layer of stage s's forward interval
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = 0; s < last; ++s) {
             const uint16_t e = w.fe[s];
             const int pos = e & kPos;
@@ -415,6 +449,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
             if (pos > start) {
                 lo = s;                                       // common case: stage s itself ends right below j
             } else {
+#pragma unroll (X::kUniform ? 1 : 0)
                 for (int u = s;; --u) {
                     if (u < s) {                              // skipped sub-layer of stage u (already placed)
                         const int t = w.lstk[u];
@@ -428,11 +463,13 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
             int hi = s + 1;
             if (hi < last && !((int)(w.fe[hi] & kPos) > next_start && !w.got[hi])) {
                 ++hi;                                         // stage s+1 is empty or already holds a leftover
+#pragma unroll (X::kUniform ? 1 : 0)
                 while (hi < last && (!fwd_nonempty(w, hi) || w.got[hi])) ++hi;
             }
             if (lo > hi) return METIS_FATAL_SCRATCH;
             int pick = lo;
             double best = w.capa[lo];
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int t = lo + 1; t <= hi; ++t)
                 if (w.capa[t] > best) { best = w.capa[t]; pick = t; }
             w.capa[pick] -= dlay[j / kH];
@@ -445,11 +482,13 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     if (m - k > Scratch<MAXS, MAXL>::kBlock) return METIS_FATAL_SCRATCH;
     {
         int below = -1;                                       // stage of the nearest block item not on `last`
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int t = 0; t < m - k; ++t) {
             const int j = k + t;
             int lo = 0;
             if (below >= 0) lo = below;
             else if (sTop >= 0) {
+#pragma unroll (X::kUniform ? 1 : 0)
                 for (int u = sTop;; --u) {
                     if (u < sTop || topSkip) {
                         const uint16_t eu = w.fe[u];
@@ -464,6 +503,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
             }
             int pick = lo;
             double best = w.capa[lo];
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int t2 = lo + 1; t2 <= last; ++t2)
                 if (w.capa[t2] > best) { best = w.capa[t2]; pick = t2; }
             w.capa[pick] -= dlay[j / kH];
@@ -478,6 +518,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     // A stage holding >= 4 of a layer's 7 sub-layers holds the middle one or one of the first
     // three, so at most four candidates are counted (SWAR byte compare on the packed layer word).
     x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
     for (int r = x.lane(); r < L; r += x.width()) {
         const int nlow = m - kH * r;                         // sub-layers of r below the backward tail
         int own;
@@ -508,10 +549,13 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     if (X::kUniform) {
         // first / last / count of the layers of each stage: one lane per stage scans the owner bytes
         const int nw = (L + 7) / 8;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int r = L + x.lane(); r < nw * 8; r += x.width()) owner[r] = kDropped;   // pad the last word
         x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < S; s += x.width()) {
             int n = 0, fi = 0, la = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int k = 0; k < nw; ++k) {
                 const uint64_t z = swar_eq(w.ownerw[k], s) & 0x8080808080808080ULL;
                 if (z) {
@@ -523,6 +567,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
             w.cnt[s] = (uint16_t)n; w.first[s] = (uint16_t)fi; w.lastl[s] = (uint16_t)la;
         }
     } else {
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int r = 0; r < L; ++r) {                        // first / last / count of layers per stage
             const int own = owner[r];
             if (own != (int)kDropped) {
@@ -533,15 +578,18 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         }
     }
     x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
     for (int s = x.lane(); s < S; s += x.width())            // :300-306
-        w.capa[s] = w.cnt[s] ? w.perf[s] - py_sum_range(lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
+        w.capa[s] = w.cnt[s] ? w.perf[s] - sum_range<X>(lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
     x.sync();
 
     x.mark(15);
     // ---- boundary adjustment (:310-356): at most three committed single-layer moves ---------
+#pragma unroll (X::kUniform ? 1 : 0)
     for (int n = 1; n <= 3; ++n) {
         int top = 0x7FFFFFFF;
         double maxc = -INFINITY;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int t = x.lane(); t < S; t += x.width())        // stable: lowest index among equal maxima (:329-331)
             if (w.capa[t] > maxc) { maxc = w.capa[t]; top = t; }
         x.argmax_first(maxc, top);
@@ -556,6 +604,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
         const double ntop = w.capa[top] - dl;
         const double nnb = w.capa[nb] + dl;
         double newmax = -INFINITY;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int t = x.lane(); t < S; t += x.width()) {
             const double v = (t == top) ? ntop : (t == nb) ? nnb : w.capa[t];
             if (v > newmax) newmax = v;
@@ -580,6 +629,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
 
     x.mark(16);
     w.part[0] = 0;                                           // :358-364
+#pragma unroll (X::kUniform ? 1 : 0)
     for (int s = 0; s < S; ++s) w.part[s + 1] = (uint16_t)(w.part[s] + w.cnt[s]);
     return METIS_FATAL_NONE;
 }
@@ -602,6 +652,7 @@ MB_HD_NOINLINE int partition_data(const Tables &T, int ns, int rank_lo, int coun
     double perf[METIS_MAX_TYPES];
     PySum total;
     out.nruns = 0;
+#pragma unroll 1
     for (int i = 0; i < dp; ++i) {
         const int t = type_of_rank(T, ns, rank_lo + i * gsz);
         if (out.nruns == 0 || out.type[out.nruns - 1] != t) {
@@ -620,6 +671,7 @@ MB_HD_NOINLINE int partition_data(const Tables &T, int ns, int rank_lo, int coun
     const double tot = total.result();
     double frac[METIS_MAX_TYPES];
     int assigned = 0;
+#pragma unroll 1
     for (int r = 0; r < out.nruns; ++r) {
         const double v = (double)bs * (perf[r] / tot);
         const int b = (int)v;
@@ -630,9 +682,12 @@ MB_HD_NOINLINE int partition_data(const Tables &T, int ns, int rank_lo, int coun
     }
     int rem = bs - assigned;
     bool used[METIS_MAX_TYPES];
+#pragma unroll 1
     for (int r = 0; r < out.nruns; ++r) used[r] = false;
+#pragma unroll 1
     for (int it = 0; it < out.nruns && rem > 0; ++it) {      // stable descending order of the remainders
         int pick = -1;
+#pragma unroll 1
         for (int r = 0; r < out.nruns; ++r)
             if (!used[r] && (pick < 0 || frac[r] > frac[pick])) pick = r;
         used[pick] = true;
@@ -684,9 +739,11 @@ struct PlanEvaluator {
         if (pd.S > MAXS || T.p.num_layers > MAXL) return -1;
         bs_total = T.p.gbs / pd.batches;
         int lb = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
         while ((2 << lb) <= bs_total) ++lb;
         nbad = 0;
         set_groups(pd.row);
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = 0; s < pd.S; ++s) {
             const int g = pd.row[s];
             const int t = g > lb ? g - lb : 0;
@@ -701,10 +758,12 @@ struct PlanEvaluator {
         int pick = -1;
         if (have_state) {
             double best = 0.0;
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int s = 0; s < pd.S; ++s)
                 if (w.gcode[s] != w.tpc[s] && (pick < 0 || w.mstate[s] < best)) { pick = s; best = w.mstate[s]; }
         } else {                                             // default state 1/dp: largest dp first
             int best = -1;
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int s = 0; s < pd.S; ++s) {
                 const int ldp = (int)w.gcode[s] - (int)w.tpc[s];
                 if (ldp != 0 && ldp > best) { pick = s; best = ldp; }
@@ -727,6 +786,7 @@ struct PlanEvaluator {
         const uint8_t *typ = T.run_type + pd.ns * nt;
         PySum acc;
         int lo = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int k = 0; k < nt; ++k) {
             const int hi = end[k];
             const int x = (a > lo ? a : lo), y = (b < hi ? b : hi);
@@ -739,6 +799,7 @@ struct PlanEvaluator {
     // hetero replica cost for StagePerformance (model/device_group.py:40-52): sum of full-model times
     MB_HD int replica_perf_cost(int type, int tpc, int h, double &out) {
         double acc = 0.;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int bit = 30; bit >= 0; --bit) {
             const int piece = 1 << bit;
             if (!(h & piece)) continue;
@@ -756,6 +817,7 @@ struct PlanEvaluator {
         int rc = partition_data(T, pd.ns, a, b - a, dp, tpc, bs_total, hs, aux);
         if (rc) return rc;
         double mx = -INFINITY;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int r = 0; r < hs.nruns; ++r) {
             double c;
             if (hs.plus[r] > 0) {
@@ -778,6 +840,7 @@ struct PlanEvaluator {
 
     MB_HD void set_groups(const uint8_t *row) {
         int a = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = 0; s < pd.S; ++s) { w.gcode[s] = row[s]; w.rs[s] = (uint16_t)a; a += 1 << row[s]; }
         w.rs[pd.S] = (uint16_t)a;
     }
@@ -786,6 +849,7 @@ struct PlanEvaluator {
     MB_HD int compute_performance() {
         const bool one_type = T.p.num_types == 1;
         int fail = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < pd.S; s += x.width()) {
             const int g = w.gcode[s], tpc = w.tpc[s];
             double p = 0.0;
@@ -814,6 +878,7 @@ struct PlanEvaluator {
         }
         x.sync();
         PySum total;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = 0; s < pd.S; ++s) {                     // first failing stage in stage order, like the reference
             if (w.extra[s] != 0.0) {
                 const uint64_t code = (uint64_t)w.extra[s];
@@ -825,6 +890,7 @@ struct PlanEvaluator {
         const double tot = total.result();
         if (tot == 0.0) return METIS_FATAL_ZERODIV;
         x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < pd.S; s += x.width()) w.perf[s] = w.perf[s] / tot;
         x.sync();
         return 0;
@@ -836,15 +902,18 @@ struct PlanEvaluator {
         HSplit hs;                                           // whole-cluster device list (quirk Q6)
         const int rc = partition_data(T, pd.ns, 0, T.p.total_devices, dp_of(s), tpc, bs_total, hs, aux);
         if (rc) return rc;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int r = 0; r < hs.nruns; ++r)
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int i = 0; i < hs.n[r]; ++i) {
                 const int h = hs.base[r] + (i < hs.plus[r] ? 1 : 0);
+#pragma unroll (X::kUniform ? 1 : 0)
                 for (int bit = 30; bit >= 0; --bit) {
                     const int piece = 1 << bit;
                     if (!(h & piece)) continue;
                     const int key = key_of(T, type0, tpc, piece);
                     if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)piece; return METIS_FATAL_KEY_MEMORY; }
-                    demand += py_sum_range(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
+                    demand += sum_range<X>(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
                 }
             }
         return 0;
@@ -857,6 +926,7 @@ struct PlanEvaluator {
         const bool one_type = T.p.num_types == 1;
         double *ratio = reinterpret_cast<double *>(w.subw);      // free after the vote (MAXL >= MAXS)
         x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < S; s += x.width()) {          // independent per stage (:80-89)
             const int a = one_type ? 0 : rank_start(s), b = a + group(s);
             const double c = w.perf[s], md = w.extra[s];
@@ -875,6 +945,7 @@ struct PlanEvaluator {
         x.sync();
         double need = 0.;
         PySum avail_sum;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = 0; s < S; ++s) {                            // order-dependent accumulations (:89-91)
             const int a = one_type ? 0 : rank_start(s);
             const double mc = one_type ? T.type_memory[0] * (double)group(s) : memory_capacity(a, a + group(s));
@@ -883,17 +954,22 @@ struct PlanEvaluator {
         }
         if (avail_sum.result() < need) return 1;
         x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < S; s += x.width()) w.extra[s] = 0.;
         x.sync();
         int guard = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
         while (need > 0.01) {
             PySum tot;
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int s = 0; s < S; ++s) tot.add(w.capa[s] > 0.001 ? w.perf[s] : 0.0);
             const double tmp_total = tot.result();
             x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int s = x.lane(); s < S; s += x.width())        // c_capa_ratio list (:98), before the updates
                 ratio[s] = w.capa[s] > 0.001 ? w.perf[s] / tmp_total : 0.0;
             x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int s = 0; s < S; ++s) {                        // :100-104, sequential: `need` changes as it goes
                 const double av = w.capa[s];
                 const double want = need * ratio[s];
@@ -905,6 +981,7 @@ struct PlanEvaluator {
             if (++guard > 4096) return -METIS_FATAL_HANG;
         }
         x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < S; s += x.width()) w.perf[s] = w.extra[s] + w.mstate[s];
         x.sync();
         return 0;
@@ -920,6 +997,7 @@ struct PlanEvaluator {
         const int S = pd.S;
         const bool one_type = T.p.num_types == 1;
         const int type0 = T.run_type[pd.ns * T.p.num_types];
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < S; s += x.width()) {
             const int g = w.gcode[s], tpc = w.tpc[s];
             const int a = one_type ? 0 : rank_start(s), b = a + (1 << g);
@@ -928,7 +1006,7 @@ struct PlanEvaluator {
                 const int bs = bs_total >> (g - tpc);
                 const int key = key_of(T, type0, tpc, bs);
                 if (key < 0) err = (double)METIS_FATAL_KEY_MEMORY + (double)(((uint32_t)tpc << 16) | (uint32_t)bs) * 256.0;
-                else md += py_sum_range(T.mem + (size_t)key * T.p.lpad, w.part[s], w.part[s + 1]) * kMemCoef;
+                else md += sum_range<X>(T.mem + (size_t)key * T.p.lpad, w.part[s], w.part[s + 1]) * kMemCoef;
             } else {
                 const int rc = hetero_memory_demand(s, type0, md);
                 if (rc) err = (double)rc + (double)aux * 256.0;
@@ -939,6 +1017,7 @@ struct PlanEvaluator {
         }
         x.sync();
         bool oom = false;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = 0; s < S; ++s) {
             if (w.mstate[s] != 0.0) {
                 const uint64_t code = (uint64_t)w.mstate[s];
@@ -949,6 +1028,7 @@ struct PlanEvaluator {
         }
         if (!oom) {
             x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int s = x.lane(); s < S; s += x.width()) w.mstate[s] = w.capa[s];
             x.sync();
             return 1;
@@ -964,6 +1044,7 @@ struct PlanEvaluator {
     // returns attempt number 1..3, 0 = (None, -1, None), <0 = fatal (negated code)
     template <class Sink>
     MB_HD_NOINLINE int partition_layer(Sink &sink) {
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int attempt = 1; attempt <= 3; ++attempt) {
             sink.balancer_run();
             const int rc = balance_run<MAXS, MAXL>(T, pd.S, w, x);
@@ -984,6 +1065,7 @@ struct PlanEvaluator {
         const int32_t *end = T.run_end + pd.ns * nt;
         const uint8_t *typ = T.run_type + pd.ns * nt;
         int lo = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int k = 0; k < nt; ++k) {                       // types whose node run intersects [n0, n1]
             const int hi = end[k];
             if (hi > lo && n0 * per < hi && (n1 + 1) * per > lo) {
@@ -998,12 +1080,14 @@ struct PlanEvaluator {
     MB_HD double dp_bandwidth(int a, int dp, int tp) const {
         const int per = T.p.devices_per_node;
         double slow = INFINITY;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int d = 0; d < dp; ++d) {                       // group d = ranks a + d + i*dp (:148-156)
             const int n0 = (a + d) / per;
             int nlast = n0;
             bool multi = false;
             double gmin = INFINITY;
             int tprev = -1;
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int i = 0; i < tp; ++i) {
                 const int node = (a + d + i * dp) / per;
                 if (node != nlast) { multi = true; nlast = node; }
@@ -1022,19 +1106,22 @@ struct PlanEvaluator {
         uint32_t dummy;
         if (partition_data(T, pd.ns, a, b - a, dp, tpc, bs_total, hs, dummy)) return 1;
         len = -INFINITY;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int r = 0; r < hs.nruns; ++r)
+#pragma unroll (X::kUniform ? 1 : 0)
             for (int v = 0; v < 2; ++v) {
                 const int cntv = v ? hs.plus[r] : hs.n[r] - hs.plus[r];
                 const int h = hs.base[r] + v;
                 if (cntv <= 0 || h == 0) continue;
                 double acc = 0.;
+#pragma unroll (X::kUniform ? 1 : 0)
                 for (int bit = 30; bit >= 0; --bit) {
                     const int piece = 1 << bit;
                     if (!(h & piece)) continue;
                     if (piece > T.p.max_bs) return 1;            // :166-167
                     const int key = key_of(T, hs.type[r], tpc, piece);
                     if (key < 0) return 1;
-                    acc += py_sum_range(T.lc + (size_t)key * T.p.lpad, la, lb);
+                    acc += sum_range<X>(T.lc + (size_t)key * T.p.lpad, la, lb);
                 }
                 if (acc > len) len = acc;
             }
@@ -1048,6 +1135,7 @@ struct PlanEvaluator {
         const uint8_t *typ = T.run_type + pd.ns * nt;
         double mx = -INFINITY;
         int lo = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int k = 0; k < nt; ++k) {
             const int hi = end[k];
             if ((a > lo ? a : lo) < (b < hi ? b : hi)) {
@@ -1074,6 +1162,7 @@ struct PlanEvaluator {
         const int nstage = pd.label < pd.S ? pd.label : pd.S;  // zip(range(plan.num_stage), strategies)
         // execution time of every stage first (independent range sums; w.capa[s] = time, w.extra[s] = error flag)
         x.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < nstage; s += x.width()) {
             const int g = w.gcode[s], tpc = w.tpc[s];
             const int a = one_type ? 0 : rank_start(s), b = a + (1 << g);
@@ -1085,7 +1174,7 @@ struct PlanEvaluator {
             if (ta == tb) {                                   // _get_execution_cost :175-188
                 const int key = key_of(T, ta, tpc, bs_total >> ldp);
                 if (key < 0) err = 1.0;
-                else len = py_sum_range(T.lc + (size_t)key * T.p.lpad, la, lb);
+                else len = sum_range<X>(T.lc + (size_t)key * T.p.lpad, la, lb);
             } else if (hetero_exec_cost(a, b, 1 << ldp, tpc, la, lb, len)) {
                 err = 1.0;
             }
@@ -1094,10 +1183,12 @@ struct PlanEvaluator {
         }
         x.sync();
         bool bad = false;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < nstage; s += x.width()) bad = bad || (w.extra[s] != 0.0);
         if (x.any(bad)) return 1;                             // KeyError raised while costing a stage
         double *ppterm = reinterpret_cast<double *>(w.subw);  // free after the vote (MAXL >= MAXS)
         double max_len = -INFINITY, max_upd = -INFINITY, max_dp = -INFINITY;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < nstage; s += x.width()) {  // independent per-stage terms
             const int g = w.gcode[s], tpc = w.tpc[s];
             const int la = w.part[s], lb = w.part[s + 1];
@@ -1142,6 +1233,7 @@ struct PlanEvaluator {
         x.sync();
         PySum lens_sum;                                       // order-dependent sums, stage order
         double pp_cost = 0., fb_sync = 0.;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = 0; s < nstage; ++s) {
             lens_sum.add(w.capa[s]);
             if (s < nstage - 1) pp_cost += ppterm[s];
@@ -1169,9 +1261,11 @@ struct PlanEvaluator {
         if (ok == 0) return;
         bool started = false, have_state = false;
         int nrep = 0, step = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
         for (;;) {
             if (nrep == 1) return;                            // plan.py:194-195
             int attempt = 0;
+#pragma unroll (X::kUniform ? 1 : 0)
             for (;;) {
                 if (!started) started = true;                 // first strategy that can be valid (see begin)
                 else if (!next_strategy(have_state)) return;  // :203-204
@@ -1236,6 +1330,7 @@ MB_HD void begin_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp 
     if (cont) {
         out.hdr[pos] = pack_task(plan.ordinal, 0, 1, 0, false);
         out.geo[pos] = plan.geo;
+#pragma unroll 1
         for (int s = 0; s < plan.S; ++s) out.tpc[(int64_t)s * out.cap + pos] = w.tpc[s];
     }
 }
@@ -1258,6 +1353,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
         ev.bs_total = T.p.gbs / plan.batches;
         ev.nbad = 0;
         ev.set_groups(plan.row);
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = lanes.lane(); s < plan.S; s += lanes.width()) {
             w.tpc[s] = in.tpc[(int64_t)s * in.cap + pos];
             if (retry) w.perf[s] = in.perf[(int64_t)s * in.cap + pos];
@@ -1272,6 +1368,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
     }
     // In the cooperative mode a re-partition attempt follows immediately (same warp, state in shared
     // memory); in the throughput mode it becomes a task of the next round so the warp stays converged.
+#pragma unroll (X::kUniform ? 1 : 0)
     for (;;) {
         sink.phase(2);
         if (has) {                                           // ---- R ----
@@ -1303,6 +1400,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
     lanes.mark(23);
     sink.phase(0);
     if (has && advance) {                                    // ---- chain (plan.py:197-206) ----
+#pragma unroll (X::kUniform ? 1 : 0)
         for (;;) {
             if (!ev.next_strategy(have_state)) break;        // :203-204
             if (ev.valid()) { cont = true; retry = false; attempt = 1; break; }
@@ -1314,6 +1412,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
         out.hdr[opos] = pack_task(plan.ordinal, step, attempt, nrep, retry);
         out.geo[opos] = plan.geo;
         lanes.sync();
+#pragma unroll (X::kUniform ? 1 : 0)
         for (int s = lanes.lane(); s < plan.S; s += lanes.width()) {
             out.tpc[(int64_t)s * out.cap + opos] = w.tpc[s];
             if (retry) out.perf[(int64_t)s * out.cap + opos] = w.perf[s];
@@ -1331,6 +1430,7 @@ MB_HD int homo_cost(const Tables &T, int type, int dp, int pp, int tp, int mbs, 
     const int L = T.p.num_layers;
     const int per = T.p.devices_per_node;
     int tpc = 0;
+#pragma unroll 1
     while ((1 << tpc) < tp) ++tpc;
     const int key = ((1 << tpc) == tp) ? key_of(T, type, tpc, mbs) : -1;   // unprofiled tp -> KeyError (:93-94)
     if (key < 0) return 1;
@@ -1343,6 +1443,7 @@ MB_HD int homo_cost(const Tables &T, int type, int dp, int pp, int tp, int mbs, 
     double max_len = -INFINITY, max_params = -INFINITY, max_mem = -INFINITY;
     double pp_cost = 0., fb_sync = 0.;
     int a = 0;
+#pragma unroll 1
     for (int s = 0; s < pp; ++s) {
         int count = base + ((s >= 1 && s <= rem) ? 1 : 0) + (s == 0 ? 1 : 0) + (s == pp - 1 ? 1 : 0);
         const int b = a + count;
@@ -1351,6 +1452,7 @@ MB_HD int homo_cost(const Tables &T, int type, int dp, int pp, int tp, int mbs, 
         if (len > max_len) max_len = len;
         // sum(model_parameters[a:b]) over get_parameter_size(tp) (model/activation_parameter.py:34-38)
         PySum ps;
+#pragma unroll 1
         for (int r = a; r < b && r < L; ++r) {
             const double v = (r == 0) ? T.p.input_params / (double)tp
                            : (r == L - 1) ? T.p.output_params / (double)tp
@@ -1370,7 +1472,9 @@ MB_HD int homo_cost(const Tables &T, int type, int dp, int pp, int tp, int mbs, 
             if (b == L - 1) act = (double)((int64_t)mbs * T.p.sequence_length * T.p.vocab_size) / (double)tp;
             else act = (double)((int64_t)mbs * T.p.sequence_length * T.p.hidden_size);
             double bw = intra;                                // cluster_bandwidth.py:111-123
+#pragma unroll 1
             for (int d = 0; d < dp; ++d)
+#pragma unroll 1
                 for (int t = 0; t < tp; ++t) {
                     const int r0 = s * dp * tp + d * tp + t, r1 = r0 + dp * tp;
                     if (r0 / per != r1 / per) bw = inter;
@@ -1383,6 +1487,7 @@ MB_HD int homo_cost(const Tables &T, int type, int dp, int pp, int tp, int mbs, 
     const double exec = ((double)(num_mbs - 1) * max_len) + lens_sum.result();
     const double upd = T.p.optimizer_time / (double)pp / (double)tp;
     double bw = intra;                                        // :125-132
+#pragma unroll 1
     for (int p = 0; p < pp; ++p)
         if ((p * dp * tp) / per != ((p + 1) * dp * tp - 1) / per) bw = inter;
     const double dpc = (double)(2 * (dp - 1)) / ((double)dp * (bw * 1048576.0)) * max_params;

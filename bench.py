@@ -184,25 +184,34 @@ def workload_config(name, num_plans):
 # GPU side
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """Streams `nvidia-smi -lms 50` for one GPU while the timed region runs (B200_PROFILING.md clocks line)."""
+
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self.stop_flag = threading.Event()
+        self.proc = None
+        self.armed = threading.Event()
 
     def run(self):
-        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
-            'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_power_cap'
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([x.strip() for x in out.stdout.strip().split(',')])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.armed.is_set() and line.strip():
+                    self.rows.append([x.strip() for x in line.strip().split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.armed.clear()
+        if self.proc is not None:
+            self.proc.terminate()
 
     def summary(self):
         if not self.rows:
@@ -290,11 +299,14 @@ def run_ours(ns):
 
     # ---- timed: K steps, device events, L2 flushed between steps ---------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()                  # nvidia-smi is already streaming when the timed region starts
+        time.sleep(0.3)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     if sampler:
-        sampler.start()
+        sampler.armed.set()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ns.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ns.steps)]
     for a, b in kev:
@@ -311,6 +323,8 @@ def run_ours(ns):
         dist.barrier()
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - wall0
+    if sampler:
+        sampler.armed.clear()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     kern_ms = [a.elapsed_time(b) for a, b in kev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -355,7 +369,7 @@ def run_ours(ns):
     e2e_s = float(e2e_t.item())
 
     if sampler:
-        sampler.stop_flag.set()
+        sampler.stop()
         sampler.join(timeout=3)
 
     A = space.num_plans

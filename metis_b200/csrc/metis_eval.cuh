@@ -350,15 +350,11 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
                     j += kH;
                     continue;
                 }
-                uint64_t word = 0;
                 int q = 0;
-#pragma unroll (X::kUniform ? 1 : 0)
+#pragma unroll 1
                 while (q < nsub && s < last) {
-                    int k = 0;
-#pragma unroll (X::kUniform ? 1 : 0)
-                    while (q + k < nsub && c > d) { c -= d; ++k; }       // sub-layers that fit on stage s
-                    if (k) word |= (((uint64_t)s * kOnes) & ((k == 8 ? 0 : (1ULL << (8 * k))) - 1ULL)) << (8 * q);
-                    q += k;
+#pragma unroll 1
+                    while (q < nsub && c > d) { c -= d; subb[r * 8 + q] = (uint8_t)s; ++q; }   // sub-layers that fit on stage s
                     if (q < nsub) {                                      // sub-layer q does not fit: skipped
                         w.capa[s] = c;
                         w.fe[s] = (uint16_t)((j + q) | kBroke);
@@ -367,7 +363,6 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
                         ++q;
                     }
                 }
-                w.subw[r] = word;
                 j += nsub;
                 continue;
             }

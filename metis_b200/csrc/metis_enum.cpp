@@ -165,55 +165,91 @@ void list_compositions(int stages, int gpus, const std::vector<int> &shapes, std
 // One stage count: prepare (compositions, merged groups, row offsets), then fill rows.
 struct StageTable {
     int stages = 0;
+    std::vector<std::vector<int>> comps;
     std::vector<std::vector<Group>> merged;
     std::vector<int64_t> offset;          // row offset of each composition, size merged.size()+1
     int64_t rows() const { return offset.empty() ? 0 : offset.back(); }
 };
 
-StageTable prepare_stage(int num_stages, int num_gpus, double variance, int max_permute_len) {
-    StageTable t;
+void list_stage(StageTable &t, int num_stages, int num_gpus, double variance) {
     t.stages = num_stages;
     const int share = std::max(num_gpus / num_stages, num_stages / num_gpus);   // :96-98
     const double floor_share = (double)share * variance;
     std::vector<int> shapes;
     for (int s = 1; s <= num_gpus; s <<= 1)
         if ((double)s >= floor_share) shapes.push_back(s);
-    std::vector<std::vector<int>> comps;
-    list_compositions(num_stages, num_gpus, shapes, comps);
-    t.merged.resize(comps.size());
-    t.offset.assign(comps.size() + 1, 0);
-    for (size_t c = 0; c < comps.size(); ++c) {
-        t.merged[c] = merge_groups(comps[c], max_permute_len);
-        t.offset[c + 1] = t.offset[c] + multiset_permutation_count(t.merged[c]);
-    }
-    return t;
-}
-
-void fill_stage(const StageTable &t, uint8_t *out) {
-    for (size_t c = 0; c < t.merged.size(); ++c) williams_rows(t.merged[c], t.stages, out + t.offset[c] * t.stages);
+    list_compositions(num_stages, num_gpus, shapes, t.comps);
+    t.merged.resize(t.comps.size());
+    t.offset.assign(t.comps.size() + 1, 0);
 }
 
 template <class F>
-void parallel_for(int n, F body) {
+void parallel_for(int64_t n, int64_t grain, F body) {        // body(begin, end) on chunks of `grain` items
     unsigned nthreads = std::thread::hardware_concurrency();
     if (nthreads > 32) nthreads = 32;
-    if (nthreads < 2 || n < 2) { for (int i = 0; i < n; ++i) body(i); return; }
+    const int64_t chunks = (n + grain - 1) / grain;
+    if (nthreads < 2 || chunks < 2) { if (n > 0) body((int64_t)0, n); return; }
+    if ((int64_t)nthreads > chunks) nthreads = (unsigned)chunks;
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < nthreads; ++t)
-        pool.emplace_back([=]() { for (int i = (int)t; i < n; i += (int)nthreads) body(i); });
+        pool.emplace_back([=]() {
+            for (int64_t c = t; c < chunks; c += nthreads) body(c * grain, std::min(n, (c + 1) * grain));
+        });
     for (auto &th : pool) th.join();
 }
+
+// All stage counts of a range: compositions per stage count, then merge + count and row generation
+// over the flattened (stage count, composition) list so the host threads are evenly loaded.
+struct TableSet {
+    int first = 0;
+    std::vector<StageTable> tables;
+    std::vector<std::pair<int, int>> items;                  // (table index, composition index)
+
+    void prepare(int first_stage, int last_stage, int num_gpus, double variance, int max_permute_len) {
+        first = first_stage;
+        const int n = last_stage - first_stage + 1;
+        tables.assign(n, StageTable());
+        parallel_for(n, 1, [&](int64_t b, int64_t e) {
+            for (int64_t i = b; i < e; ++i) list_stage(tables[i], first_stage + (int)i, num_gpus, variance);
+        });
+        items.clear();
+        for (int i = 0; i < n; ++i)
+            for (int c = 0; c < (int)tables[i].comps.size(); ++c) items.emplace_back(i, c);
+        parallel_for((int64_t)items.size(), 256, [&](int64_t b, int64_t e) {
+            for (int64_t k = b; k < e; ++k) {
+                StageTable &t = tables[items[k].first];
+                const int c = items[k].second;
+                t.merged[c] = merge_groups(t.comps[c], max_permute_len);
+                t.offset[c + 1] = multiset_permutation_count(t.merged[c]);   // count; prefix-summed below
+            }
+        });
+        for (StageTable &t : tables)
+            for (size_t c = 0; c < t.merged.size(); ++c) t.offset[c + 1] += t.offset[c];
+    }
+
+    void fill(const std::vector<int64_t> &byte_off, uint8_t *out) const {
+        parallel_for((int64_t)items.size(), 64, [&](int64_t b, int64_t e) {
+            for (int64_t k = b; k < e; ++k) {
+                const StageTable &t = tables[items[k].first];
+                const int c = items[k].second;
+                williams_rows(t.merged[c], t.stages, out + byte_off[items[k].first] + t.offset[c] * t.stages);
+            }
+        });
+    }
+};
 
 }  // namespace
 
 extern "C" int64_t metis_enum_device_groups(int32_t num_stages, int32_t num_gpus, double variance,
                                             int32_t max_permute_len, uint8_t *out, int64_t capacity_rows) {
     if (num_stages < 1 || num_gpus < 1 || max_permute_len < 1) return METIS_E_ARG;
-    const StageTable t = prepare_stage(num_stages, num_gpus, variance, max_permute_len);
-    if (!out) return t.rows();
-    if (t.rows() > capacity_rows) return METIS_E_CAPACITY;
-    fill_stage(t, out);
-    return t.rows();
+    TableSet set;
+    set.prepare(num_stages, num_stages, num_gpus, variance, max_permute_len);
+    const int64_t rows = set.tables[0].rows();
+    if (!out) return rows;
+    if (rows > capacity_rows) return METIS_E_CAPACITY;
+    set.fill(std::vector<int64_t>{0, rows * num_stages}, out);
+    return rows;
 }
 
 extern "C" int64_t metis_enum_device_group_tables(int32_t first_stage, int32_t last_stage, int32_t num_gpus,
@@ -223,25 +259,26 @@ extern "C" int64_t metis_enum_device_group_tables(int32_t first_stage, int32_t l
         return METIS_E_ARG;
     const int n = last_stage - first_stage + 1;
     // the sizing call (out == NULL) and the filling call that follows it share the prepared tables
-    struct Prepared { int first, last, gpus, mpl; double variance; std::vector<StageTable> tables; };
+    struct Prepared { int first, last, gpus, mpl; double variance; TableSet set; };
     static thread_local Prepared cache{0, 0, 0, 0, 0.0, {}};
     const bool hit = cache.first == first_stage && cache.last == last_stage && cache.gpus == num_gpus &&
-                     cache.mpl == max_permute_len && cache.variance == variance && (int)cache.tables.size() == n;
+                     cache.mpl == max_permute_len && cache.variance == variance && (int)cache.set.tables.size() == n;
     if (!hit) {
-        cache = Prepared{first_stage, last_stage, num_gpus, max_permute_len, variance, std::vector<StageTable>(n)};
-        std::vector<StageTable> &fresh = cache.tables;
-        parallel_for(n, [&](int i) { fresh[i] = prepare_stage(first_stage + i, num_gpus, variance, max_permute_len); });
+        cache.first = first_stage; cache.last = last_stage; cache.gpus = num_gpus; cache.mpl = max_permute_len;
+        cache.variance = variance;
+        cache.set.prepare(first_stage, last_stage, num_gpus, variance, max_permute_len);
     }
-    std::vector<StageTable> &tables = cache.tables;
+    const TableSet &set = cache.set;
     std::vector<int64_t> byte_off(n + 1, 0);
     for (int i = 0; i < n; ++i) {
-        rows_per_stage[i] = tables[i].rows();
-        byte_off[i + 1] = byte_off[i] + tables[i].rows() * (first_stage + i);
+        rows_per_stage[i] = set.tables[i].rows();
+        byte_off[i + 1] = byte_off[i] + set.tables[i].rows() * (first_stage + i);
     }
     if (!out) return byte_off[n];
     if (byte_off[n] > capacity_bytes) return METIS_E_CAPACITY;
-    parallel_for(n, [&](int i) { fill_stage(tables[i], out + byte_off[i]); });
+    set.fill(byte_off, out);
     const int64_t total_bytes = byte_off[n];
-    cache = Prepared{0, 0, 0, 0, 0.0, {}};                 // release the prepared tables
+    cache.first = cache.last = 0;                            // release the prepared tables
+    cache.set = TableSet();
     return total_bytes;
 }

@@ -12,6 +12,7 @@
 // permutations of disjoint composition ranges on several host threads straight into the output.
 // This is enumeration (integer tuples) - the candidate evaluation itself only runs on the GPU.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -185,8 +186,14 @@ void list_stage(StageTable &t, int num_stages, int num_gpus, double variance) {
 
 template <class F>
 void parallel_for(int64_t n, int64_t grain, F body) {        // body(begin, end) on chunks of `grain` items
-    unsigned nthreads = std::thread::hardware_concurrency();
-    if (nthreads > 32) nthreads = 32;
+    static const unsigned configured = []() {
+        const char *env = getenv("METIS_ENUM_THREADS");
+        unsigned v = env ? (unsigned)atoi(env) : 8u;        // 8 host threads measured best on the B200 hosts
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (hw && v > hw) v = hw;
+        return v ? v : 1u;
+    }();
+    unsigned nthreads = configured;
     const int64_t chunks = (n + grain - 1) / grain;
     if (nthreads < 2 || chunks < 2) { if (n > 0) body((int64_t)0, n); return; }
     if ((int64_t)nthreads > chunks) nthreads = (unsigned)chunks;

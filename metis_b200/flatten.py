@@ -217,7 +217,7 @@ def enumerate_device_group_tables(first_stage: int, last_stage: int, num_gpus: i
                                                counts.ctypes.data, None, 0)
     if total < 0:
         raise native.MetisNativeError(f'metis_enum_device_group_tables failed ({total})')
-    blob = np.empty(max(int(total), 1), dtype=np.uint8)
+    blob = np.zeros(((max(int(total), 1) + 15) // 16) * 16, dtype=np.uint8)      # 16 B multiple for the device copy
     got = lib.metis_enum_device_group_tables(first_stage, last_stage, num_gpus, float(variance), max_permute_len,
                                              counts.ctypes.data, blob.ctypes.data, int(total))
     if got != total:
@@ -227,7 +227,7 @@ def enumerate_device_group_tables(first_stage: int, last_stage: int, num_gpus: i
     for i in range(n):
         stages = first_stage + i
         size = int(counts[i]) * stages
-        out[stages] = blob[off:off + size].reshape(int(counts[i]), stages)
+        out[stages] = blob[off:off + size].reshape(int(counts[i]), stages)   # views into the one blob
         off += size
     return out
 
@@ -304,9 +304,15 @@ def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_la
 
     tables: Dict[int, Tuple[int, np.ndarray]] = {}
     chunks, offset = [], 0
+    # fast path: every table is a view into the blob of the one library call -> ship that blob as is
+    base = cache[1].base if (1 in cache and cache[1].base is not None) else None
+    shared = base is not None and all(r.base is base for _, _, r in plan_blocks)
     for _, _, rows in plan_blocks:
         stages = rows.shape[1]
         if stages not in tables:
+            if shared:
+                tables[stages] = (rows.__array_interface__['data'][0] - base.__array_interface__['data'][0], rows)
+                continue
             tables[stages] = (offset, rows)
             chunks.append(rows.reshape(-1))
             offset += rows.size
@@ -320,7 +326,10 @@ def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_la
         blocks[i]['label_stage'] = label
         blocks[i]['num_stage'] = rows.shape[1]
         ordinal += len(rows) * len(batches)
-    blob = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)
-    if blob.size % 16:
-        blob = np.concatenate([blob, np.zeros(16 - blob.size % 16, dtype=np.uint8)])
+    if shared:
+        blob = base
+    else:
+        blob = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)
+        if blob.size % 16:
+            blob = np.concatenate([blob, np.zeros(16 - blob.size % 16, dtype=np.uint8)])
     return FlatPlanSpace(ordinal, blocks, np.asarray(batches, dtype=np.int32), blob, tables)

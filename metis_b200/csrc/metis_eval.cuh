@@ -324,6 +324,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     const int last = S - 1;
 
 #pragma unroll (X::kUniform ? 1 : 0)
+    x.sync();                                                // lane-strided writes below: earlier readers are done
     for (int s = x.lane(); s < S; s += x.width()) { w.capa[s] = w.perf[s]; w.got[s] = 0; w.cnt[s] = 0; }
     x.sync();
 
@@ -844,6 +845,7 @@ struct PlanEvaluator {
     MB_HD int compute_performance() {
         const bool one_type = T.p.num_types == 1;
         int fail = 0;
+        x.sync();
 #pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < pd.S; s += x.width()) {
             const int g = w.gcode[s], tpc = w.tpc[s];

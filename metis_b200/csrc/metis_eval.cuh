@@ -323,8 +323,8 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     const int lim = (N - 1 - kH) > 0 ? (N - 1 - kH) : 0;   // :218
     const int last = S - 1;
 
-#pragma unroll (X::kUniform ? 1 : 0)
     x.sync();                                                // lane-strided writes below: earlier readers are done
+#pragma unroll (X::kUniform ? 1 : 0)
     for (int s = x.lane(); s < S; s += x.width()) { w.capa[s] = w.perf[s]; w.got[s] = 0; w.cnt[s] = 0; }
     x.sync();
 

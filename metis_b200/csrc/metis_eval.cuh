@@ -738,14 +738,17 @@ struct PlanEvaluator {
 #pragma unroll (X::kUniform ? 1 : 0)
         while ((2 << lb) <= bs_total) ++lb;
         nbad = 0;
-        set_groups(pd.row);
-#pragma unroll (X::kUniform ? 1 : 0)
-        for (int s = 0; s < pd.S; ++s) {
+        int a = 0;
+        for (int s = 0; s < pd.S; ++s) {                     // set_groups + first strategy in one pass
             const int g = pd.row[s];
             const int t = g > lb ? g - lb : 0;
+            if (stage_bad(g, t)) { nbad = 1; return 0; }     // the plan can never become valid: drop it now
+            w.gcode[s] = (uint8_t)g;
+            w.rs[s] = (uint16_t)a;
+            a += 1 << g;
             w.tpc[s] = (uint8_t)t;
-            nbad += stage_bad(g, t) ? 1 : 0;
         }
+        w.rs[pd.S] = (uint16_t)a;
         return nbad == 0 ? 1 : 0;
     }
 

@@ -15,6 +15,7 @@
 #include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "metis_eval.cuh"
@@ -154,12 +155,25 @@ __device__ __forceinline__ void stage_blob_tma(uint8_t *smem, const uint8_t *blo
 }
 
 // ---- ordinal -> plan ---------------------------------------------------------------------------
-__device__ __forceinline__ bool decode_plan(const MetisPlanSpace &sp, int64_t ordinal, PlanDesc &pd) {
-    if (ordinal < 0 || ordinal >= sp.num_plans) return false;
+__device__ __forceinline__ int find_block(const MetisPlanSpace &sp, int64_t ordinal) {
     int lo = 0, hi = sp.num_blocks - 1;
     while (lo < hi) {                                         // last block with first_ordinal <= ordinal
         const int mid = (lo + hi + 1) >> 1;
         if (__ldg(&sp.blocks[mid].first_ordinal) <= ordinal) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// `hint` >= 0: a block known to start at or before `ordinal` (the warp's first plan); blocks are walked
+// forward from it, so the 32 consecutive plans of a warp cost one binary search instead of 32.
+__device__ __forceinline__ bool decode_plan(const MetisPlanSpace &sp, int64_t ordinal, PlanDesc &pd, int hint = -1) {
+    if (ordinal < 0 || ordinal >= sp.num_plans) return false;
+    int lo;
+    if (hint >= 0) {
+        lo = hint;
+        while (lo + 1 < sp.num_blocks && __ldg(&sp.blocks[lo + 1].first_ordinal) <= ordinal) ++lo;
+    } else {
+        lo = find_block(sp, ordinal);
     }
     const MetisPlanBlock b = sp.blocks[lo];
     const int64_t rel = ordinal - b.first_ordinal;
@@ -372,9 +386,14 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                     const long long i = b0 + lane;
                     PlanDesc pd;
                     bool has = false;
+                    // tiles are multiples of 32, so a warp's 32 plans are consecutive ordinals
+                    const long long first = ((b0 / sh.tile) * sh.world + sh.rank) * sh.tile + (b0 % sh.tile);
+                    int hint = 0;
+                    if (lane == 0 && first < sp.num_plans) hint = find_block(sp, first);
+                    hint = __shfl_sync(0xFFFFFFFFu, hint, 0);
                     if (i < wave1) {
-                        const long long ordinal = ((i / sh.tile) * sh.world + sh.rank) * sh.tile + (i % sh.tile);
-                        has = decode_plan(sp, ordinal, pd);
+                        const long long ordinal = first + lane;
+                        has = decode_plan(sp, ordinal, pd, hint);
                     }
                     begin_task<MAXS, MAXL>(T, w, sink, warp, rb.buf[(round + 1) & 1], has, pd);
                 }
@@ -706,7 +725,11 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "pack_tables_kernel");
 
-    int use_smem = lay.total <= (uint32_t)kSmemBlobMax;
+    static const uint32_t blob_max = []() {
+        const char *env = getenv("METIS_SMEM_BLOB_MAX");        // tuning knob: tables larger than this stay in global memory
+        return env ? (uint32_t)atoi(env) : (uint32_t)kSmemBlobMax;
+    }();
+    int use_smem = lay.total <= blob_max;
     unsigned int scratch_off = use_smem ? ((lay.total + 127u) & ~127u) : 0u;
     // two instantiations: the small one (S <= 64, L <= 128) halves the per-warp scratch -> more resident warps
     const bool small = space->max_stage <= 64 && problem->num_layers <= 128;

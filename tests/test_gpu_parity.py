@@ -148,6 +148,20 @@ def test_full_size_c3_vs_golden(name, workload_dir):
     assert out.best[:3] == (float(arr['cost'][i]), int(arr['ordinal'][i]), int(arr['step'][i]))
 
 
+def test_many_waves_give_the_same_records(workload_dir, monkeypatch):
+    """Task-list storage cut to 64 MiB: the 7.7e5-plan space runs as ~12 waves (each with its own sorted first
+    list and tail rounds) and must still produce every golden candidate."""
+    _gpu()
+    monkeypatch.setenv('METIS_TASK_MIB', '64')
+    meta, arr = load_golden('c3_homo64_mpl6')
+    w, root, _ = workload_dir('c3_homo64_mpl6')
+    problem, space, out = _device_search(meta, root, 'profile', _cfg(w))
+    c = meta['counters']
+    s = out.summary
+    assert (s['num_partition_calls'], s['num_balancer_runs'], s['num_records']) == (c['B'], c['runs'], c['C'])
+    _assert_arrays_equal(out, space, arr)
+
+
 def test_c4_sampled_vs_golden(workload_dir):
     """BASELINE configs[3] (3 types, 128 GPUs, 4.5e6 plans): the reference was run on 20 000 sampled
     ordinals; the full space is searched on the GPU and the sampled candidates compared."""

@@ -34,7 +34,7 @@ def main(argv=None):
                                       layer_load_balancer)
     print(f'search_time: {time.time() - start_time}s')
     print(f'len(costs): {len(estimate_costs)}')
-    ranked = sorted(estimate_costs, key=lambda kv: kv[6])
+    ranked = estimate_costs.ranked()     # = sorted(estimate_costs, key=lambda kv: kv[6]), order from the device sort
     print('rank, cost, node_sequence, device_groups, strategies(dp_deg, tp_deg), batches(number of batch), '
           'layer_partition')
     for idx, r in enumerate(ranked):

@@ -212,6 +212,26 @@ int metis_layer_balance(const double *capa, const int32_t *num_stage, int64_t n,
                         void *workspace, int64_t workspace_bytes, void *stream);
 
 /*
+ * Orders the records written by metis_het_search on the device (stable LSD radix sort, one cooperative kernel).
+ *   METIS_SORT_POSITION        by (ordinal, step): the order of `estimate_costs` as the reference appends it
+ *                              (cost_het_cluster.py:44)
+ *   METIS_SORT_RANKED          by (cost, ordinal, step): `sorted(estimate_costs, key=lambda kv: kv[-1])`
+ *                              (cost_het_cluster.py:76; Python's sort is stable, so equal costs stay in
+ *                              estimate_costs order)
+ *   METIS_SORT_BY_COST_STABLE  by cost only, equal costs keep their current order (the second half of
+ *                              METIS_SORT_RANKED, for records that are already in position order)
+ *   records   [device] n records, sorted in place
+ *   perm_out  [device] optional n uint32: perm_out[i] = index before the call of the record now at i
+ *   workspace [device] metis_sort_workspace_bytes(n) bytes
+ */
+#define METIS_SORT_POSITION        0
+#define METIS_SORT_RANKED          1
+#define METIS_SORT_BY_COST_STABLE  2
+int64_t metis_sort_workspace_bytes(int64_t n);
+int metis_sort_records(MetisRecord *records, int64_t n, int32_t mode, uint32_t *perm_out, void *workspace,
+                       int64_t workspace_bytes, void *stream);
+
+/*
  * Host-side enumeration of gen_dgroups_for_stages_with_variance (search_space/device_group.py:93-107)
  * in reference order.  Writes log2 codes, num_stages bytes per row, into out (host memory) and
  * returns the number of rows, or METIS_E_CAPACITY if capacity_rows is too small (call with

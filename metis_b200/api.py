@@ -160,9 +160,17 @@ class InterStagePlanGenerator:
 
 
 class HetSearchResult(list):
-    """List of the reference's 7-tuples plus the counters of the run."""
+    """List of the reference's 7-tuples plus the counters of the run.  ``rank_order`` is the permutation
+    that ``sorted(result, key=lambda kv: kv[6])`` applies (cost_het_cluster.py:76), computed on the device by
+    the stable record sort."""
     summary: Dict[str, int]
     timings: Dict[str, float]
+    rank_order: Optional[np.ndarray] = None
+
+    def ranked(self) -> list:
+        if self.rank_order is None:
+            return sorted(self, key=lambda kv: kv[6])
+        return [self[int(i)] for i in self.rank_order]
 
 
 def het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer=None,
@@ -195,9 +203,9 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
     dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     dp = search.DeviceProblem(problem, space, device)
-    searcher = search.HetSearcher(dp, rank, world, want_records=True, want_detail=True)
+    searcher = search.HetSearcher(dp, rank, world, want_records=True, want_detail=True, want_ranking=not dist)
     out = searcher.run()
-    summary, records, detail = out.summary, out.records, out.detail
+    summary, records, detail, rank_order = out.summary, out.records, out.detail, out.rank_order
     if dist:
         summary = search.global_counters(summary, dp.device)
         summary['fatal_ordinal'] = summary['global_fatal_ordinal'] if summary['global_fatal_ordinal'] < 2 ** 62 \
@@ -209,6 +217,7 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
         detail = np.concatenate([g[1] for g in gathered])
         order = np.lexsort((records['step'], records['ordinal']))
         records, detail = records[order], detail[order]
+        rank_order = np.argsort(records['cost'], kind='stable').astype(np.uint32)   # merged shards: ranked on the host
         for g in gathered:
             if g[4] == summary['fatal_ordinal']:
                 summary['fatal_code'], summary['fatal_aux'] = g[2], g[3]
@@ -218,6 +227,7 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
     t2 = time.perf_counter()
     result = HetSearchResult(search.materialize(records, detail, space, seqs))
     result.summary = dict(summary, num_plans=space.num_plans)
+    result.rank_order = rank_order
     result.timings = {'flatten_enumerate_s': t1 - t0, 'gpu_search_s': t2 - t1,
                       'materialize_s': time.perf_counter() - t2}
     return result

@@ -9,8 +9,8 @@ from typing import List
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmetis_b200.so')
-SOURCES = ['metis_search.cu', 'metis_enum.cpp']
-HEADERS = ['metis_eval.cuh', os.path.join('..', '..', 'include', 'metis_b200.h')]
+SOURCES = ['metis_search.cu', 'metis_rank.cu', 'metis_enum.cpp']
+HEADERS = ['metis_eval.cuh', 'metis_internal.h', os.path.join('..', '..', 'include', 'metis_b200.h')]
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-fmad=false',            # parity: no FMA contraction (CPython evaluates a*b+c in two roundings)

@@ -13,6 +13,9 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no FMA contraction: parity).
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
+#ifndef METIS_COOP_FIFO
+#define METIS_COOP_FIFO 0
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -47,6 +50,8 @@ static int arg_fail(const char *what) {
     snprintf(g_err, sizeof(g_err), "%s", what);
     return METIS_E_ARG;
 }
+int fail_cuda(cudaError_t e, const char *what) { return cuda_fail(e, what); }   // metis_internal.h
+int fail_arg(const char *what) { return arg_fail(what); }
 
 struct BlobLayout {
     uint32_t total;
@@ -419,7 +424,7 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                     grid.sync();
                     if (threadIdx.x == 0) {
                         unsigned int acc = 0;
-                        for (int k = 0; k < METIS_MAX_STAGES; ++k) { s_base[k] = acc; acc += *(volatile unsigned int *)&hist[k]; }
+                        for (int k = METIS_MAX_STAGES - 1; k >= 0; --k) { s_base[k] = acc; acc += *(volatile unsigned int *)&hist[k]; }   // longest first
                     }
                     __syncthreads();
                     for (long long pos = (long long)blockIdx.x * kThreads + threadIdx.x; pos < upto; pos += span) {
@@ -460,7 +465,12 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                 const TaskBuffers &in = rb.buf[round & 1], &nxt = rb.buf[(round + 1) & 1];
                 if ((long long)n >= rb.coop_below) {
                     // throughput mode: one task per lane, 32 tasks per warp in lockstep
-                    for (long long b0 = gwarp * 32; b0 < (long long)n; b0 += nwarps * 32) {
+                    // (batches are handed out dynamically: the list is ordered longest first)
+                    for (;;) {
+                        unsigned int fetched = 0;
+                        if (lane == 0) fetched = atomicAdd(&rb.counts[4 + round % 3], 1u);
+                        const long long b0 = 32LL * __shfl_sync(0xFFFFFFFFu, fetched, 0);
+                        if (b0 >= (long long)n) break;
                         const long long pos = b0 + lane;
                         PlanDesc pd;
                         bool has = false;
@@ -475,8 +485,10 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                     for (;;) {                                    // tasks differ in length (re-weighting): fetch dynamically
                         unsigned int fetched = 0;
                         if (lane == 0) fetched = atomicAdd(&rb.counts[4 + round % 3], 1u);
-                        const long long pos = __shfl_sync(0xFFFFFFFFu, fetched, 0);
-                        if (pos >= (long long)n) break;
+                        const long long taken = __shfl_sync(0xFFFFFFFFu, fetched, 0);
+                        if (taken >= (long long)n) break;
+                        // newest first: the tasks appended last by the previous round were its slowest
+                        const long long pos = METIS_COOP_FIFO ? taken : (long long)n - 1 - taken;
                         PlanDesc pd;
                         decode_task(sp, in.hdr[pos], in.geo[pos], pd);
                         const bool has = true;

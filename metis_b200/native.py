@@ -75,7 +75,8 @@ BLOCK_DTYPE = [('first_ordinal', '<i8'), ('rows_offset', '<i8'), ('num_rows', '<
 
 SYMBOLS = ['metis_last_error', 'metis_abi_version', 'metis_set_profile_events', 'metis_het_workspace_bytes', 'metis_het_search',
            'metis_het_detail', 'metis_homo_cost', 'metis_layer_balance', 'metis_enum_device_groups',
-           'metis_enum_device_group_tables']
+           'metis_enum_device_group_tables', 'metis_sort_workspace_bytes', 'metis_sort_records']
+SORT_POSITION, SORT_RANKED, SORT_BY_COST_STABLE = 0, 1, 2
 
 _lib = None
 
@@ -118,6 +119,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.metis_enum_device_group_tables.restype = C.c_int64
     lib.metis_enum_device_group_tables.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p,
                                                    C.c_void_p, C.c_int64]
+    lib.metis_sort_workspace_bytes.restype = C.c_int64
+    lib.metis_sort_workspace_bytes.argtypes = [C.c_int64]
+    lib.metis_sort_records.restype = C.c_int
+    lib.metis_sort_records.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     if lib.metis_abi_version() != 1:
         raise MetisNativeError('libmetis_b200.so ABI version mismatch; rebuild')
     if path == LIB_PATH:

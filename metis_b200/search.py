@@ -73,14 +73,18 @@ class HetSearchOutput:
     records: Optional[np.ndarray]                         # native.RECORD_DTYPE sorted by (ordinal, step)
     detail: Optional[np.ndarray]                          # uint8 [n, DETAIL_STRIDE] aligned with records
     d2h_bytes: int = 0
+    rank_order: Optional[np.ndarray] = None               # uint32: records[rank_order] = sorted(..., key=cost), stable
 
 
 class HetSearcher:
     """Owns the output buffers for repeated searches over one DeviceProblem."""
 
     def __init__(self, dp: DeviceProblem, rank: int = 0, world: int = 1, tile: int = 128,
-                 want_records: bool = True, want_detail: bool = False, capacity: Optional[int] = None):
+                 want_records: bool = True, want_detail: bool = False, capacity: Optional[int] = None,
+                 want_ranking: bool = False):
         self.dp = dp
+        self.want_ranking = want_ranking and want_records
+        self._sort_ws = None
         self.shard = native.MetisShard(rank, world, tile, 0)
         self.want_records = want_records
         self.want_detail = want_detail and want_records
@@ -137,21 +141,41 @@ class HetSearcher:
             if sm.num_records > 0:
                 b = sm.best
                 best = (float(b.cost), int(b.ordinal), int(b.step), int(b.num_repartition), int(b.num_stage))
-            records = detail = None
+            records = detail = rank_order = None
             d2h = C.sizeof(native.MetisSearchSummary)
             if self.want_records:
                 n = int(sm.num_records)
-                rec = self.records[:2 * n].view(n, 2)
-                meta = rec[:, 1]
-                key = ((meta & 0xFFFFFFFF) << 16) | ((meta >> 32) & 0xFFFF)
-                order = torch.argsort(key)                   # estimate_costs order = (ordinal, step)
-                rec_sorted = rec.index_select(0, order).contiguous()
-                records = rec_sorted.cpu().numpy().view(np.uint8).reshape(-1).view(native.RECORD_DTYPE)
+                # estimate_costs order = (ordinal, step): rank_records_kernel, in place
+                order = self.sort_records(n, native.SORT_POSITION, s, want_perm=self.want_detail)
+                records = self.records[:2 * n].cpu().numpy().view(np.uint8).reshape(-1).view(native.RECORD_DTYPE)
                 d2h += n * 16
                 if self.want_detail:
-                    detail = self.detail[:n].index_select(0, order).cpu().numpy()
+                    detail = self.detail[:n].index_select(0, order.long()).cpu().numpy()
                     d2h += n * native.DETAIL_STRIDE
-        return HetSearchOutput(out_summary, best, records, detail, d2h)
+                if self.want_ranking:
+                    # sorted(estimate_costs, key=cost): stable by cost on a copy of the ordered records
+                    by_cost = self.records[:2 * n].clone()
+                    rank_order = self.sort_records(n, native.SORT_BY_COST_STABLE, s, want_perm=True,
+                                                   buf=by_cost).cpu().numpy().view(np.uint32)
+                    d2h += n * 4
+        return HetSearchOutput(out_summary, best, records, detail, d2h, rank_order)
+
+    def sort_records(self, n: int, mode: int, stream: torch.cuda.Stream, want_perm: bool = False, buf=None):
+        """metis_sort_records on the first n records (device, in place); returns the permutation tensor
+        (int32 view of the uint32 indices) when asked."""
+        dp = self.dp
+        need = int(dp.lib.metis_sort_workspace_bytes(C.c_int64(n)))
+        if self._sort_ws is None or self._sort_ws.numel() < need:
+            self._sort_ws = torch.empty(need, dtype=torch.uint8, device=dp.device)
+        perm = torch.empty(max(n, 1), dtype=torch.int32, device=dp.device) if want_perm else None
+        buf = self.records if buf is None else buf
+        rc = dp.lib.metis_sort_records(C.c_void_p(buf.data_ptr()), C.c_int64(n), C.c_int32(mode),
+                                       C.c_void_p(perm.data_ptr() if perm is not None else 0),
+                                       C.c_void_p(self._sort_ws.data_ptr()), C.c_int64(self._sort_ws.numel()),
+                                       C.c_void_p(stream.cuda_stream))
+        native.check(rc, 'metis_sort_records')
+        stream.synchronize()
+        return perm[:n] if perm is not None else None
 
     def detail_for(self, picks: np.ndarray, stream: Optional[torch.cuda.Stream] = None) -> np.ndarray:
         """Strategies and partition of chosen records (metis_het_detail replay)."""

@@ -325,3 +325,65 @@ def test_cli_transcript_matches_reference_format(capsys):
     assert len(ranked) == 19
     if listed[0] == order_first:
         assert "1, 621.8881853975784, (<DeviceType.A100: 'a100'>,), [64], [(64, 1)], 1, [0, 10]" in text
+
+
+def _sort_on_device(rec_np, mode):
+    import ctypes as C
+    import torch
+    from metis_b200 import native
+    lib = native.load_library()
+    n = len(rec_np)
+    raw = torch.from_numpy(rec_np.view(np.uint8).reshape(-1).copy()).cuda() if n else torch.zeros(16, dtype=torch.uint8).cuda()
+    perm = torch.full((max(n, 1),), -1, dtype=torch.int32, device='cuda')
+    ws = torch.empty(int(lib.metis_sort_workspace_bytes(n)), dtype=torch.uint8, device='cuda')
+    rc = lib.metis_sort_records(C.c_void_p(raw.data_ptr()), C.c_int64(n), C.c_int32(mode), C.c_void_p(perm.data_ptr()),
+                                C.c_void_p(ws.data_ptr()), C.c_int64(ws.numel()),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    native.check(rc, 'metis_sort_records')
+    torch.cuda.synchronize()
+    out = raw.cpu().numpy()[:n * 16].view(native.RECORD_DTYPE) if n else rec_np[:0]
+    return out, perm.cpu().numpy()[:n].view(np.uint32)
+
+
+@pytest.mark.parametrize('n', [0, 1, 31, 32, 33, 1000, 100003, 300000])
+def test_record_sort_is_the_stable_python_sort(n):
+    """metis_sort_records against numpy's stable sorts: many equal costs (ties must keep estimate_costs
+    order, cost_het_cluster.py:76), negative / huge / infinite costs, ordinals up to 2^32, steps up to 2^16."""
+    _gpu()
+    from metis_b200 import native
+    rng = np.random.default_rng(n + 5)
+    rec = np.zeros(n, dtype=native.RECORD_DTYPE)
+    pool = np.concatenate([rng.uniform(-1e3, 1e6, 40), [np.inf, 1e300, 5e-324, 1.0, 1.0000000000000002, -7.5]])
+    rec['cost'] = rng.choice(pool, n)
+    rec['ordinal'] = rng.integers(0, 2 ** 32 - 32, n, dtype=np.uint64).astype(np.uint32) if n % 2 else rng.integers(0, 5000, n)
+    rec['step'] = rng.integers(0, 2 ** 16, n) if n % 3 == 0 else rng.integers(0, 19, n)
+    rec['num_repartition'] = rng.integers(1, 4, n)
+    rec['num_stage'] = rng.integers(1, 129, n)
+    got, perm = _sort_on_device(rec, native.SORT_POSITION)
+    want = np.lexsort((rec['step'], rec['ordinal']))
+    assert (perm == want).all() and (got.view(np.uint8) == rec[want].view(np.uint8)).all()
+    got, perm = _sort_on_device(rec, native.SORT_RANKED)
+    want = np.lexsort((rec['step'], rec['ordinal'], rec['cost']))
+    assert (perm == want).all() and (got.view(np.uint8) == rec[want].view(np.uint8)).all()
+    got, perm = _sort_on_device(rec, native.SORT_BY_COST_STABLE)
+    want = np.argsort(rec['cost'], kind='stable')
+    assert (perm == want).all() and (got.view(np.uint8) == rec[want].view(np.uint8)).all()
+
+
+def test_ranked_listing_is_sorted_estimate_costs(workload_dir):
+    """The ranked list of the CLI (cost_het_cluster.py:76-80) from the device sort equals Python's
+    sorted(estimate_costs, key=cost) on the golden candidates of the reference."""
+    torch = _gpu()
+    from metis_b200 import flatten, search
+    meta, arr = load_golden('c3_homo64_mpl4')
+    w, root, _ = workload_dir('c3_homo64_mpl4')
+    cfg = _cfg(w)
+    cluster, profile, _, mc = _inputs(root, 'profile', meta['file_order'], cfg['L'], cfg['hidden'], cfg['seq'], cfg['vocab'])
+    seqs = [tuple(s) for s in meta['node_sequences']]
+    problem = flatten.build_problem(profile, cluster, mc, cfg['gbs'], cfg['max_tp'], cfg['max_bs'], seqs)
+    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), cfg['gbs'], cfg['L'], cfg['variance'], cfg['mpl'])
+    out = search.HetSearcher(search.DeviceProblem(problem, space, 'cuda:0'), want_records=True, want_ranking=True).run()
+    gold_cost = arr['cost']
+    want = sorted(range(len(gold_cost)), key=lambda i: gold_cost[i])         # Python's stable sort, as the reference
+    assert out.rank_order.tolist() == want
+    assert (out.records['cost'].view(np.uint64) == gold_cost.view(np.uint64)).all()

@@ -105,6 +105,29 @@ def test_units_enumerator(units):
         assert ((1 << rows.astype(np.int64)) == want).all(), case
 
 
+def test_enumerator_vs_oracle_grid():
+    """The C++ enumerator (count-vector search with exact feasibility, slice-based merging) against the
+    oracle's restatement of gen_dgroups_for_stages_with_variance over a grid of cluster sizes, stage counts,
+    variances and max_permute_len - including spaces the unit fixtures do not hold (256 devices, variance 0 / 0.5)."""
+    from oracle import metis_oracle as orc
+    lib = _lib_or_skip()
+    checked = rows_total = 0
+    for ndev in (4, 8, 16, 32, 64, 128, 256):
+        for stages in sorted({1, 2, 3, 5, 7, 8, 12, 16, 24, 31, 32, 48, 64, 100, 128, ndev - 1, ndev, ndev + 1}):
+            for variance in (0, 0.5, 1):
+                for mpl in (1, 2, 4, 6):
+                    if stages < 1 or (variance != 1 and (stages > 24 or ndev > 64)) or (mpl == 6 and ndev > 64 and stages > 40):
+                        continue                      # keep the Python side to seconds
+                    rows = flatten.enumerate_device_groups(stages, ndev, variance, mpl, lib)
+                    want = orc.device_group_rows(stages, ndev, variance, mpl)
+                    assert rows.shape[0] == len(want), (ndev, stages, variance, mpl)
+                    if want:
+                        assert ((1 << rows.astype(np.int64)) == np.array(want, dtype=np.int64)).all(), (ndev, stages, variance, mpl)
+                    checked += 1
+                    rows_total += len(want)
+    assert checked > 400 and rows_total > 50000
+
+
 def test_units_balancer(units):
     by_l = {}
     for case in units['balancer']:

@@ -256,8 +256,9 @@ def run_ours(ns):
     seqs = list(itertools.permutations(w.device_types()))
     ndev = cluster.get_total_num_devices()
 
-    def enumerate_space():
-        return flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len)
+    def enumerate_space(rows_out=None):
+        return flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len,
+                                        rows_out=rows_out)
 
     t0 = time.perf_counter()
     problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
@@ -346,10 +347,9 @@ def run_ours(ns):
             dist.barrier()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        sp2 = enumerate_space()                               # host enumeration (C++), part of time-to-best
+        sp2 = enumerate_space(dp.staging('rows'))             # host enumeration (C++) straight into pinned staging
         t1 = time.perf_counter()
-        dp._host['rows'].numpy()[:sp2.rows.size] = sp2.rows   # refresh the pinned staging buffers
-        dp._host['blocks'].numpy()[:] = sp2.blocks.view(np.uint8).reshape(-1)
+        dp.restage_space(sp2)
         dp.upload(stream)                                     # H2D of every table (pinned -> HBM)
         out = full.run(stream)                                # kernels + device sort + D2H of all records
         best = exchange(out.best)

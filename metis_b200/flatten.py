@@ -208,8 +208,9 @@ def enumerate_device_groups(num_stages: int, num_gpus: int, variance, max_permut
 
 
 def enumerate_device_group_tables(first_stage: int, last_stage: int, num_gpus: int, variance, max_permute_len: int,
-                                  lib=None) -> Dict[int, np.ndarray]:
-    """All row tables for stage counts first_stage..last_stage in one threaded library call."""
+                                  lib=None, out: Optional[np.ndarray] = None) -> Dict[int, np.ndarray]:
+    """All row tables for stage counts first_stage..last_stage in one threaded library call.  ``out`` (uint8,
+    e.g. the pinned staging buffer of a DeviceProblem) receives the tables when it is large enough."""
     lib = lib or native.load_library()
     n = last_stage - first_stage + 1
     counts = np.zeros(n, dtype=np.int64)
@@ -217,7 +218,12 @@ def enumerate_device_group_tables(first_stage: int, last_stage: int, num_gpus: i
                                                counts.ctypes.data, None, 0)
     if total < 0:
         raise native.MetisNativeError(f'metis_enum_device_group_tables failed ({total})')
-    blob = np.zeros(((max(int(total), 1) + 15) // 16) * 16, dtype=np.uint8)      # 16 B multiple for the device copy
+    padded = ((max(int(total), 1) + 15) // 16) * 16                              # 16 B multiple for the device copy
+    if out is not None and out.dtype == np.uint8 and out.ndim == 1 and out.size >= padded and out.flags.c_contiguous:
+        blob = out[:padded]
+        blob[int(total):] = 0
+    else:
+        blob = np.zeros(padded, dtype=np.uint8)
     got = lib.metis_enum_device_group_tables(first_stage, last_stage, num_gpus, float(variance), max_permute_len,
                                              counts.ctypes.data, blob.ctypes.data, int(total))
     if got != total:
@@ -264,12 +270,13 @@ class FlatPlanSpace:
 
 
 def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_layers: int, variance,
-                     max_permute_len: int, lib=None) -> FlatPlanSpace:
+                     max_permute_len: int, lib=None, rows_out: Optional[np.ndarray] = None) -> FlatPlanSpace:
     """Block structure of InterStagePlanGenerator.__next__ (search_space/plan.py:153-175),
     including the mislabelled num_stage=1 block of every later node sequence (quirk Q1)."""
     cap = min(num_devices, num_layers)
     lib = lib or native.load_library()
-    cache: Dict[int, np.ndarray] = enumerate_device_group_tables(1, cap + 1, num_devices, variance, max_permute_len, lib)
+    cache: Dict[int, np.ndarray] = enumerate_device_group_tables(1, cap + 1, num_devices, variance, max_permute_len, lib,
+                                                                 rows_out)
 
     def rows_of(stages: int) -> np.ndarray:
         if stages not in cache:

@@ -46,6 +46,21 @@ class DeviceProblem:
             self.h2d_bytes += host.numel()
         self.upload()
 
+    def staging(self, name: str) -> np.ndarray:
+        """The pinned host copy of one table (numpy view): fill it in place, then upload()."""
+        return self._host[name].numpy()
+
+    def restage_space(self, space: flatten.FlatPlanSpace) -> None:
+        """Put a freshly enumerated space of the same shape into the staging buffers; tables that
+        build_plan_space(rows_out=staging('rows')) already wrote in place are not copied again."""
+        rows, blocks = self.staging('rows'), self.staging('blocks')
+        if space.rows.size > rows.size or space.blocks.nbytes != blocks.size:
+            raise ValueError('space does not fit the staging buffers of this DeviceProblem')
+        if space.rows.size and not np.shares_memory(space.rows, rows):
+            rows[:space.rows.size] = space.rows
+        blocks[:] = space.blocks.view(np.uint8).reshape(-1)
+        self.space = space
+
     def upload(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Host -> HBM copy of every table (part of the end-to-end timed region)."""
         with torch.cuda.device(self.device), torch.cuda.stream(stream or torch.cuda.current_stream(self.device)):

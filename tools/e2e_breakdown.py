@@ -40,11 +40,11 @@ for it in range(N):
     def mark(label):
         torch.cuda.synchronize()
         marks.append((label, time.perf_counter()))
-    sp2 = flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len)
+    sp2 = flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len,
+                                   rows_out=dp.staging('rows'))
     mark('host enumeration')
-    dp._host['rows'].numpy()[:sp2.rows.size] = sp2.rows
-    dp._host['blocks'].numpy()[:] = sp2.blocks.view(np.uint8).reshape(-1)
-    mark('copy into pinned staging')
+    dp.restage_space(sp2)
+    mark('restage')
     dp.upload(stream)
     mark('H2D')
     full.launch(stream)

@@ -771,7 +771,9 @@ struct PlanEvaluator {
         if (pick < 0) return false;
         const int g = w.gcode[pick], t = w.tpc[pick];
         nbad += (stage_bad(g, t + 1) ? 1 : 0) - (stage_bad(g, t) ? 1 : 0);
+        x.sync();                                            // every lane has read tpc[pick] before any lane rewrites it
         w.tpc[pick] = (uint8_t)(t + 1);
+        x.sync();
         return true;
     }
 
@@ -997,6 +999,7 @@ struct PlanEvaluator {
         const int S = pd.S;
         const bool one_type = T.p.num_types == 1;
         const int type0 = T.run_type[pd.ns * T.p.num_types];
+        x.sync();                                            // balance_run's last readers of capa/extra/mstate are done
 #pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < S; s += x.width()) {
             const int g = w.gcode[s], tpc = w.tpc[s];
@@ -1343,6 +1346,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
     bool retry = false, cont = false, advance = false, have_state = false, costing = false;
     lanes.mark(1);
     sink.phase(1);
+    lanes.sync();                                            // the warp's previous task is finished in every lane
     if (has) {                                               // ---- restore, P ----
         const uint64_t h = in.hdr[pos];
         step = (int)((h >> 32) & 0xFFFF);
@@ -1399,6 +1403,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
     }
     lanes.mark(23);
     sink.phase(0);
+    lanes.sync();                                            // the leader's record is written: lanes walk the chain together
     if (has && advance) {                                    // ---- chain (plan.py:197-206) ----
 #pragma unroll (X::kUniform ? 1 : 0)
         for (;;) {
@@ -1407,6 +1412,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
         }
     }
     lanes.mark(24);
+    lanes.sync();
     const int64_t opos = warp.append(has && cont);
     if (has && cont) {
         out.hdr[opos] = pack_task(plan.ordinal, step, attempt, nrep, retry);

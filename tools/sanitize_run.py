@@ -19,7 +19,7 @@ for name in sys.argv[1:] or ['c2_v100', 'mix32']:
     space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance, w.max_permute_len)
     dp = search.DeviceProblem(problem, space, 'cuda:0')
     for coop in (1, 1000):
-        s = search.HetSearcher(dp, want_records=True, want_detail=True)
+        s = search.HetSearcher(dp, want_records=True, want_detail=True, want_ranking=True)
         s.shard.reserved = coop
         out = s.run()
-        print(name, 'coop factor', coop, out.summary['num_records'], out.best[:3])
+        print(name, 'coop factor', coop, out.summary['num_records'], out.best[:3], 'ranked first', int(out.rank_order[0]))

@@ -291,7 +291,7 @@ struct DeviceWarp {
 
 // Lane policy of the cooperative (latency) mode, see metis_eval.cuh `Serial`.
 #ifdef METIS_PROFILE_PHASES
-__device__ long long g_mark_acc[32];
+__device__ long long g_mark_acc[64];   // [0,32) cycles per phase, [32,64) largest lane skew seen at each mark
 #endif
 struct WarpLanes {
     static constexpr bool kUniform = true;
@@ -299,6 +299,14 @@ struct WarpLanes {
     mutable long long t_last = 0;
     mutable int cur = 0;
     __device__ void mark(int id) const {
+#ifdef METIS_PROBE_SKEW
+        {   // do the lanes of the warp reach this point in the same cycle?  (redundant execution relies on it)
+            const long long t = clock64();
+            const long long t0 = __shfl_sync(0xFFFFFFFFu, t, 0);
+            const long long d = t > t0 ? t - t0 : t0 - t;
+            if (d) atomicMax((unsigned long long *)&g_mark_acc[32 + (id & 31)], (unsigned long long)d);
+        }
+#endif
         if ((threadIdx.x & 31) != 0) return;
         const long long now = clock64();
         if (t_last) atomicAdd((unsigned long long *)&g_mark_acc[cur & 31], (unsigned long long)(now - t_last));
@@ -677,8 +685,8 @@ const char *metis_last_error(void) { return g_err; }
 int metis_abi_version(void) { return METIS_ABI_VERSION; }
 #ifdef METIS_PROFILE_PHASES
 int metis_debug_marks(long long *out32, int reset) {
-    long long zero[32] = {0};
-    if (out32) cudaMemcpyFromSymbol(out32, g_mark_acc, sizeof(zero));
+    long long zero[64] = {0};
+    if (out32) cudaMemcpyFromSymbol(out32, g_mark_acc, sizeof(zero));      // caller provides 64 entries
     if (reset) cudaMemcpyToSymbol(g_mark_acc, zero, sizeof(zero));
     return 0;
 }

@@ -35,7 +35,7 @@ for _ in range(3):
     s.launch()
 torch.cuda.synchronize()
 import ctypes
-marks = (ctypes.c_longlong * 32)()
+marks = (ctypes.c_longlong * 64)()
 native._lib.metis_debug_marks(None, 1)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record(); s.launch(); b.record(); torch.cuda.synchronize()
@@ -44,7 +44,7 @@ cyc = list(sm.reserved)[:5]
 tot = sum(cyc) or 1
 native._lib.metis_debug_marks(marks, 0)
 names = {0: 'between tasks', 1: 'restore', 2: 'P perf', 10: 'R fwd', 11: 'R bwd', 12: 'R leftovers', 13: 'R vote', 14: 'R cnt+capa', 15: 'R adjust', 16: 'R part', 20: 'M demand', 21: 'M reweight', 22: 'C cost', 23: 'chain', 24: 'save'}
-mt = sum(marks) or 1
+mt = sum(marks[:32]) or 1
 print('  cooperative-mode marks (leader-lane cycles): ' + ', '.join(f'{names.get(i, i)} {100.0 * marks[i] / mt:.1f}%' for i in range(32) if marks[i]))
 print(f'{name}: {a.elapsed_time(b):.2f} ms, plans {space.num_plans}, B {sm.num_partition_calls}, runs {sm.num_balancer_runs}, C {sm.num_records}')
 import numpy as np  # noqa: E402
@@ -60,3 +60,7 @@ if rows:
         print(f'  {i + 1:3d}: {n:7d} {(t - t0) / 1e3:9.1f}  ({dur:8.1f})')
 for k, n in zip(cyc, ['F fetch/advance', 'P performance', 'R balance_run', 'M memory/adjust', 'C cost/emit']):
     print(f'  {n:18s} {100.0 * k / tot:6.2f} %   {k / 1e6:10.1f} Mcycles (summed over warps)')
+if any(marks[32:]):
+    print('  largest lane skew (cycles) at marks: ' + ', '.join(f'{names.get(i, i)} {marks[32 + i]}' for i in range(32) if marks[32 + i]))
+elif os.environ.get('METIS_LIB', '').find('skew') >= 0:
+    print('  lane skew: 0 cycles at every mark (all lanes read the same clock value)')

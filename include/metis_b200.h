@@ -45,6 +45,7 @@ extern "C" {
 #define METIS_FATAL_HANG        4   /* reference loop at load_balancer.py:96-104 would not terminate                */
 #define METIS_FATAL_SCRATCH     5   /* internal scratch exceeded (more stages / leftovers than compiled limits)     */
 #define METIS_FATAL_ZERODIV     6   /* ZeroDivisionError in the reference (zero profiled time / zero total)         */
+#define METIS_FATAL_SCHEDULER   7   /* internal: the device task queue made no progress for 2 s (watchdog; a bug)    */
 
 /* limits compiled into the kernels */
 #define METIS_MAX_TYPES   8

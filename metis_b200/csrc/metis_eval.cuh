@@ -30,6 +30,18 @@
 
 namespace metis {
 
+// Task-list words are read with ld.global.cg (L2 only): in the barrier-free latency mode another SM may have
+// rewritten a neighbouring slot of the same 128-byte line a moment ago, and an L1 copy of that line fetched
+// by a different warp of this SM could be stale (L1 is not coherent; every task is read exactly once anyway).
+template <class V>
+MB_HD V list_load(const V *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
 constexpr int kH = 7;                 // hallucination (model/load_balancer.py:183)
 constexpr double kMemCoef = 5.0;      // mem_coef (model/load_balancer.py:31)
 constexpr uint8_t kDropped = 0xFF;    // real layer kept by no stage (quirk Q5)
@@ -1305,6 +1317,8 @@ struct PlanEvaluator {
 //   run_task   : [P stage performance] -> R LayerComputeBalancer.run -> M memory check /
 //                re-weighting -> C cost + record -> advance along the chain (plan.py:192-268)
 // All lanes of a warp walk these steps together; `Warp::append(cont)` is called convergently.
+// `Warp::consumed(pos)` / `Warp::publish(pos, cont)` bracket the life of a list slot for schedulers that
+// hand tasks over without a barrier (metis_search.cu: QueueWarp); the round-based ones ignore them.
 // ---------------------------------------------------------------------------
 struct TaskBuffers {
     uint64_t *hdr;      // [cap]            ordinal | step << 32 | attempt << 48 | nrep << 52 | retry << 56
@@ -1348,7 +1362,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
     sink.phase(1);
     lanes.sync();                                            // the warp's previous task is finished in every lane
     if (has) {                                               // ---- restore, P ----
-        const uint64_t h = in.hdr[pos];
+        const uint64_t h = list_load(&in.hdr[pos]);
         step = (int)((h >> 32) & 0xFFFF);
         attempt = (int)((h >> 48) & 0xF);
         nrep = (int)((h >> 52) & 0xF);
@@ -1359,10 +1373,11 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
         ev.set_groups(plan.row);
 #pragma unroll (X::kUniform ? 1 : 0)
         for (int s = lanes.lane(); s < plan.S; s += lanes.width()) {
-            w.tpc[s] = in.tpc[(int64_t)s * in.cap + pos];
-            if (retry) w.perf[s] = in.perf[(int64_t)s * in.cap + pos];
+            w.tpc[s] = list_load(&in.tpc[(int64_t)s * in.cap + pos]);
+            if (retry) w.perf[s] = list_load(&in.perf[(int64_t)s * in.cap + pos]);
         }
         lanes.sync();
+        warp.consumed(pos);                                  // the task's slot may be reused from here on
         lanes.mark(2);
         if (!retry) {
             sink.partition_call();
@@ -1424,6 +1439,7 @@ MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sin
             if (retry) out.perf[(int64_t)s * out.cap + opos] = w.perf[s];
         }
     }
+    warp.publish(opos, has && cont);                         // successor complete in memory
     lanes.mark(0);
 }
 

@@ -287,6 +287,8 @@ struct DeviceWarp {
         base = __shfl_sync(full, base, leader);
         return (int64_t)base + __popc(m & ((1u << lane) - 1u));
     }
+    __device__ void consumed(int64_t) const {}
+    __device__ void publish(int64_t, bool) const {}
 };
 
 // Lane policy of the cooperative (latency) mode, see metis_eval.cuh `Serial`.
@@ -348,11 +350,107 @@ struct UniformWarp {
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         return want ? (int64_t)base : -1;
     }
+    __device__ void consumed(int64_t) const {}
+    __device__ void publish(int64_t, bool) const {}
+};
+
+// Continuous latency mode: once a list is short enough to run one task per warp, the grid stops meeting at
+// barriers.  The remaining tasks live in a bounded multi-producer / multi-consumer ring over the slots of one
+// task buffer (sequence number per slot: == ticket -> free for that ticket, == ticket + 1 -> published); a
+// warp pops a ticket, runs the task, pushes its successor (if the plan continues) and pops again, so nobody
+// idles while any chain still has a step to run.  At most one task per chain is alive, so with ring >= number of
+// tasks at the switch a producer never finds its slot occupied; `alive` (pushed - retired) reaching zero tells
+// the poppers that no ticket will ever be published again.
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {     // polling: no L1 invalidation per try
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Watchdog of the queue's spin loops: a waiter that sees neither a push nor a retirement for 2 s declares the
+// scheduler dead (ctl[3] = 1 releases every waiter, the search reports METIS_FATAL_SCHEDULER instead of hanging).
+// All waiting below is written warp-uniformly: every lane runs the same loop and takes the same branches, lane 0
+// performs the memory operation (a single predicated instruction) and its value is broadcast.  A branchy
+// `if (lane == 0) { spin }` lets the compiler keep lane 0 and lanes 1-31 as two separately scheduled groups for
+// the rest of the task, and the redundant-execution sections of the latency mode then see
+// each other's half-finished updates.
+struct QueueWatch {
+    unsigned int *ctl;
+    unsigned long long *diag;          // counters[16..]: which loop, ticket, slot value, head, tail, alive
+    unsigned int polls = 0, last_tail = 0, last_alive = 0;
+    unsigned long long since = 0;
+    __device__ QueueWatch(unsigned int *c, unsigned long long *d) : ctl(c), diag(d) {}
+    // true = give up (uniform: every lane evaluates the same broadcast values)
+    __device__ bool expired(int which, unsigned int ticket, unsigned int seen) {
+        if ((++polls & 1023u) != 0) return false;
+        unsigned int tail = 0, alive = 0, fired = 0;
+        unsigned long long now = 0;
+        if ((threadIdx.x & 31) == 0) {
+            tail = *(volatile unsigned int *)&ctl[1]; alive = *(volatile unsigned int *)&ctl[2];
+            fired = *(volatile unsigned int *)&ctl[3]; now = global_ns();
+        }
+        tail = __shfl_sync(0xFFFFFFFFu, tail, 0); alive = __shfl_sync(0xFFFFFFFFu, alive, 0);
+        fired = __shfl_sync(0xFFFFFFFFu, fired, 0); now = __shfl_sync(0xFFFFFFFFu, now, 0);
+        if (fired) return true;
+        if (since == 0 || tail != last_tail || alive != last_alive) { since = now; last_tail = tail; last_alive = alive; return false; }
+        if (now - since < 2000000000ULL) return false;
+        if ((threadIdx.x & 31) == 0 && atomicExch(&ctl[3], 1u) == 0u) {
+            diag[0] = (unsigned long long)which; diag[1] = ticket; diag[2] = seen;
+            diag[3] = *(volatile unsigned int *)&ctl[0]; diag[4] = tail; diag[5] = alive;
+        }
+        return true;
+    }
+};
+struct QueueWarp {
+    unsigned int *seq;         // [ring]
+    unsigned int *ctl;         // [0] head (pop tickets) [1] tail (push tickets) [2] alive [3] watchdog fired
+    unsigned long long *diag;
+    unsigned int ring;
+    unsigned int taken;        // ticket of the task being run
+    unsigned int pushed;       // ticket of the successor being written
+    __device__ int64_t append(bool want) {
+        if (!want) return -1;                                // uniform
+        const bool lead = (threadIdx.x & 31) == 0;
+        unsigned int t = 0;
+        if (lead) t = atomicAdd(&ctl[1], 1u);
+        if (lead) atomicAdd(&ctl[2], 1u);                    // alive before the parent retires
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        QueueWatch watch(ctl, diag);
+        for (;;) {                                           // slot free for this ticket? (never waits when ring >= tasks alive)
+            unsigned int v = 0;
+            if (lead) v = ld_relaxed_u32(&seq[t % ring]);
+            v = __shfl_sync(0xFFFFFFFFu, v, 0);
+            if (v == t || watch.expired(1, t, v)) break;
+            __nanosleep(64);
+        }
+        __threadfence();                                     // every lane: acquire side of the slot hand-over
+        pushed = t;
+        return (int64_t)(t % ring);
+    }
+    __device__ void publish(int64_t slot, bool want) const {
+        if (!want) return;
+        __threadfence();                                     // every lane's stores to the slot are visible ...
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) st_relaxed_u32(&seq[slot], pushed + 1u);   // ... before the flag
+    }
+    __device__ void consumed(int64_t slot) const {
+        __threadfence();                                     // every lane's loads from the slot are complete
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) st_relaxed_u32(&seq[slot], taken + ring);
+    }
 };
 
 struct RoundBuffers {
     TaskBuffers buf[2];
     unsigned int *counts;      // [3] rotating task counters
+    unsigned int *seq;         // [wave] slot sequence numbers of the continuous latency mode
     long long wave;            // plans admitted per wave (= capacity of the task lists)
     long long coop_below;      // rounds with fewer pending tasks run one task per warp (latency mode)
     unsigned long long *trace; // profiling builds: (tasks, globaltimer ns) per round, 512 entries
@@ -482,27 +580,61 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                         const long long pos = b0 + lane;
                         PlanDesc pd;
                         bool has = false;
-                        if (pos < (long long)n) { decode_task(sp, in.hdr[pos], in.geo[pos], pd); has = true; }
+                        if (pos < (long long)n) { decode_task(sp, list_load(&in.hdr[pos]), list_load(&in.geo[pos]), pd); has = true; }
                         run_task<MAXS, MAXL>(T, w, Serial(), sink, warp, in, nxt, has, pos, pd);
                     }
                 } else {
-                    // latency mode: one task per warp on shared-memory scratch
-                    UniformWarp uwarp(&rb.counts[(round + 1) % 3]);
+                    // latency mode: one task per warp on shared-memory scratch, no more barriers (QueueWarp)
+                    unsigned int *ctl = rb.counts + 8;
+                    const long long room = in.cap < (long long)n + 64 ? in.cap : (long long)n + 64;
+                    const unsigned int ring = (unsigned int)room;
+                    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < room; i += (long long)gridDim.x * kThreads)
+                        rb.seq[i] = i < (long long)n ? (unsigned int)i + 1u : (unsigned int)i;
+                    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[0] = 0; ctl[1] = n; ctl[2] = n; ctl[3] = 0; }
+                    grid.sync();
+                    QueueWarp qwarp{rb.seq, ctl, out.counters + 16, ring, 0u, 0u};
                     WarpLanes lanes_coop;
                     sink.leader = lane == 0;
-                    for (;;) {                                    // tasks differ in length (re-weighting): fetch dynamically
-                        unsigned int fetched = 0;
-                        if (lane == 0) fetched = atomicAdd(&rb.counts[4 + round % 3], 1u);
-                        const long long taken = __shfl_sync(0xFFFFFFFFu, fetched, 0);
-                        if (taken >= (long long)n) break;
-                        // newest first: the tasks appended last by the previous round were its slowest
-                        const long long pos = METIS_COOP_FIFO ? taken : (long long)n - 1 - taken;
+                    for (;;) {
+                        unsigned int h = 0;
+                        if (lane == 0) h = atomicAdd(&ctl[0], 1u);
+                        h = __shfl_sync(0xFFFFFFFFu, h, 0);
+                        // every chain is finite (tp only grows, <= 3 attempts per strategy): far more pops than that = runaway
+                        if (h > 4096u * METIS_MAX_STAGES + 64u * n) {
+                            if (lane == 0 && atomicExch(&ctl[3], 1u) == 0u) { out.counters[16] = 3; out.counters[17] = h; out.counters[20] = ctl[1]; out.counters[21] = ctl[2]; }
+                            break;
+                        }
+                        int ready = 0;
+                        QueueWatch watch(ctl, out.counters + 16);
+                        for (;;) {                                // warp-uniform wait: lane 0 loads, everyone decides
+                            unsigned int v = 0, alive = 0;
+                            if (lane == 0) v = ld_relaxed_u32(&rb.seq[h % ring]);
+                            if (lane == 0) alive = ld_relaxed_u32(&ctl[2]);
+                            v = __shfl_sync(0xFFFFFFFFu, v, 0);
+                            alive = __shfl_sync(0xFFFFFFFFu, alive, 0);
+                            if (v == h + 1u) { ready = 1; break; }
+                            if (alive == 0u) break;               // nothing alive: ticket h will never exist
+                            if (watch.expired(2, h, v)) break;
+                            __nanosleep(256);
+                        }
+                        if (!ready) break;
+                        __threadfence();                          // acquire: the slot's words were written before its flag
+                        qwarp.taken = h;
+                        const long long pos = (long long)(h % ring);
                         PlanDesc pd;
-                        decode_task(sp, in.hdr[pos], in.geo[pos], pd);
-                        const bool has = true;
-                        run_task<MAXS, MAXL>(T, *wsh, lanes_coop, sink, uwarp, in, nxt, has, pos, pd);
+                        decode_task(sp, list_load(&in.hdr[pos]), list_load(&in.geo[pos]), pd);
+                        run_task<MAXS, MAXL>(T, *wsh, lanes_coop, sink, qwarp, in, in, true, pos, pd);
+                        __threadfence();                          // the successor (if any) is published before the parent retires
+                        if (lane == 0) atomicSub(&ctl[2], 1u);
                     }
                     sink.leader = true;
+                    grid.sync();
+                    if (blockIdx.x == 0 && threadIdx.x == 0) {
+                        rb.counts[round % 3] = 0;                 // this wave is finished
+                        if (ctl[3]) atomicMin(&out.counters[4], (unsigned long long)METIS_FATAL_SCHEDULER << 24);
+                    }
+                    grid.sync();
+                    break;
                 }
                 grid.sync();
                 ++round;
@@ -586,6 +718,8 @@ __global__ void het_finalize_kernel(const MetisRecord *block_best, int nblocks, 
         s.best.num_repartition = (uint8_t)(mt >> 8); s.best.num_stage = (uint8_t)mt;
         s.reserved[0] = counters[8]; s.reserved[1] = counters[9];        // profiling builds: phase clocks
         s.reserved[2] = counters[10]; s.reserved[3] = counters[11]; s.reserved[4] = counters[12];
+        if (s.fatal_code == METIS_FATAL_SCHEDULER)                       // watchdog diagnostics (QueueWatch)
+            for (int k = 0; k < 6; ++k) s.reserved[k] = counters[16 + k];
         *summary = s;
     }
 }
@@ -730,7 +864,7 @@ int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans
     const BlobLayout lay = make_layout(*problem);
     const int64_t cap = wave_size(num_plans, max_stage);
     return 256 + kFixedWs + (int64_t)align16(lay.total) + kMaxBlocks * (int64_t)sizeof(MetisRecord) +
-           2 * cap * task_slot_bytes(max_stage) + 1024;
+           2 * cap * task_slot_bytes(max_stage) + cap * 4 + 1024;
 }
 
 struct Workspace {
@@ -817,6 +951,7 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     rb.wave = wave_size(slots, space->max_stage);
     rb.buf[0] = carve_tasks(tp, rb.wave, space->max_stage);
     rb.buf[1] = carve_tasks(tp, rb.wave, space->max_stage);
+    rb.seq = reinterpret_cast<unsigned int *>(tp);
     rb.counts = ws.round_counts;
     rb.trace = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(ws.summary) + 4096);
     // cooperative persistent grid: every block is resident, rounds are separated by grid.sync()

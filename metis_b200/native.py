@@ -17,7 +17,8 @@ METIS_MAX_STAGES = 128
 METIS_MAX_LAYERS = 256
 DETAIL_STRIDE = 3 * METIS_MAX_STAGES + 1
 
-FATAL_NAMES = {1: 'KEY_EXEC', 2: 'KEY_MEMORY', 3: 'INDEX', 4: 'HANG', 5: 'SCRATCH', 6: 'ZERODIV'}
+FATAL_NAMES = {1: 'KEY_EXEC', 2: 'KEY_MEMORY', 3: 'INDEX', 4: 'HANG', 5: 'SCRATCH', 6: 'ZERODIV', 7: 'SCHEDULER'}
+FATAL_SCHEDULER = 7
 
 
 class MetisProblem(C.Structure):

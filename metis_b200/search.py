@@ -143,6 +143,9 @@ class HetSearcher:
             self.launch(s)
             s.synchronize()
             sm = self.summary()
+            if sm.fatal_code == native.FATAL_SCHEDULER:
+                raise native.MetisNativeError('device task queue watchdog fired (loop, ticket, slot value, head, tail, '
+                                              f'alive) = {[int(v) for v in sm.reserved]}')
             if self.want_records and sm.num_records > self.capacity:
                 self._alloc(int(sm.num_records) + 1024)
                 self.launch(s)

@@ -124,6 +124,8 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
         struct HostWarp {
             int64_t *count;
             int64_t append(bool want) const { return want ? (*count)++ : -1; }
+            void consumed(int64_t) const {}
+            void publish(int64_t, bool) const {}
         };
         const int smax = sp->max_stage > 0 ? sp->max_stage : METIS_MAX_STAGES;
         int64_t cap = 1;                  // count the admitted plans first so the lists are sized exactly

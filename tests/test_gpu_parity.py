@@ -387,3 +387,27 @@ def test_ranked_listing_is_sorted_estimate_costs(workload_dir):
     want = sorted(range(len(gold_cost)), key=lambda i: gold_cost[i])         # Python's stable sort, as the reference
     assert out.rank_order.tolist() == want
     assert (out.records['cost'].view(np.uint64) == gold_cost.view(np.uint64)).all()
+
+
+@pytest.mark.parametrize('name', ['mix32', 'het32_tight', 'c2_het16'])
+@pytest.mark.parametrize('factor', [1, 1000], ids=['throughput_first', 'latency_only'])
+def test_scheduler_modes_agree(name, factor, workload_dir):
+    """The two execution modes of the round scheduler (32 tasks per warp in lockstep / one task per warp fed by
+    the barrier-free queue) are forced in turn (MetisShard.reserved); both must reproduce every golden candidate,
+    including the re-partition counts of mixed-type and memory-tight plans."""
+    _gpu()
+    from metis_b200 import flatten, search
+    meta, arr = load_golden(name)
+    w, root, _ = workload_dir(name)
+    cfg = _cfg(w)
+    cluster, profile, _, mc = _inputs(root, 'profile', meta['file_order'], cfg['L'], cfg['hidden'], cfg['seq'], cfg['vocab'])
+    seqs = [tuple(s) for s in meta['node_sequences']]
+    problem = flatten.build_problem(profile, cluster, mc, cfg['gbs'], cfg['max_tp'], cfg['max_bs'], seqs)
+    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), cfg['gbs'], cfg['L'], cfg['variance'], cfg['mpl'])
+    s = search.HetSearcher(search.DeviceProblem(problem, space, 'cuda:0'), want_records=True, want_detail=True)
+    s.shard.reserved = factor
+    out = s.run()
+    c = meta['counters']
+    assert (out.summary['num_partition_calls'], out.summary['num_balancer_runs'], out.summary['num_records']) == \
+        (c['B'], c['runs'], c['C'])
+    _assert_arrays_equal(out, space, arr)

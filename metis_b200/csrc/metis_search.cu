@@ -389,7 +389,7 @@ struct QueueWatch {
     __device__ QueueWatch(unsigned int *c, unsigned long long *d) : ctl(c), diag(d) {}
     // true = give up (uniform: every lane evaluates the same broadcast values)
     __device__ bool expired(int which, unsigned int ticket, unsigned int seen) {
-        if ((++polls & 1023u) != 0) return false;
+        if ((++polls & 255u) != 0) return false;
         unsigned int tail = 0, alive = 0, fired = 0;
         unsigned long long now = 0;
         if ((threadIdx.x & 31) == 0) {
@@ -605,6 +605,7 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                             break;
                         }
                         int ready = 0;
+                        unsigned int nap = 128;                   // back off to 2 us: idle warps share issue slots with working ones
                         QueueWatch watch(ctl, out.counters + 16);
                         for (;;) {                                // warp-uniform wait: lane 0 loads, everyone decides
                             unsigned int v = 0, alive = 0;
@@ -615,7 +616,8 @@ het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
                             if (v == h + 1u) { ready = 1; break; }
                             if (alive == 0u) break;               // nothing alive: ticket h will never exist
                             if (watch.expired(2, h, v)) break;
-                            __nanosleep(256);
+                            __nanosleep(nap);
+                            if (nap < 2048) nap <<= 1;
                         }
                         if (!ready) break;
                         __threadfence();                          // acquire: the slot's words were written before its flag
@@ -971,7 +973,7 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
         BlobLayout lay_arg = lay;
         const uint8_t *blob_arg = ws.blob;
         long long slots_arg = slots;
-        rb.coop_below = (long long)(shard->reserved > 0 ? shard->reserved : 6) * grid * (kThreads / 32);
+        rb.coop_below = (long long)(shard->reserved > 0 ? shard->reserved : 12) * grid * (kThreads / 32);
         void *args[] = {&p_arg, &s_arg, &sh_arg, &lay_arg, &blob_arg, &use_smem, &scratch_off, &slots_arg, &out, &rb};
         if (g_ev_before) cudaEventRecord(g_ev_before, stream);
         e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(kThreads), args, dyn, stream);

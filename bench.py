@@ -167,7 +167,7 @@ def run_reference_arm(ns):
         'e2e': {'value': value, 'unit': 'plans/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'costed_per_s': costed / wall,
     }
-    print(json.dumps(line))
+    emit_result(line)
 
 
 def workload_config(name, num_plans):
@@ -384,9 +384,9 @@ def run_ours(ns):
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
         achieved = alg_bytes / world / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = None                                        # measured for the 1-GPU launch only
         tpath = os.path.join(REPO, 'profiles', 'r01_traffic.json')
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and world == 1:
             traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
         line = {
             'metric': METRIC, 'value': A / (ms_per_step * 1e-3), 'unit': 'plans/s', 'n_gpus': world,
@@ -424,7 +424,7 @@ def run_ours(ns):
                                     'sample': f'{a} uniformly sampled inter-stage plans of the same {A}-plan space '
                                               f'({c} costed), oracle/metis_oracle.py (Python port of the pure-Python '
                                               f'reference), {port.cores} processes, {t:.1f} s'}
-        print(json.dumps(line))
+        emit_result(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -441,10 +441,28 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=3000, help='plans per host core for cpu_baseline')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ns = ap.parse_args()
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version there when
+    # NCCL_DEBUG=VERSION) are sent to stderr for the duration of the run
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if ns.impl == 'reference':
         run_reference_arm(ns)
     else:
         run_ours(ns)
+
+
+_RESULT_FD = None
+
+
+def emit_result(line):
+    data = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
 
 
 if __name__ == '__main__':

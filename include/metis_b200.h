@@ -151,8 +151,8 @@ typedef struct MetisShard {
     int32_t rank;                 /* 0 <= rank < world                                              */
     int32_t world;
     int32_t tile;                 /* plans per interleave tile (multiple of 32)                     */
-    int32_t reserved;             /* tuning: rounds with fewer than reserved x (resident warps) pending
-                                     tasks run one task per warp; 0 = default                        */
+    int32_t reserved;             /* tuning: task lists shorter than reserved x (resident warps) run one task
+                                     per warp through the barrier-free queue; 0 = default (12)        */
 } MetisShard;
 
 const char *metis_last_error(void);
@@ -178,6 +178,7 @@ int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans
  *                dp code[num_stage], tp code[num_stage] (log2) then layer_partition[num_stage+1]
  *                (uint8 each); detail_stride >= 3*METIS_MAX_STAGES+1, or NULL
  *   workspace    [device] metis_het_workspace_bytes(problem, plans in shard, space->max_stage) bytes
+ *                (task lists for one wave of plans: up to 32 GiB by default, METIS_TASK_MIB overrides)
  *   summary      [host]   filled asynchronously (use pinned memory)
  */
 int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, const MetisShard *shard,

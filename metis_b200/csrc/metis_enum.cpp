@@ -30,12 +30,6 @@ namespace {
 
 using Group = std::vector<int>;   // one merged group = tuple of device-group sizes
 
-int group_sum(const Group &g) {
-    int s = 0;
-    for (int v : g) s += v;
-    return s;
-}
-
 uint8_t ilog2(int v) {
     uint8_t c = 0;
     while ((1 << c) < v) ++c;

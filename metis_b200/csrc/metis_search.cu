@@ -13,9 +13,6 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no FMA contraction: parity).
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
-#ifndef METIS_COOP_FIFO
-#define METIS_COOP_FIFO 0
-#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -337,21 +334,6 @@ struct WarpLanes {
         }
         return v;
     }
-};
-
-// Cooperative mode: the 32 lanes of a warp execute ONE task redundantly on shared-memory scratch
-// (identical data => identical control flow, no divergence); lane 0 appends for the warp.
-struct UniformWarp {
-    unsigned int *counter;
-    __device__ explicit UniformWarp(unsigned int *c) : counter(c) {}
-    __device__ int64_t append(bool want) const {
-        unsigned int base = 0;
-        if (want && (threadIdx.x & 31) == 0) base = atomicAdd(counter, 1u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        return want ? (int64_t)base : -1;
-    }
-    __device__ void consumed(int64_t) const {}
-    __device__ void publish(int64_t, bool) const {}
 };
 
 // Continuous latency mode: once a list is short enough to run one task per warp, the grid stops meeting at

@@ -185,3 +185,53 @@ def test_two_rank_reduction_gloo(tmp_path):
                                       stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), '\n'.join(outs)
+
+
+def test_python_constants_match_header():
+    """The numeric constants the ctypes layer uses are the ones include/metis_b200.h defines."""
+    import re
+    from metis_b200 import native
+    text = open(os.path.join(REPO, 'include', 'metis_b200.h')).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r'#define\s+(METIS_[A-Z_0-9]+)\s+(-?\d+)\b', text)}
+    assert (defs['METIS_SORT_POSITION'], defs['METIS_SORT_RANKED'], defs['METIS_SORT_BY_COST_STABLE']) == \
+        (native.SORT_POSITION, native.SORT_RANKED, native.SORT_BY_COST_STABLE)
+    assert defs['METIS_FATAL_SCHEDULER'] == native.FATAL_SCHEDULER
+    for code, name in native.FATAL_NAMES.items():
+        assert defs['METIS_FATAL_' + name] == code
+    assert native.DETAIL_STRIDE == 3 * defs['METIS_MAX_STAGES'] + 1
+
+
+def test_enumeration_into_a_caller_buffer():
+    """build_plan_space(rows_out=...) (the pinned staging buffer in production) yields the same space as the
+    allocating call, in place, and falls back to its own buffer when the caller's is too small."""
+    from metis_b200 import flatten
+    base = flatten.build_plan_space(2, 32, 64, 24, 1, 4)
+    buf = np.full(base.rows.size + 4096, 0xAB, dtype=np.uint8)
+    inplace = flatten.build_plan_space(2, 32, 64, 24, 1, 4, rows_out=buf)
+    assert np.shares_memory(inplace.rows, buf)
+    assert inplace.num_plans == base.num_plans and (inplace.blocks == base.blocks).all()
+    assert (inplace.rows[:base.rows.size] == base.rows).all()
+    small = np.zeros(16, dtype=np.uint8)
+    other = flatten.build_plan_space(2, 32, 64, 24, 1, 4, rows_out=small)
+    assert not np.shares_memory(other.rows, small) and (other.rows == base.rows).all()
+
+
+def _enumerate_in_child(queue):
+    from metis_b200 import flatten
+    queue.put(int(flatten.build_plan_space(1, 64, 512, 96, 1, 4).num_plans))
+
+
+def test_enumerator_worker_pool_survives_fork():
+    """The C++ enumerator keeps persistent worker threads; a forked child (where they do not exist) must build
+    its own pool instead of waiting for the parent's."""
+    import multiprocessing as mp
+    from metis_b200 import flatten
+    want = int(flatten.build_plan_space(1, 64, 512, 96, 1, 4).num_plans)      # creates the pool in this process
+    ctx = mp.get_context('fork')
+    q = ctx.Queue()
+    p = ctx.Process(target=_enumerate_in_child, args=(q,))
+    p.start()
+    p.join(60)
+    assert not p.is_alive(), 'enumeration in the forked child did not finish'
+    assert p.exitcode == 0 and q.get(timeout=5) == want == 82520
+    assert int(flatten.build_plan_space(1, 64, 512, 96, 1, 4).num_plans) == want   # the parent's pool still works

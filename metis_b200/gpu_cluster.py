@@ -7,9 +7,23 @@ from .utils import DeviceType, GPUNode, parse_hostfile, parse_nodefile
 
 
 class GPUCluster:
-    def __init__(self, hostfile_path: str, clusterfile_path: str):
-        self.host_entries = parse_hostfile(hostfile_path)
+    def __init__(self, hostfile_path: str, clusterfile_path: str, strict: bool = False):
+        """``strict=True`` (opt-in): multi-digit ``slots=`` counts, and a ValueError that names the host for a
+        node missing from the clusterfile, an unknown instance type or a missing field; the default reproduces
+        the reference's parsing (quirk Q10) and its bare KeyError / ValueError."""
+        self.host_entries = parse_hostfile(hostfile_path, strict=strict)
         self.nodes_info = parse_nodefile(clusterfile_path)
+        if strict:
+            for host in self.host_entries.values():
+                info = self.nodes_info.get(host['ip'])
+                if info is None:
+                    raise ValueError(f"host {host['ip']!r} of {hostfile_path} is not in {clusterfile_path}")
+                for key in ('instance_type', 'memory', 'intra_bandwidth', 'inter_bandwidth'):
+                    if key not in info:
+                        raise ValueError(f"{clusterfile_path}: node {host['ip']!r} has no {key!r}")
+                if str(info['instance_type']).upper() not in DeviceType.__members__:
+                    raise ValueError(f"{clusterfile_path}: node {host['ip']!r} has unknown instance_type "
+                                     f"{info['instance_type']!r} (known: {', '.join(DeviceType.__members__)})")
         self.nodes = {
             node_id: GPUNode(device_type=DeviceType.from_string(self.nodes_info[host['ip']]['instance_type']),
                              num_devices=host['num_device'])

@@ -47,14 +47,26 @@ class GPUNode:
     num_devices: int
 
 
-def parse_hostfile(file_path: str) -> Dict[int, Dict[str, Union[str, int]]]:
+def parse_hostfile(file_path: str, strict: bool = False) -> Dict[int, Dict[str, Union[str, int]]]:
     """utils.py:8-24.  The device count is the single character at offset 6 of the
-    second token (quirk Q10: ``IP4 8888888`` and ``host slots=8`` both give 8)."""
+    second token (quirk Q10: ``IP4 8888888`` and ``host slots=8`` both give 8, ``slots=16`` gives 1).
+    ``strict=True`` (opt-in) parses ``<host> slots=<N>`` with a multi-digit N, skips blank lines and
+    rejects anything else with a ValueError naming the line."""
     entries: Dict[int, Dict[str, Union[str, int]]] = {}
     with open(file_path, 'rt') as fh:
-        for node_id, line in enumerate(iter(fh.readline, '')):
-            fields = line.split(' ')
-            entries[node_id] = {'ip': fields[0], 'num_device': int(fields[1][6:7])}
+        if not strict:
+            for node_id, line in enumerate(iter(fh.readline, '')):
+                fields = line.split(' ')
+                entries[node_id] = {'ip': fields[0], 'num_device': int(fields[1][6:7])}
+            return entries
+        for lineno, line in enumerate(fh, 1):
+            fields = line.split()
+            if not fields:
+                continue
+            if len(fields) != 2 or not fields[1].startswith('slots=') or not fields[1][6:].isdigit() \
+                    or int(fields[1][6:]) < 1:
+                raise ValueError(f'{file_path}:{lineno}: expected "<host> slots=<N>", got {line.strip()!r}')
+            entries[len(entries)] = {'ip': fields[0], 'num_device': int(fields[1][6:])}
     return entries
 
 

@@ -235,3 +235,83 @@ def test_enumerator_worker_pool_survives_fork():
     assert not p.is_alive(), 'enumeration in the forked child did not finish'
     assert p.exitcode == 0 and q.get(timeout=5) == want == 82520
     assert int(flatten.build_plan_space(1, 64, 512, 96, 1, 4).num_plans) == want   # the parent's pool still works
+
+
+def _write_profile(path, layers=4, **overrides):
+    import json
+    raw = {'model': {'parameters': {'parameters_per_layer_bytes': [10] * layers}},
+           'execution_time': {'layer_compute_total_ms': [1.0] * layers, 'forward_backward_time_ms': 5.0,
+                              'optimizer_time_ms': 2.0, 'batch_generator_time_ms': 0.5},
+           'execution_memory': {'layer_memory_total_mb': [100.0] * layers}}
+    for dotted, value in overrides.items():
+        node = raw
+        keys = dotted.split('__')
+        for k in keys[:-1]:
+            node = node[k]
+        if value is None:
+            del node[keys[-1]]
+        else:
+            node[keys[-1]] = value
+    with open(path, 'w') as fh:
+        json.dump(raw, fh)
+
+
+def test_opt_in_profile_validation_and_sorted_listing(tmp_path):
+    """schema validation and a deterministic listing are opt-in; the default loader behaves like
+    the reference (no checks, os.listdir order)."""
+    from metis_b200.data_loader import ProfileDataLoader, ProfileSchemaError
+    d = tmp_path / 'p'
+    d.mkdir()
+    _write_profile(d / 'DeviceType.H100_tp1_bs1.json')
+    _write_profile(d / 'DeviceType.A100_tp2_bs1.json')
+    data, types = ProfileDataLoader(str(d), sort_files=True, validate=True).load_profile_data_all()
+    assert types == ['A100', 'H100'] and set(data) == {'model', 'DeviceType.A100', 'DeviceType.H100'}
+    assert data['DeviceType.A100']['tp2_bs1']['time']['fb_sync'] == 1.0
+    # the same files through the default path give the same dict (order of types aside)
+    plain, _ = ProfileDataLoader(str(d)).load_profile_data_all()
+    assert plain['DeviceType.H100'] == data['DeviceType.H100']
+    for bad, text in [({'execution_time__layer_compute_total_ms': None}, 'missing key execution_time/layer_compute_total_ms'),
+                      ({'execution_memory__layer_memory_total_mb': [1.0, 'x', 3.0, 4.0]}, 'non-numeric'),
+                      ({'execution_memory__layer_memory_total_mb': [1.0, 2.0]}, 'differ in length'),
+                      ({'execution_time__optimizer_time_ms': '3'}, 'must be a number')]:
+        _write_profile(d / 'DeviceType.H100_tp1_bs1.json', **bad)
+        with pytest.raises(ProfileSchemaError, match=text):
+            ProfileDataLoader(str(d), sort_files=True, validate=True).load_profile_data_all()
+    _write_profile(d / 'DeviceType.H100_tp1_bs1.json', layers=6)
+    with pytest.raises(ProfileSchemaError, match='6 layers, other profiles have 4'):
+        ProfileDataLoader(str(d), sort_files=True, validate=True).load_profile_data_all()
+    _write_profile(d / 'DeviceType.H100_tp1_bs1.json')
+    _write_profile(d / 'notes.json')
+    with pytest.raises(ProfileSchemaError, match='file name must look like'):
+        ProfileDataLoader(str(d), sort_files=True, validate=True).load_profile_data_all()
+
+
+def test_opt_in_strict_cluster_files(tmp_path):
+    """Multi-digit `slots=` counts and named errors are opt-in; the default keeps quirk Q10 (`slots=16` reads 1)."""
+    import json
+    from metis_b200.gpu_cluster import GPUCluster
+    from metis_b200.utils import parse_hostfile
+    host = tmp_path / 'hostfile'
+    host.write_text('n0 slots=16\nn1 slots=16\n\n')
+    nodes = {f'n{i}': {'instance_type': 'B200', 'inter_bandwidth': 1e9, 'intra_bandwidth': 9e11, 'memory': 180}
+             for i in range(2)}
+    cl = tmp_path / 'cluster.json'
+    cl.write_text(json.dumps(nodes))
+    assert [e['num_device'] for e in parse_hostfile(str(host), strict=True).values()] == [16, 16]
+    loose = tmp_path / 'hostfile_q10'
+    loose.write_text('n0 slots=16\nn1 slots=16\n')
+    assert [e['num_device'] for e in parse_hostfile(str(loose)).values()] == [1, 1]      # the reference's reading
+    cluster = GPUCluster(str(host), str(cl), strict=True)
+    assert cluster.get_total_num_devices() == 32 and cluster.get_num_devices_per_node() == 16
+    assert cluster.get_device_memory(0) == 180 * 1024
+    host.write_text('n0 slots=16\nn7 slots=16\n')
+    with pytest.raises(ValueError, match="host 'n7'"):
+        GPUCluster(str(host), str(cl), strict=True)
+    host.write_text('n0 slots=16\nn1 gpus=16\n')
+    with pytest.raises(ValueError, match=':2: expected'):
+        GPUCluster(str(host), str(cl), strict=True)
+    host.write_text('n0 slots=16\nn1 slots=16\n')
+    nodes['n1']['instance_type'] = 'MI300'
+    cl.write_text(json.dumps(nodes))
+    with pytest.raises(ValueError, match="unknown instance_type 'MI300'"):
+        GPUCluster(str(host), str(cl), strict=True)

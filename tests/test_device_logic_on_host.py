@@ -190,3 +190,74 @@ def test_homo_cost_on_host(name, root_kind, workload_dir):
     keep = status != 1
     assert plans[keep].tolist() == arr['plan'].tolist()
     assert cost[keep].tolist() == arr['cost'].tolist()
+
+
+def _random_workload(rng, idx):
+    from metis_b200.workloads import Workload
+    types = rng.sample(['A100', 'H100', 'B200', 'V100'], rng.choice([1, 1, 2, 2, 3]))
+    per = rng.choice([2, 4, 8])
+    nnodes = rng.choice([1, 2, 2, 3, 4]) if per < 8 else rng.choice([1, 2, 3])
+    nnodes = max(nnodes, len(types))
+    nodes = [(types[(i * len(types)) // nnodes], per) for i in range(nnodes)]      # runs of equal types, like a hostfile
+    layers = rng.randint(6, 28)
+    memory = {t: rng.choice([6, 10, 16, 24, 40, 80]) for t in types}               # small memories force re-partitioning
+    bw = {t: rng.choice([5312500000.0, 2.5e9, 9.0e10]) for t in types}
+    return Workload(f'fuzz{idx}', nodes, layers, rng.choice([8, 12, 16, 24, 32, 48, 64]),
+                    rng.choice([1024, 4096, 8192]), rng.choice([512, 2048]), rng.choice([30522, 51200]),
+                    variance=rng.choice([0, 0.5, 1, 1]), max_permute_len=rng.choice([2, 3, 4, 6]),
+                    max_tp=rng.choice([1, 2, 4]), max_bs=rng.choice([1, 2, 4]), bss=(1, 2, 4, 8, 16), seed=idx,
+                    memory_gb=memory, intra_bw=bw)
+
+
+def test_random_small_clusters_vs_oracle(tmp_path):
+    """Seeded fuzz: 160 random small clusters (1-3 device types, 2-32 GPUs, odd layer counts and batch sizes, tight
+    memories, variance 0 / 0.5 / 1) searched by the device code (host build, all three scheduling modes in turn) and
+    by the oracle; every candidate, counter and fp64 cost bit must agree, and a search the oracle aborts with a
+    KeyError must report the same plan."""
+    import itertools
+    import random
+    from oracle import metis_oracle as orc
+    from metis_b200.workloads import materialize, profile_file_order
+    rng = random.Random(20260921)
+    done = fatal = candidates = 0
+    idx = 0
+    while done < 160 and idx < 1600:
+        idx += 1
+        w = _random_workload(rng, idx)
+        root = str(tmp_path / w.name)
+        materialize(w, root)
+        order = profile_file_order(w)
+        cluster, profile, _types, cfg = hs.load_inputs(root, 'profile', order, w.num_layers, w.hidden_size,
+                                                       w.sequence_length, w.vocab_size)
+        seqs = list(itertools.permutations(w.device_types()))
+        ndev = cluster.get_total_num_devices()
+        try:
+            space = flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len)
+        except IndexError:
+            continue                                   # no stage-1 rows: the reference raises before searching
+        if not 1 <= space.num_plans <= 6000:
+            continue
+        problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
+        rec, det, summary = hs.host_het_search(problem, space, mode=done % 3)
+        ocl = orc.OracleCluster(os.path.join(root, 'hostfile'), os.path.join(root, 'clusterfile.json'))
+        oprof, _ = orc.load_profile_dir(os.path.join(root, 'profile'), order)
+        omodel = orc.OracleModel(w.num_layers, w.hidden_size, w.sequence_length, w.vocab_size, oprof['model']['parameters'])
+        try:
+            want, counters = orc.het_search(oprof, ocl, omodel, seqs, w.gbs, w.num_layers, w.variance,
+                                            w.max_permute_len, w.max_tp, w.max_bs)
+        except KeyError:
+            assert summary.fatal_ordinal != 2 ** 64 - 1 and summary.fatal_code in (1, 2), w
+            fatal += 1
+            done += 1
+            continue
+        assert summary.fatal_ordinal == 2 ** 64 - 1, w
+        assert (space.num_plans, summary.num_partition_calls, summary.num_balancer_runs, summary.num_records) == \
+            (counters['A'], counters['B'], counters['runs'], counters['C']), w
+        got = hs.unpack_candidates(rec, det, space)
+        assert len(got) == len(want), w
+        for g, x in zip(got, want):
+            assert (g[0], g[1], g[3], g[4], g[5], g[6], g[7]) == (x[0], x[1], x[3], x[4], x[5], x[6], x[7]), (w, g, x)
+            assert g[8] == x[8], (w, g[0], g[1], g[8].hex(), x[8].hex())
+        candidates += len(want)
+        done += 1
+    assert done == 160 and candidates > 2000 and 0 < fatal < 40, (done, fatal, candidates)

@@ -261,3 +261,28 @@ def test_random_small_clusters_vs_oracle(tmp_path):
         candidates += len(want)
         done += 1
     assert done == 160 and candidates > 2000 and 0 < fatal < 40, (done, fatal, candidates)
+
+
+def test_task_queue_protocol_model(tmp_path):
+    """Host model of the barrier-free latency-mode queue (tests/hostsim/queue_model.cpp: the ring / ticket /
+    alive-counter protocol of metis_search.cu restated with std::atomic, threads for warps): every chain step runs
+    exactly once, payloads are never torn or stale, all workers terminate - with slack slots and with the tightest
+    legal ring - and ThreadSanitizer sees no data race in the slot hand-over."""
+    import shutil
+    import subprocess
+    if shutil.which('g++') is None:
+        pytest.skip('g++ not available')
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'hostsim', 'queue_model.cpp')
+    exe = str(tmp_path / 'queue_model')
+    subprocess.run(['g++', '-O2', '-std=c++17', '-pthread', src, '-o', exe], check=True)
+    for args in (['8', '1000', '1', '64'], ['16', '3000', '2', '0'], ['32', '500', '3', '1'], ['4', '20000', '4', '64']):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=120)
+        stats = json.loads(out.stdout)
+        assert out.returncode == 0 and stats['executed'] == stats['expected'] and stats['wrong_chains'] == 0 \
+            and stats['errors'] == 0 and stats['alive'] == 0, (args, stats)
+    tsan = str(tmp_path / 'queue_model_tsan')
+    built = subprocess.run(['g++', '-O1', '-g', '-std=c++17', '-pthread', '-fsanitize=thread', src, '-o', tsan],
+                           capture_output=True, text=True)
+    if built.returncode == 0:
+        out = subprocess.run([tsan, '8', '400', '5', '0'], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and 'ThreadSanitizer' not in out.stderr, out.stderr[-2000:]

@@ -174,31 +174,41 @@ class HetSearchResult(list):
 
 
 def het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer=None,
-                node_sequences: Optional[Sequence[Sequence]] = None):
+                node_sequences: Optional[Sequence[Sequence]] = None, corrected: Sequence[str] = ()):
     """Flatten the inputs of cost_het_cluster() (order of ``set(device_types)`` = quirk Q4)."""
     if node_sequences is None:
         node_sequences = list(permutations(set(gpu_cluster.get_device_types())))
     norm = layer_load_balancer.norm_layer_duration if layer_load_balancer is not None else None
     problem = flatten.build_problem(profile_data, gpu_cluster, model_config, args.gbs,
                                     args.max_profiled_tp_degree, args.max_profiled_batch_size, node_sequences,
-                                    norm)
+                                    norm, corrected=corrected)
     space = flatten.build_plan_space(len(node_sequences), gpu_cluster.get_total_num_devices(), args.gbs,
-                                     args.num_layers, args.min_group_scale_variance, args.max_permute_len)
+                                     args.num_layers, args.min_group_scale_variance, args.max_permute_len,
+                                     corrected=corrected)
     return problem, space, [tuple(s) for s in node_sequences]
 
 
 def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, model_config: ModelConfig,
                      cost_estimator: HeteroCostEstimator, layer_load_balancer: LayerLoadBalancer,
-                     node_sequences: Optional[Sequence[Sequence]] = None, device=None) -> HetSearchResult:
+                     node_sequences: Optional[Sequence[Sequence]] = None, device=None,
+                     corrected: Sequence[str] = ()) -> HetSearchResult:
     """cost_het_cluster.py:21-50 on the GPU.  Returns the same list of
     (node_sequence, device_groups, strategies, batches, layer_partition, num_repartition, cost) in the
     same order.  With torch.distributed initialised the plans are sharded over the ranks and every
-    rank returns the full list."""
+    rank returns the full list.
+
+    ``corrected`` (opt-in, default = strict parity with the reference): a subset of ('Q1', 'Q2') - 'Q1' drops the
+    mislabelled one-stage block of every node sequence after the first (plan.py:144-148), 'Q2' uses the
+    clusterfile's inter_bandwidth between nodes (gpu_cluster.py:56-58 returns the intra value).  Results of a
+    corrected search are NOT the reference's; ``result.summary['corrected']`` records what was applied."""
+    unknown = set(corrected) - {'Q1', 'Q2'}
+    if unknown:
+        raise ValueError(f'unknown corrections {sorted(unknown)}: only Q1 and Q2 can be corrected on the host')
     import torch
     from . import search
     t0 = time.perf_counter()
     problem, space, seqs = het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer,
-                                       node_sequences)
+                                       node_sequences, corrected=tuple(corrected))
     t1 = time.perf_counter()
     dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
@@ -226,7 +236,7 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
         search.raise_fatal(summary, problem)
     t2 = time.perf_counter()
     result = HetSearchResult(search.materialize(records, detail, space, seqs))
-    result.summary = dict(summary, num_plans=space.num_plans)
+    result.summary = dict(summary, num_plans=space.num_plans, corrected=tuple(sorted(corrected)))
     result.rank_order = rank_order
     result.timings = {'flatten_enumerate_s': t1 - t0, 'gpu_search_s': t2 - t1,
                       'materialize_s': time.perf_counter() - t2}

@@ -86,7 +86,10 @@ def norm_layer_duration(profile_data: Dict) -> List[float]:
 
 
 def build_problem(profile_data: Dict, gpu_cluster, model_config, gbs: int, max_tp: int, max_bs: int,
-                  node_sequences: Sequence[Sequence], norm_lc: Optional[Sequence[float]] = None) -> FlatProblem:
+                  node_sequences: Sequence[Sequence], norm_lc: Optional[Sequence[float]] = None,
+                  corrected: Sequence[str] = ()) -> FlatProblem:
+    """``corrected`` (opt-in): 'Q2' fills the between-node bandwidth table from the
+    clusterfile's ``inter_bandwidth`` instead of reproducing gpu_cluster.py:56-58, which returns the intra value."""
     nodes = [gpu_cluster.nodes[i] for i in gpu_cluster.nodes.keys()]
     per_node = nodes[0].num_devices
     if any(n.num_devices != per_node for n in nodes):
@@ -147,7 +150,11 @@ def build_problem(profile_data: Dict, gpu_cluster, model_config, gbs: int, max_t
         type_memory.append(float(mem))
         mine = [i for i in node_ids if _type_name(gpu_cluster.nodes[i].device_type) == name]
         bw_first.append(float(gpu_cluster.get_intra_bandwidth(mine[0])))     # cluster_bandwidth.py:49-54
-        bw_min.append(float(min(gpu_cluster.get_inter_bandwidth(i) for i in mine)))   # :56-68 (Q2)
+        if 'Q2' in corrected:
+            bw_min.append(float(min(gpu_cluster.nodes_info[gpu_cluster.host_entries[i]['ip']]['inter_bandwidth']
+                                    for i in mine)))
+        else:
+            bw_min.append(float(min(gpu_cluster.get_inter_bandwidth(i) for i in mine)))   # :56-68 (Q2)
     uniform_bw = int(len(set(bw_first + bw_min)) == 1)
 
     seqs = [tuple(_type_name(t) for t in seq) for seq in node_sequences]
@@ -270,9 +277,11 @@ class FlatPlanSpace:
 
 
 def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_layers: int, variance,
-                     max_permute_len: int, lib=None, rows_out: Optional[np.ndarray] = None) -> FlatPlanSpace:
+                     max_permute_len: int, lib=None, rows_out: Optional[np.ndarray] = None,
+                     corrected: Sequence[str] = ()) -> FlatPlanSpace:
     """Block structure of InterStagePlanGenerator.__next__ (search_space/plan.py:153-175),
-    including the mislabelled num_stage=1 block of every later node sequence (quirk Q1)."""
+    including the mislabelled num_stage=1 block of every later node sequence (quirk Q1).  With 'Q1' in
+    ``corrected`` (opt-in) every node sequence starts with the real one-stage rows, like the first one."""
     cap = min(num_devices, num_layers)
     lib = lib or native.load_library()
     cache: Dict[int, np.ndarray] = enumerate_device_group_tables(1, cap + 1, num_devices, variance, max_permute_len, lib,
@@ -303,7 +312,10 @@ def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_la
             ns += 1
             if ns >= num_node_sequences:
                 break
-            label, (_, rows) = 1, next_stage(2)                # plan.py:144-148 (Q1)
+            if 'Q1' in corrected:
+                label, rows = 1, rows_of(1)
+            else:
+                label, (_, rows) = 1, next_stage(2)            # plan.py:144-148 (Q1)
             if not len(rows):
                 raise IndexError('list index out of range')    # plan.py:173
         else:

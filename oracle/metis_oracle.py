@@ -78,7 +78,10 @@ def fsum(values) -> float:
 class OracleCluster:
     """gpu_cluster.py:8-58 + utils.py:8-31 restated on plain lists."""
 
-    def __init__(self, hostfile_path: str, clusterfile_path: str):
+    def __init__(self, hostfile_path: str, clusterfile_path: str, corrected: Sequence[str] = ()):
+        """``corrected`` mirrors the product's opt-in mode: with 'Q2' inter_bw() returns the
+        clusterfile's inter_bandwidth.  Default = the reference."""
+        self.corrected = tuple(corrected)
         self.node_ip: List[str] = []
         self.node_ndev: List[int] = []
         with open(hostfile_path, 'rt') as fh:            # utils.py:8-24
@@ -120,8 +123,13 @@ class OracleCluster:
     def intra_bw(self, node_id: int):                     # gpu_cluster.py:52-54
         return self.info[self.node_ip[node_id]]['intra_bandwidth']
 
-    def inter_bw(self, node_id: int):                     # gpu_cluster.py:56-58 (Q2: returns intra)
+    def inter_bw_strict(self, node_id: int):              # gpu_cluster.py:56-58 (Q2: returns intra)
         return self.info[self.node_ip[node_id]]['intra_bandwidth']
+
+    def inter_bw(self, node_id: int):                     # het path: the opt-in correction applies here only
+        if 'Q2' in self.corrected:
+            return self.info[self.node_ip[node_id]]['inter_bandwidth']
+        return self.inter_bw_strict(node_id)
 
     def device_types_in_host_order(self) -> List[str]:    # gpu_cluster.py:32-33
         return list(self.node_type)
@@ -359,7 +367,7 @@ def uniform_plans(num_devices: int, max_tp: int, max_gbs: int) -> Iterator[Tuple
 
 
 def inter_stage_plans(node_sequences: Sequence[Tuple[str, ...]], num_devices: int, gbs: int,
-                      num_layers: int, variance, max_permute_len: int) -> Iterator[dict]:
+                      num_layers: int, variance, max_permute_len: int, corrected: Sequence[str] = ()) -> Iterator[dict]:
     """search_space/plan.py:100-175 including quirk Q1 (:144-148).
 
     ``node_sequences`` is ``list(itertools.permutations(set_of_types))`` as the
@@ -392,7 +400,10 @@ def inter_stage_plans(node_sequences: Sequence[Tuple[str, ...]], num_devices: in
         if num_stage > cap:                                 # :165-168 with :144-148
             ns_idx += 1
             num_stage = 1
-            _, rows = next_stage_rows(2)                    # returned stage count discarded (Q1)
+            if 'Q1' in corrected:                           # opt-in: every node sequence starts at one stage
+                rows = device_group_rows(1, num_devices, variance, max_permute_len)
+            else:
+                _, rows = next_stage_rows(2)                # returned stage count discarded (Q1)
             batches = gbs
             dg_idx = 0
         if ns_idx >= len(node_sequences):                   # :170-171
@@ -872,7 +883,7 @@ def het_evaluate_plan(profile: Dict, cluster: OracleCluster, model: OracleModel,
 
 def het_search(profile: Dict, cluster: OracleCluster, model: OracleModel, node_sequences, gbs: int,
                num_layers: int, variance, max_permute_len: int, max_tp: int, max_bs: int,
-               plan_filter=None):
+               plan_filter=None, corrected: Sequence[str] = ()):
     """cost_het_cluster.py:21-50.
 
     Returns (candidates, counters); a candidate is
@@ -883,7 +894,7 @@ def het_search(profile: Dict, cluster: OracleCluster, model: OracleModel, node_s
     counters = {'A': 0, 'B': 0, 'C': 0, 'runs': 0, 'keyerr': 0}
     out: list = []
     for ordinal, plan in enumerate(inter_stage_plans(node_sequences, cluster.total_devices, gbs,
-                                                     num_layers, variance, max_permute_len)):
+                                                     num_layers, variance, max_permute_len, corrected)):
         counters['A'] += 1
         if plan_filter is not None and not plan_filter(ordinal):
             continue
@@ -912,7 +923,7 @@ def homo_cost(profile: Dict, cluster: OracleCluster, model: OracleModel, plan, d
     dp, pp, tp, mbs, gbs = plan
     per_node = cluster.devices_per_node
     total = cluster.total_devices
-    intra, inter = cluster.intra_bw(0), cluster.inter_bw(0)
+    intra, inter = cluster.intra_bw(0), cluster.inter_bw_strict(0)
     params = model.parameter_list(tp)
     counts = uniform_layer_counts(model.num_layers, pp)
     num_mbs = gbs // mbs // dp

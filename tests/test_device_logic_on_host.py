@@ -286,3 +286,40 @@ def test_task_queue_protocol_model(tmp_path):
     if built.returncode == 0:
         out = subprocess.run([tsan, '8', '400', '5', '0'], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and 'ThreadSanitizer' not in out.stderr, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize('name', ['c2_het16', 'mix32'])
+def test_opt_in_corrected_mode(name, workload_dir):
+    """with corrected=('Q1', 'Q2') the host drops the mislabelled one-stage blocks and fills the
+    between-node bandwidth from the clusterfile's inter_bandwidth; the device code is unchanged.  The result equals
+    the oracle run with the same corrections, differs from the strict search, and the strict default still equals
+    the golden (other tests)."""
+    import itertools
+    from oracle import metis_oracle as orc
+    meta, arr = load_golden(name)
+    w, root, _ = workload_dir(name)
+    cluster, profile, _types, cfg = hs.load_inputs(root, 'profile', meta['file_order'], w.num_layers, w.hidden_size,
+                                                   w.sequence_length, w.vocab_size)
+    seqs = [tuple(s) for s in meta['node_sequences']]
+    fix = ('Q1', 'Q2')
+    problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs, corrected=fix)
+    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance,
+                                     w.max_permute_len, corrected=fix)
+    strict = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance,
+                                      w.max_permute_len)
+    mislabelled = [b for b in strict.blocks if int(b['label_stage']) != int(b['num_stage'])]
+    assert len(seqs) > 1 and len(mislabelled) == len(seqs) - 1            # quirk Q1 in the strict space ...
+    assert all(int(b['label_stage']) == int(b['num_stage']) for b in space.blocks)   # ... and gone here
+    rec, det, summary = hs.host_het_search(problem, space)
+    ocl = orc.OracleCluster(os.path.join(root, 'hostfile'), os.path.join(root, 'clusterfile.json'), corrected=fix)
+    oprof, _ = orc.load_profile_dir(os.path.join(root, 'profile'), meta['file_order'])
+    omodel = orc.OracleModel(w.num_layers, w.hidden_size, w.sequence_length, w.vocab_size, oprof['model']['parameters'])
+    want, counters = orc.het_search(oprof, ocl, omodel, seqs, w.gbs, w.num_layers, w.variance, w.max_permute_len,
+                                    w.max_tp, w.max_bs, corrected=fix)
+    assert (space.num_plans, summary.num_partition_calls, summary.num_records) == (counters['A'], counters['B'], counters['C'])
+    got = hs.unpack_candidates(rec, det, space)
+    assert len(got) == len(want)
+    for g, x in zip(got, want):
+        assert (g[0], g[1], g[3], g[4], g[5], g[6], g[7], g[8]) == (x[0], x[1], x[3], x[4], x[5], x[6], x[7], x[8])
+    gold_costs = set(arr['cost'].tolist())
+    assert any(x[8] not in gold_costs for x in want)                      # Q2 changes costs of multi-node stages

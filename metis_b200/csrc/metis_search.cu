@@ -2,13 +2,16 @@
 //
 // Kernel map:
 //   pack_tables_kernel    flattens the profile tables into one 16 B-aligned blob (+ norm_lc/7)
-//   het_search_kernel     a2..a16: one thread per inter-stage plan; tables staged into shared
-//                         memory by one TMA bulk copy (cp.async.bulk + mbarrier) per block;
-//                         16 B record per costed candidate; warp-shuffle + block argmin
+//   het_search_kernel     a2..a16: cooperative persistent kernel over task lists (a task = one partition
+//                         attempt of one plan): admission, counting sort of the first list, lockstep rounds
+//                         (32 tasks per warp) and a barrier-free queue (one task per warp) - DESIGN.md 4.1;
+//                         tables staged into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier)
+//                         per block; 16 B record per costed candidate; warp-shuffle + block argmin
 //   het_finalize_kernel   grid argmin over the per-block bests, counters -> summary
 //   het_detail_kernel     replays chosen (ordinal, step) candidates to materialise strategies/partition
 //   homo_cost_kernel      a17: one thread per UniformPlan
 //   layer_balance_kernel  a10 alone, for unit parity
+//   (rank_records_kernel, the stable record sort, lives in metis_rank.cu)
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (no FMA contraction: parity).
 #include <cuda_runtime.h>

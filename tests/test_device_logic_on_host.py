@@ -323,3 +323,68 @@ def test_opt_in_corrected_mode(name, workload_dir):
         assert (g[0], g[1], g[3], g[4], g[5], g[6], g[7], g[8]) == (x[0], x[1], x[3], x[4], x[5], x[6], x[7], x[8])
     gold_costs = set(arr['cost'].tolist())
     assert any(x[8] not in gold_costs for x in want)                      # Q2 changes costs of multi-node stages
+
+
+def test_layer_balancer_random_vs_oracle_on_host():
+    """The GPU suite's seeded balancer fuzz, on the host build of the device code: 1 600 random instances of
+    LayerComputeBalancer.run (1-64 stages, 7-128 layers, capacities that over- and under-subscribe the layers)."""
+    import random
+    from oracle import metis_oracle as orc
+    rng = random.Random(11)
+    for L in (7, 24, 96, 128):
+        lc = [0.01 + rng.random() for _ in range(L)]
+        tot = sum(lc)
+        lc = [x / tot for x in lc]
+        rows = []
+        for _ in range(400):
+            S = rng.randint(1, min(L, 64))
+            capa = [rng.random() ** rng.choice([1, 3]) + 1e-3 for _ in range(S)]
+            t = sum(capa) * rng.choice([1.0, 1.0, 0.97, 1.05])
+            rows.append([c / t for c in capa])
+        got = hs.host_layer_balance(rows, lc, L)
+        for capa, g in zip(rows, got):
+            assert g == orc.layer_compute_balance(len(capa), L, list(capa), lc)
+
+
+def test_random_homo_clusters_vs_oracle(tmp_path):
+    """Seeded fuzz of the homogeneous path: HomoCostEstimator.get_cost of every UniformPlan of 60 random
+    single-type clusters (device code, host build) against the oracle - plans kept, plans skipped by KeyError and
+    every fp64 cost."""
+    import random
+    from oracle import metis_oracle as orc
+    from metis_b200 import api
+    from metis_b200.workloads import Workload, materialize, profile_file_order
+    rng = random.Random(77)
+    costed = skipped = 0
+    for idx in range(60):
+        dev = rng.choice(['A100', 'H100', 'B200', 'V100'])
+        per = rng.choice([2, 4, 8])
+        nn = rng.choice([1, 2, 4]) if per == 8 else rng.choice([1, 2, 3, 4])
+        w = Workload(f'homo{idx}', [(dev, per)] * nn, rng.randint(6, 40), rng.choice([8, 16, 24, 32, 64, 96]),
+                     rng.choice([1024, 4096]), rng.choice([512, 2048]), 51200, max_tp=rng.choice([1, 2, 4]),
+                     tps=(1, 2, 4), bss=rng.choice([(1, 2, 4), (1, 2, 4, 8), (1, 2)]), seed=1000 + idx,
+                     memory_gb={dev: rng.choice([8, 16, 40, 80])})
+        root = str(tmp_path / w.name)
+        materialize(w, root)
+        order = profile_file_order(w)
+        cluster, profile, types, cfg = hs.load_inputs(root, 'profile', order, w.num_layers, w.hidden_size,
+                                                      w.sequence_length, w.vocab_size)
+        plans = np.array([[p.dp, p.pp, p.tp, p.mbs, p.gbs]
+                          for p in api.UniformPlanGenerator(cluster.get_total_num_devices(), w.max_tp, w.gbs)
+                          if p.gbs == w.gbs], dtype=np.int32)
+        if not len(plans):
+            continue
+        problem = flatten.build_problem(profile, cluster, cfg, w.gbs, int(plans[:, 2].max()), int(plans[:, 3].max()),
+                                        [tuple(dict.fromkeys(t.name for t in cluster.get_device_types()))])
+        cost, status = hs.host_homo_cost(problem, problem.type_names.index(types[0]), plans)
+        ocl = orc.OracleCluster(os.path.join(root, 'hostfile'), os.path.join(root, 'clusterfile.json'))
+        oprof, otypes = orc.load_profile_dir(os.path.join(root, 'profile'), order)
+        omodel = orc.OracleModel(w.num_layers, w.hidden_size, w.sequence_length, w.vocab_size, oprof['model']['parameters'])
+        want, counters = orc.homo_search(oprof, ocl, omodel, otypes[0], w.gbs, w.max_tp)
+        keep = status != 1
+        assert counters['matched'] == len(plans) and counters['keyerr'] == int((~keep).sum()), w
+        assert plans[keep].tolist() == [list(p) for p, _ in want], w
+        assert cost[keep].tolist() == [c for _, c in want], w
+        costed += len(want)
+        skipped += counters['keyerr']
+    assert costed > 500 and skipped > 0, (costed, skipped)

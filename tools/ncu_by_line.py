@@ -2,7 +2,11 @@
 """Developer tool: attribute `Instructions Executed` / stall samples of an ncu report to CUDA source
 lines (ncu's CSV source page is SASS-only; nvdisasm -g supplies the SASS offset -> file:line map).
 
-  python tools/ncu_by_line.py gpurun_out/<report>.ncu-rep [kernel-substring] [top-N]
+  python tools/ncu_by_line.py gpurun_out/<report>.ncu-rep [kernel-substring] [top-N] [--sectors]
+
+--sectors ranks the lines by L2 sectors instead ("L2 Theoretical Sectors Local" + "... Global", 32 B each): which
+source lines generate the memory traffic (local = per-thread scratch of the throughput mode, global = task lists,
+rows, records).
 """
 import collections
 import csv
@@ -12,6 +16,9 @@ import subprocess
 import sys
 import tempfile
 
+sectors = '--sectors' in sys.argv
+if sectors:
+    sys.argv.remove('--sectors')
 rep = sys.argv[1]
 kern = sys.argv[2] if len(sys.argv) > 2 else 'het_search_kernelILi64'
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 45
@@ -57,6 +64,21 @@ def text(key):
     if f not in src and os.path.exists(path):
         src[f] = open(path).read().splitlines()
     return src[f][n - 1].strip()[:90] if f in src and 0 < n <= len(src[f]) else ''
+if sectors:
+    il, ig = hdr.index('L2 Theoretical Sectors Local'), hdr.index('L2 Theoretical Sectors Global')
+    iop = hdr.index('Access Operation')
+    mem = collections.defaultdict(lambda: [0, 0, set()])
+    mt = [0, 0]
+    for r in rows[2:]:
+        key = line_of.get(int(r[ia], 16) - base, ('?', 0))
+        loc, glo = int(r[il] or 0), int(r[ig] or 0)
+        if loc or glo:
+            mem[key][0] += loc; mem[key][1] += glo; mem[key][2].add(r[iop])
+            mt[0] += loc; mt[1] += glo
+    print(f'L2 theoretical sectors: local {mt[0]/1e6:.1f} M ({mt[0]*32/1e9:.2f} GB), global {mt[1]/1e6:.1f} M ({mt[1]*32/1e9:.2f} GB)')
+    for key, (loc, glo, ops) in sorted(mem.items(), key=lambda kv: -(kv[1][0] + kv[1][1]))[:top]:
+        print(f'{100*(loc+glo)/max(mt[0]+mt[1],1):5.1f}%  local {loc*32/1e6:8.1f} MB  global {glo*32/1e6:8.1f} MB  {"/".join(sorted(o for o in ops if o and o != "-")):12s} {key[0]}:{key[1]:<5d} {text(key)}')
+    sys.exit(0)
 print(f'total warp-inst {tot[0]/1e9:.3f}e9, thread/inst {tot[1]/max(tot[0],1):.2f}, samples {tot[2]}')
 for key, (ex, th, sm) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f'{100*ex/tot[0]:5.1f}% inst {100*sm/max(tot[2],1):5.1f}% smp  {key[0]}:{key[1]:<5d} {text(key)}')

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define METIS_ABI_VERSION 1
+#define METIS_ABI_VERSION 2
 
 /* return codes */
 #define METIS_OK            0
@@ -45,7 +45,6 @@ extern "C" {
 #define METIS_FATAL_HANG        4   /* reference loop at load_balancer.py:96-104 would not terminate                */
 #define METIS_FATAL_SCRATCH     5   /* internal scratch exceeded (more stages / leftovers than compiled limits)     */
 #define METIS_FATAL_ZERODIV     6   /* ZeroDivisionError in the reference (zero profiled time / zero total)         */
-#define METIS_FATAL_SCHEDULER   7   /* internal: the device task queue made no progress for 2 s (watchdog; a bug)    */
 
 /* limits compiled into the kernels */
 #define METIS_MAX_TYPES   8
@@ -115,6 +114,7 @@ typedef struct MetisPlanBlock {
  */
 typedef struct MetisPlanSpace {
     int64_t num_plans;
+    int64_t rows_bytes;           /* size of the `rows` blob (must stay below 4 GiB)                   */
     int32_t num_blocks;
     int32_t num_div;
     int32_t max_stage;            /* largest num_stage of any block (sizes the per-plan task state)  */
@@ -143,7 +143,8 @@ typedef struct MetisSearchSummary {
     uint32_t fatal_code;          /* METIS_FATAL_* of that ordinal                                  */
     uint32_t fatal_aux;           /* tp<<16 | bs of the missing key when applicable                 */
     MetisRecord best;             /* argmin (cost, ordinal, step); cost = +inf when no record       */
-    uint64_t reserved[6];         /* profiling builds: warp-cycles spent in phases F,P,R,M,C            */
+    uint64_t reserved[6];         /* [0] plans admitted (have a valid first strategy), [1] plans handed from the
+                                     bulk round to the chain kernel; rest 0                              */
 } MetisSearchSummary;
 
 /* Shard of the ordinal space evaluated by one call (multi-GPU: rank r of n, interleaved tiles). */
@@ -151,8 +152,9 @@ typedef struct MetisShard {
     int32_t rank;                 /* 0 <= rank < world                                              */
     int32_t world;
     int32_t tile;                 /* plans per interleave tile (multiple of 32)                     */
-    int32_t reserved;             /* tuning: task lists shorter than reserved x (resident warps) run one task
-                                     per warp through the barrier-free queue; 0 = default (12)        */
+    int32_t reserved;             /* tuning: minimum number of admitted plans for which the bulk round (first
+                                     partition attempt, one plan per thread) runs before the chain kernel;
+                                     0 = default (12 x resident chain warps), INT32_MAX = chain kernel only */
 } MetisShard;
 
 const char *metis_last_error(void);
@@ -165,9 +167,9 @@ int metis_abi_version(void);
  */
 void metis_set_profile_events(void *before_kernel, void *after_kernel);
 
-/* Bytes of device scratch metis_het_search needs for a shard of `num_plans` plans whose largest
- * stage count is `max_stage` (task lists of the round scheduler; large spaces are cut into waves so
- * this stays below ~4.3 GB).  metis_het_detail / metis_homo_cost need metis_het_workspace_bytes(problem, 0, 1). */
+/* Bytes of device scratch metis_het_search needs for a shard of `num_plans` plans: the packed tables
+ * plus two lists of 16 B per plan (worst case: every plan has a valid strategy); `max_stage` is ignored.
+ * metis_het_detail / metis_homo_cost need metis_het_workspace_bytes(problem, 0, 1). */
 int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans, int32_t max_stage);
 
 /*
@@ -178,7 +180,6 @@ int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans
  *                dp code[num_stage], tp code[num_stage] (log2) then layer_partition[num_stage+1]
  *                (uint8 each); detail_stride >= 3*METIS_MAX_STAGES+1, or NULL
  *   workspace    [device] metis_het_workspace_bytes(problem, plans in shard, space->max_stage) bytes
- *                (task lists for one wave of plans: up to 32 GiB by default, METIS_TASK_MIB overrides)
  *   summary      [host]   filled asynchronously (use pinned memory)
  */
 int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, const MetisShard *shard,

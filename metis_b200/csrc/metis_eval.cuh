@@ -1006,8 +1006,9 @@ struct PlanEvaluator {
     // capacity re-weighting.  returns 1 = partition accepted (w.mstate = memory_state), 2 = retry
     // with the adjusted w.perf, 0 = (None, -1, None), <0 = fatal (negated code).  After the third
     // failed attempt the reference still evaluates _adj_compute_performance and discards it; that
-    // call is skipped here.
-    MB_HD int memory_phase(int attempt) {
+    // call is skipped here.  `defer`: report 2 on the first out-of-memory state without re-weighting (the
+    // first-task round hands such plans to the chain kernel, which replays the attempt).
+    MB_HD int memory_phase(int attempt, bool defer = false) {
         const int S = pd.S;
         const bool one_type = T.p.num_types == 1;
         const int type0 = T.run_type[pd.ns * T.p.num_types];
@@ -1049,6 +1050,7 @@ struct PlanEvaluator {
             return 1;
         }
         if (attempt >= 3) return 0;
+        if (defer) return 2;
         x.mark(21);
         const int rc = adjust_performance();
         if (rc < 0) return rc;
@@ -1304,143 +1306,53 @@ struct PlanEvaluator {
 };
 
 // ---------------------------------------------------------------------------
-// Round-based search (the search kernel's schedule).
+// First task of a plan, one plan per thread (the bulk round of the search, metis_search.cu).
 //
-// The work per inter-stage plan is heavy-tailed: most plans need one LayerComputeBalancer run, a
-// few per cent need 10-36 *sequential* runs (strategy chain x re-partition attempts).  A "task"
-// is therefore one partition attempt of one plan; every round executes all pending tasks, one
-// task per lane, packed densely into warps, and appends the plans that continue to the list of
-// the next round.  Between rounds only a header, the strategy (tp codes) and - for a re-partition
-// attempt - the re-weighted stage performance persist, in [stage][slot] arrays so that a warp
-// reads and writes them coalesced.
-//   begin_task : plan -> first strategy that can be valid (PlanEvaluator::begin)
-//   run_task   : [P stage performance] -> R LayerComputeBalancer.run -> M memory check /
-//                re-weighting -> C cost + record -> advance along the chain (plan.py:192-268)
-// All lanes of a warp walk these steps together; `Warp::append(cont)` is called convergently.
-// `Warp::consumed(pos)` / `Warp::publish(pos, cont)` bracket the life of a list slot for schedulers that
-// hand tasks over without a barrier (metis_search.cu: QueueWarp); the round-based ones ignore them.
+// The work per inter-stage plan is heavy-tailed: most plans need exactly one LayerComputeBalancer
+// run (their first strategy is partitioned at the first attempt, which also ends the chain,
+// plan.py:194-195); a few per cent need 10-36 *sequential* runs.  The first attempt of the first
+// strategy of every admitted plan is therefore evaluated with 32 plans per warp in lockstep; a
+// plan whose first attempt runs out of memory is handed, unchanged, to the chain kernel (one warp
+// per plan, metis_coop.cuh), which replays that attempt and walks the rest of the chain.
+// returns true when the plan continues in the chain kernel.
 // ---------------------------------------------------------------------------
-struct TaskBuffers {
-    uint64_t *hdr;      // [cap]            ordinal | step << 32 | attempt << 48 | nrep << 52 | retry << 56
-    uint64_t *geo;      // [cap]            plan geometry (pack_geo)
-    uint8_t *tpc;       // [smax][cap]      log2(tp) per stage
-    double *perf;       // [smax][cap]      re-weighted stage performance (retry tasks only)
-    int64_t cap;
-};
-
-MB_HD uint64_t pack_task(uint32_t ordinal, int step, int attempt, int nrep, bool retry) {
-    return (uint64_t)ordinal | ((uint64_t)(step & 0xFFFF) << 32) | ((uint64_t)(attempt & 0xF) << 48) |
-           ((uint64_t)(nrep & 0xF) << 52) | ((uint64_t)(retry ? 1 : 0) << 56);
-}
-
-template <int MAXS, int MAXL, class Sink, class Warp>
-MB_HD void begin_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, Warp &warp, const TaskBuffers &out,
-                      bool has, const PlanDesc &plan) {
+template <int MAXS, int MAXL, class Sink>
+MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool has, const PlanDesc &plan) {
     PlanEvaluator<MAXS, MAXL, Serial> ev(T, w);
     bool cont = false;
-    if (has) {
+    sink.phase(1);
+    if (has) {                                               // ---- P ----
         const int ok = ev.begin(plan);
         if (ok < 0) sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0);
-        cont = ok == 1;
+        has = ok == 1;
     }
-    const int64_t pos = warp.append(cont);
-    if (cont) {
-        out.hdr[pos] = pack_task(plan.ordinal, 0, 1, 0, false);
-        out.geo[pos] = plan.geo;
-#pragma unroll 1
-        for (int s = 0; s < plan.S; ++s) out.tpc[(int64_t)s * out.cap + pos] = w.tpc[s];
+    if (has) {
+        sink.partition_call();
+        const int rc = ev.compute_performance();
+        if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
     }
-}
-
-template <int MAXS, int MAXL, class X, class Sink, class Warp>
-MB_HD void run_task(const Tables &T, Scratch<MAXS, MAXL> &w, const X &lanes, Sink &sink, Warp &warp,
-                    const TaskBuffers &in, const TaskBuffers &out, bool has, int64_t pos, const PlanDesc &plan) {
-    PlanEvaluator<MAXS, MAXL, X> ev(T, w, lanes);
-    int step = 0, attempt = 1, nrep = 0;
-    bool retry = false, cont = false, advance = false, have_state = false, costing = false;
-    lanes.mark(1);
-    sink.phase(1);
-    lanes.sync();                                            // the warp's previous task is finished in every lane
-    if (has) {                                               // ---- restore, P ----
-        const uint64_t h = list_load(&in.hdr[pos]);
-        step = (int)((h >> 32) & 0xFFFF);
-        attempt = (int)((h >> 48) & 0xF);
-        nrep = (int)((h >> 52) & 0xF);
-        retry = ((h >> 56) & 1) != 0;
-        ev.pd = plan;
-        ev.bs_total = T.p.gbs / plan.batches;
-        ev.nbad = 0;
-        ev.set_groups(plan.row);
-#pragma unroll (X::kUniform ? 1 : 0)
-        for (int s = lanes.lane(); s < plan.S; s += lanes.width()) {
-            w.tpc[s] = list_load(&in.tpc[(int64_t)s * in.cap + pos]);
-            if (retry) w.perf[s] = list_load(&in.perf[(int64_t)s * in.cap + pos]);
-        }
-        lanes.sync();
-        warp.consumed(pos);                                  // the task's slot may be reused from here on
-        lanes.mark(2);
-        if (!retry) {
-            sink.partition_call();
-            const int rc = ev.compute_performance();
-            if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
-        }
+    sink.phase(2);
+    if (has) {                                               // ---- R ----
+        sink.balancer_run();
+        const int rc = balance_run<MAXS, MAXL>(T, plan.S, w, Serial());
+        if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
     }
-    // In the cooperative mode a re-partition attempt follows immediately (same warp, state in shared
-    // memory); in the throughput mode it becomes a task of the next round so the warp stays converged.
-#pragma unroll (X::kUniform ? 1 : 0)
-    for (;;) {
-        sink.phase(2);
-        if (has) {                                           // ---- R ----
-            sink.balancer_run();
-            const int rc = balance_run<MAXS, MAXL>(T, plan.S, w, lanes);
-            if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
-        }
-        lanes.mark(20);
-        sink.phase(3);
-        bool again = false;
-        if (has) {                                           // ---- M ----
-            const int r = ev.memory_phase(attempt);
-            if (r < 0) { sink.fatal(plan.ordinal, -r, ev.aux); has = false; }
-            else if (r == 2) { retry = true; ++attempt; if (X::kUniform) again = true; else cont = true; }
-            else if (r == 0) { have_state = false; advance = true; }     // memory_state = None (plan.py:225)
-            else { have_state = true; nrep = attempt; costing = true; }
-        }
-        if (!again) break;
+    sink.phase(3);
+    bool costing = false;
+    if (has) {                                               // ---- M ----
+        const int r = ev.memory_phase(1, true);
+        if (r < 0) sink.fatal(plan.ordinal, -r, ev.aux);
+        else if (r == 2) cont = true;                        // out of memory: re-weighting and the rest in the chain kernel
+        else costing = true;                                 // r == 1: partition accepted at the first attempt
     }
-    lanes.mark(22);
     sink.phase(4);
-    if (has && costing) {                                    // ---- C ----
+    if (costing) {                                           // ---- C ---- (num_repartition == 1 ends the chain)
         double cost;
-        if (ev.get_cost(cost) == 0) sink.emit(plan, step, nrep, cost, w.tpc, w.part);
+        if (ev.get_cost(cost) == 0) sink.emit(plan, 0, 1, cost, w.tpc, w.part);
         else sink.keyerror();
-        ++step;
-        advance = nrep != 1;                                 // plan.py:194-195
     }
-    lanes.mark(23);
     sink.phase(0);
-    lanes.sync();                                            // the leader's record is written: lanes walk the chain together
-    if (has && advance) {                                    // ---- chain (plan.py:197-206) ----
-#pragma unroll (X::kUniform ? 1 : 0)
-        for (;;) {
-            if (!ev.next_strategy(have_state)) break;        // :203-204
-            if (ev.valid()) { cont = true; retry = false; attempt = 1; break; }
-        }
-    }
-    lanes.mark(24);
-    lanes.sync();
-    const int64_t opos = warp.append(has && cont);
-    if (has && cont) {
-        out.hdr[opos] = pack_task(plan.ordinal, step, attempt, nrep, retry);
-        out.geo[opos] = plan.geo;
-        lanes.sync();
-#pragma unroll (X::kUniform ? 1 : 0)
-        for (int s = lanes.lane(); s < plan.S; s += lanes.width()) {
-            out.tpc[(int64_t)s * out.cap + opos] = w.tpc[s];
-            if (retry) out.perf[(int64_t)s * out.cap + opos] = w.perf[s];
-        }
-    }
-    warp.publish(opos, has && cont);                         // successor complete in memory
-    lanes.mark(0);
+    return cont;
 }
 
 // ---------------------------------------------------------------------------

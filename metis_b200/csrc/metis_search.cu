@@ -2,11 +2,13 @@
 //
 // Kernel map:
 //   pack_tables_kernel    flattens the profile tables into one 16 B-aligned blob (+ norm_lc/7)
-//   het_search_kernel     a2..a16: cooperative persistent kernel over task lists (a task = one partition
-//                         attempt of one plan): admission, counting sort of the first list, lockstep rounds
-//                         (32 tasks per warp) and a barrier-free queue (one task per warp) - DESIGN.md 4.1;
-//                         tables staged into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier)
-//                         per block; 16 B record per costed candidate; warp-shuffle + block argmin
+//   het_admit_kernel      a2: ordinal -> plan, plans without a valid strategy dropped, survivors listed
+//   het_scatter_kernel    counting sort of the list by stage count (longest first)
+//   het_first_kernel      a5..a16, bulk round: first partition attempt of every listed plan, one plan per thread
+//   het_chain_kernel      a5..a16: one warp per plan walks the whole strategy chain (metis_coop.cuh);
+//                         both evaluation kernels stage the tables into shared memory by one TMA bulk copy
+//                         (cp.async.bulk + mbarrier) per block, write a 16 B record per costed candidate and
+//                         reduce their best candidate by warp shuffles + shared memory
 //   het_finalize_kernel   grid argmin over the per-block bests, counters -> summary
 //   het_detail_kernel     replays chosen (ordinal, step) candidates to materialise strategies/partition
 //   homo_cost_kernel      a17: one thread per UniformPlan
@@ -22,6 +24,7 @@
 #include <string.h>
 
 #include "metis_eval.cuh"
+#include "metis_coop.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -227,24 +230,16 @@ struct DeviceSink {
     unsigned int n_part, n_run, n_key;
     double best_cost;
     uint32_t best_ord, best_step, best_meta;
-    bool leader;                    // cooperative mode: only lane 0 of the warp produces side effects
+    bool leader;                    // chain kernel: only lane 0 of the warp produces side effects
     __device__ DeviceSink(const DeviceOut &out)
         : o(out), n_part(0), n_run(0), n_key(0), best_cost(INFINITY), best_ord(0xFFFFFFFFu), best_step(0xFFFFu),
           best_meta(0), leader(true) {}
-#ifdef METIS_PROFILE_PHASES
-    long long t_last = 0; int cur = -1; long long acc[6] = {0, 0, 0, 0, 0, 0};
-    __device__ void phase(int k) {
-        if (!leader) return;
-        const long long now = clock64();
-        if (cur >= 0) acc[cur] += now - t_last;
-        cur = k; t_last = now;
-    }
-#else
     __device__ void phase(int) {}
-#endif
     __device__ void partition_call() { n_part += leader ? 1u : 0u; }
     __device__ void balancer_run() { n_run += leader ? 1u : 0u; }
     __device__ void keyerror() { n_key += leader ? 1u : 0u; }
+    // lowest ordinal wins; among several fatal conditions of one plan the earliest (first raised) is kept by the
+    // caller order: a plan reports at most one fatal condition (its evaluation stops there)
     __device__ void fatal(uint32_t ordinal, int code, uint32_t aux) {
         if (!leader) return;
         const unsigned long long key = ((unsigned long long)ordinal << 32) | ((unsigned long long)(code & 0xFF) << 24) |
@@ -272,43 +267,182 @@ struct DeviceSink {
     }
 };
 
-// Warp-level services of begin_task / run_task: ballot + one aggregated atomicAdd per warp hands
-// out consecutive slots of the next round's task list (so the state stores are coalesced).
-struct DeviceWarp {
-    unsigned int *counter;
-    __device__ explicit DeviceWarp(unsigned int *c) : counter(c) {}
-    __device__ int64_t append(bool want) const {
-        const unsigned full = 0xFFFFFFFFu;
-        const unsigned m = __ballot_sync(full, want);
-        if (m == 0) return -1;
-        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        unsigned int base = 0;
-        if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
-        base = __shfl_sync(full, base, leader);
-        return (int64_t)base + __popc(m & ((1u << lane) - 1u));
+// End of a search kernel: counters (warp reduce, one atomic per warp) and the block's best candidate:
+// argmin (cost, ordinal, step) by __shfl_xor_sync inside the warp, then across the warps through shared memory.
+__device__ __forceinline__ void finish_block(const DeviceSink &sink, const DeviceOut &out, int slot) {
+    __shared__ double s_cost[32];
+    __shared__ uint32_t s_ord[32], s_step[32], s_meta[32];
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned np = __reduce_add_sync(full, sink.n_part);
+    const unsigned nr = __reduce_add_sync(full, sink.n_run);
+    const unsigned nk = __reduce_add_sync(full, sink.n_key);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        if (np) atomicAdd(&out.counters[1], (unsigned long long)np);
+        if (nr) atomicAdd(&out.counters[2], (unsigned long long)nr);
+        if (nk) atomicAdd(&out.counters[3], (unsigned long long)nk);
     }
-    __device__ void consumed(int64_t) const {}
-    __device__ void publish(int64_t, bool) const {}
-};
+    double c = sink.best_cost;
+    uint32_t o = sink.best_ord, st = sink.best_step, mt = sink.best_meta;
+    for (int d = 16; d > 0; d >>= 1) {
+        const double c2 = __shfl_xor_sync(full, c, d);
+        const uint32_t o2 = __shfl_xor_sync(full, o, d), s2 = __shfl_xor_sync(full, st, d),
+                       m2 = __shfl_xor_sync(full, mt, d);
+        if (rec_less(c2, o2, s2, c, o, st)) { c = c2; o = o2; st = s2; mt = m2; }
+    }
+    if (lane == 0) { s_cost[warp] = c; s_ord[warp] = o; s_step[warp] = st; s_meta[warp] = mt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int wi = 1; wi < nw; ++wi)
+            if (rec_less(s_cost[wi], s_ord[wi], s_step[wi], c, o, st)) { c = s_cost[wi]; o = s_ord[wi]; st = s_step[wi]; mt = s_meta[wi]; }
+        MetisRecord r;
+        r.cost = c; r.ordinal = o; r.step = (uint16_t)st; r.num_repartition = (uint8_t)(mt >> 8); r.num_stage = (uint8_t)mt;
+        out.block_best[slot] = r;
+    }
+}
 
-// Lane policy of the cooperative (latency) mode, see metis_eval.cuh `Serial`.
+// ---- the search, four kernels on one stream ---------------------------------------
+//   het_admit_kernel    one thread per inter-stage plan: decode, first strategy that can be valid, drop the plans
+//                       that have none (78 % at BASELINE configs[2]); survivors -> list A + histogram of stage counts
+//   het_scatter_kernel  counting sort of list A by stage count, longest first -> list B
+//   het_first_kernel    bulk round: first partition attempt of every listed plan, one plan per thread, 32 plans of
+//                       equal stage count per warp in lockstep; plans that run out of memory -> list C
+//   het_chain_kernel    one warp per plan: the whole strategy chain, depth first (metis_coop.cuh), over list C -
+//                       or over list B when the list is too short to fill the bulk round
+// List entry: (ordinal, flags, geometry word); flags bit 0 = first attempt already counted by the bulk round.
+struct SearchLists {
+    uint4 *a, *b;                 // list C reuses the storage of list A
+    unsigned int *ctl;            // [0] admitted [1] bulk fetch cursor [2] continuations [3] chain fetch cursor
+                                  // [16..16+128) histogram by stage count, [160+16..) scatter cursors
+    long long bulk_min;           // lists shorter than this skip the bulk round
+};
+constexpr int kCtlHist = 16, kCtlCursor = 16 + 160;
+
+__device__ __forceinline__ uint4 make_entry(uint32_t ordinal, uint32_t flags, uint64_t geo) {
+    return make_uint4(ordinal, flags, (uint32_t)geo, (uint32_t)(geo >> 32));
+}
+__device__ __forceinline__ void decode_entry(const MetisPlanSpace &sp, const uint4 e, PlanDesc &pd) {
+    decode_task(sp, (uint64_t)e.x, ((uint64_t)e.w << 32) | e.z, pd);
+}
+
+__global__ void __launch_bounds__(256)
+het_admit_kernel(const __grid_constant__ MetisPlanSpace sp, const MetisShard sh, const long long slots,
+                 const int gbs, const int max_bs, const int max_tp, const SearchLists ls) {
+    const int lane = threadIdx.x & 31;
+    const long long b0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31LL;   // the warp's first slot
+    if (b0 >= slots) return;
+    // tiles are multiples of 32, so a warp's 32 plans are consecutive ordinals
+    const long long first = ((b0 / sh.tile) * sh.world + sh.rank) * sh.tile + (b0 % sh.tile);
+    int hint = 0;
+    if (lane == 0 && first < sp.num_plans) hint = find_block(sp, first);
+    hint = __shfl_sync(0xFFFFFFFFu, hint, 0);
+    PlanDesc pd;
+    bool ok = b0 + lane < slots && decode_plan(sp, first + lane, pd, hint);
+    if (ok) {
+        // PlanEvaluator::begin: tp_s = max(1, group_s / B), B = 2^floor(log2(gbs // batches)); the plan has a
+        // valid strategy iff that one is valid (search_space/plan.py:238-249)
+        const int bs_total = gbs / pd.batches;
+        const int lb = 31 - __clz(bs_total > 0 ? bs_total : 1);
+        if (bs_total <= 0) ok = false;
+        for (int s = 0; ok && s < pd.S; ++s) {
+            const int g = __ldg(&pd.row[s]);
+            const int t = g > lb ? g - lb : 0;
+            const int mbs = bs_total >> (g - t);
+            if (mbs == 0 || mbs > max_bs || (1 << t) > max_tp) ok = false;
+        }
+    }
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned m = __ballot_sync(full, ok);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(&ls.ctl[0], (unsigned int)__popc(m));
+    base = __shfl_sync(full, base, leader);
+    const int k = ok ? pd.S - 1 : -1;
+    const unsigned peers = __match_any_sync(full, k);        // neighbours mostly share the stage count
+    if (ok) {
+        ls.a[base + __popc(m & ((1u << lane) - 1u))] = make_entry(pd.ordinal, 0u, pd.geo);
+        if (lane == __ffs(peers) - 1) atomicAdd(&ls.ctl[kCtlHist + k], (unsigned int)__popc(peers));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+het_scatter_kernel(const SearchLists ls) {
+    __shared__ unsigned int s_base[METIS_MAX_STAGES];
+    const unsigned int n = ls.ctl[0];
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int k = METIS_MAX_STAGES - 1; k >= 0; --k) { s_base[k] = acc; acc += ls.ctl[kCtlHist + k]; }   // longest first
+    }
+    __syncthreads();
+    const long long span = (long long)gridDim.x * blockDim.x;
+    const long long upto = (((long long)n + 31) / 32) * 32;
+    for (long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x; pos < upto; pos += span) {
+        const bool live = pos < (long long)n;
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (live) e = ls.a[pos];
+        const int k = live ? (int)(e.w & 0xFF) : -1;         // geometry bits 32..39 = S - 1
+        const unsigned int peers = __match_any_sync(0xFFFFFFFFu, k);
+        const int leader = __ffs(peers) - 1, me = threadIdx.x & 31;
+        unsigned int at = 0;
+        if (live && me == leader) at = atomicAdd(&ls.ctl[kCtlCursor + k], (unsigned int)__popc(peers));
+        at = __shfl_sync(0xFFFFFFFFu, at, leader);
+        if (live) ls.b[(long long)s_base[k] + at + __popc(peers & ((1u << me) - 1u))] = e;
+    }
+}
+
+template <int MAXS, int MAXL>
+__global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? METIS_MIN_BLOCKS : (METIS_MIN_BLOCKS * 2 + 2) / 3))
+het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
+                 const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob, const int use_smem,
+                 const __grid_constant__ DeviceOut out, const SearchLists ls, const int best_slot) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    DeviceSink sink(out);
+    const unsigned int n = ls.ctl[0];
+    if ((long long)n >= ls.bulk_min) {
+        const uint8_t *base = blob;
+        if (use_smem) {
+            stage_blob_tma(smem, blob, lay.total, &mbar);
+            base = smem;
+        }
+        const Tables T = make_tables(p, lay, base);
+        Scratch<MAXS, MAXL> w;
+        const int lane = threadIdx.x & 31;
+        for (;;) {                                           // batches of 32 plans, longest stage counts first
+            unsigned int fetched = 0;
+            if (lane == 0) fetched = atomicAdd(&ls.ctl[1], 1u);
+            const long long b0 = 32LL * __shfl_sync(0xFFFFFFFFu, fetched, 0);
+            if (b0 >= (long long)n) break;
+            const long long pos = b0 + lane;
+            PlanDesc pd;
+            const bool has = pos < (long long)n;
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if (has) { e = ls.b[pos]; decode_entry(sp, e, pd); }
+            const bool cont = first_task<MAXS, MAXL>(T, w, sink, has, pd);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, cont);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                unsigned int at = 0;
+                if (lane == leader) at = atomicAdd(&ls.ctl[2], (unsigned int)__popc(m));
+                at = __shfl_sync(0xFFFFFFFFu, at, leader);
+                if (cont) { e.y = 1u; ls.a[at + __popc(m & ((1u << lane) - 1u))] = e; }
+            }
+        }
+    }
+    finish_block(sink, out, best_slot + blockIdx.x);
+}
+
+// Lane policy of the chain kernel (metis_coop.cuh): 32 lanes, leader = lane 0, __syncwarp between sections.
 #ifdef METIS_PROFILE_PHASES
-__device__ long long g_mark_acc[64];   // [0,32) cycles per phase, [32,64) largest lane skew seen at each mark
+__device__ long long g_mark_acc[64];   // cycles per phase of the chain evaluator (leader lane)
 #endif
-struct WarpLanes {
-    static constexpr bool kUniform = true;
+struct WarpCoop {
 #ifdef METIS_PROFILE_PHASES
     mutable long long t_last = 0;
     mutable int cur = 0;
     __device__ void mark(int id) const {
-#ifdef METIS_PROBE_SKEW
-        {   // do the lanes of the warp reach this point in the same cycle?  (redundant execution relies on it)
-            const long long t = clock64();
-            const long long t0 = __shfl_sync(0xFFFFFFFFu, t, 0);
-            const long long d = t > t0 ? t - t0 : t0 - t;
-            if (d) atomicMax((unsigned long long *)&g_mark_acc[32 + (id & 31)], (unsigned long long)d);
-        }
-#endif
         if ((threadIdx.x & 31) != 0) return;
         const long long now = clock64();
         if (t_last) atomicAdd((unsigned long long *)&g_mark_acc[cur & 31], (unsigned long long)(now - t_last));
@@ -319,12 +453,29 @@ struct WarpLanes {
 #endif
     __device__ int lane() const { return threadIdx.x & 31; }
     __device__ int width() const { return 32; }
+    __device__ bool leader() const { return (threadIdx.x & 31) == 0; }
     __device__ void sync() const { __syncwarp(); }
     __device__ bool any(bool p) const { return __any_sync(0xFFFFFFFFu, p); }
     __device__ void argmax_first(double &v, int &i) const {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             const double v2 = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+            const int i2 = __shfl_xor_sync(0xFFFFFFFFu, i, d);
+            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+        }
+    }
+    __device__ void argmin_first(double &v, int &i) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double v2 = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+            const int i2 = __shfl_xor_sync(0xFFFFFFFFu, i, d);
+            if (v2 < v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+        }
+    }
+    __device__ void imax_first(int &v, int &i) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int v2 = __shfl_xor_sync(0xFFFFFFFFu, v, d);
             const int i2 = __shfl_xor_sync(0xFFFFFFFFu, i, d);
             if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
         }
@@ -337,337 +488,70 @@ struct WarpLanes {
         }
         return v;
     }
-};
-
-// Continuous latency mode: once a list is short enough to run one task per warp, the grid stops meeting at
-// barriers.  The remaining tasks live in a bounded multi-producer / multi-consumer ring over the slots of one
-// task buffer (sequence number per slot: == ticket -> free for that ticket, == ticket + 1 -> published); a
-// warp pops a ticket, runs the task, pushes its successor (if the plan continues) and pops again, so nobody
-// idles while any chain still has a step to run.  At most one task per chain is alive, so with ring >= number of
-// tasks at the switch a producer never finds its slot occupied; `alive` (pushed - retired) reaching zero tells
-// the poppers that no ticket will ever be published again.
-__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {     // polling: no L1 invalidation per try
-    unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// Watchdog of the queue's spin loops: a waiter that sees neither a push nor a retirement for 2 s declares the
-// scheduler dead (ctl[3] = 1 releases every waiter, the search reports METIS_FATAL_SCHEDULER instead of hanging).
-// All waiting below is written warp-uniformly: every lane runs the same loop and takes the same branches, lane 0
-// performs the memory operation (a single predicated instruction) and its value is broadcast.  A branchy
-// `if (lane == 0) { spin }` lets the compiler keep lane 0 and lanes 1-31 as two separately scheduled groups for
-// the rest of the task, and the redundant-execution sections of the latency mode then see
-// each other's half-finished updates.
-struct QueueWatch {
-    unsigned int *ctl;
-    unsigned long long *diag;          // counters[16..]: which loop, ticket, slot value, head, tail, alive
-    unsigned int polls = 0, last_tail = 0, last_alive = 0;
-    unsigned long long since = 0;
-    __device__ QueueWatch(unsigned int *c, unsigned long long *d) : ctl(c), diag(d) {}
-    // true = give up (uniform: every lane evaluates the same broadcast values)
-    __device__ bool expired(int which, unsigned int ticket, unsigned int seen) {
-        if ((++polls & 255u) != 0) return false;
-        unsigned int tail = 0, alive = 0, fired = 0;
-        unsigned long long now = 0;
-        if ((threadIdx.x & 31) == 0) {
-            tail = *(volatile unsigned int *)&ctl[1]; alive = *(volatile unsigned int *)&ctl[2];
-            fired = *(volatile unsigned int *)&ctl[3]; now = global_ns();
+    __device__ int incl_scan(int v) const {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if (lane >= d) v += u;
         }
-        tail = __shfl_sync(0xFFFFFFFFu, tail, 0); alive = __shfl_sync(0xFFFFFFFFu, alive, 0);
-        fired = __shfl_sync(0xFFFFFFFFu, fired, 0); now = __shfl_sync(0xFFFFFFFFu, now, 0);
-        if (fired) return true;
-        if (since == 0 || tail != last_tail || alive != last_alive) { since = now; last_tail = tail; last_alive = alive; return false; }
-        if (now - since < 2000000000ULL) return false;
-        if ((threadIdx.x & 31) == 0 && atomicExch(&ctl[3], 1u) == 0u) {
-            diag[0] = (unsigned long long)which; diag[1] = ticket; diag[2] = seen;
-            diag[3] = *(volatile unsigned int *)&ctl[0]; diag[4] = tail; diag[5] = alive;
-        }
-        return true;
+        return v;
     }
-};
-struct QueueWarp {
-    unsigned int *seq;         // [ring]
-    unsigned int *ctl;         // [0] head (pop tickets) [1] tail (push tickets) [2] alive [3] watchdog fired
-    unsigned long long *diag;
-    unsigned int ring;
-    unsigned int taken;        // ticket of the task being run
-    unsigned int pushed;       // ticket of the successor being written
-    __device__ int64_t append(bool want) {
-        if (!want) return -1;                                // uniform
-        const bool lead = (threadIdx.x & 31) == 0;
-        unsigned int t = 0;
-        if (lead) t = atomicAdd(&ctl[1], 1u);
-        if (lead) atomicAdd(&ctl[2], 1u);                    // alive before the parent retires
-        t = __shfl_sync(0xFFFFFFFFu, t, 0);
-        QueueWatch watch(ctl, diag);
-        for (;;) {                                           // slot free for this ticket? (never waits when ring >= tasks alive)
-            unsigned int v = 0;
-            if (lead) v = ld_relaxed_u32(&seq[t % ring]);
-            v = __shfl_sync(0xFFFFFFFFu, v, 0);
-            if (v == t || watch.expired(1, t, v)) break;
-            __nanosleep(64);
-        }
-        __threadfence();                                     // every lane: acquire side of the slot hand-over
-        pushed = t;
-        return (int64_t)(t % ring);
-    }
-    __device__ void publish(int64_t slot, bool want) const {
-        if (!want) return;
-        __threadfence();                                     // every lane's stores to the slot are visible ...
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) st_relaxed_u32(&seq[slot], pushed + 1u);   // ... before the flag
-    }
-    __device__ void consumed(int64_t slot) const {
-        __threadfence();                                     // every lane's loads from the slot are complete
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) st_relaxed_u32(&seq[slot], taken + ring);
-    }
-};
-
-struct RoundBuffers {
-    TaskBuffers buf[2];
-    unsigned int *counts;      // [3] rotating task counters
-    unsigned int *seq;         // [wave] slot sequence numbers of the continuous latency mode
-    long long wave;            // plans admitted per wave (= capacity of the task lists)
-    long long coop_below;      // rounds with fewer pending tasks run one task per warp (latency mode)
-    unsigned long long *trace; // profiling builds: (tasks, globaltimer ns) per round, 512 entries
+    __device__ int last_lane(int v) const { return __shfl_sync(0xFFFFFFFFu, v, 31); }
 };
 
 template <int MAXS, int MAXL>
-__global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? METIS_MIN_BLOCKS : (METIS_MIN_BLOCKS * 2 + 2) / 3))
-het_search_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
-                  const MetisShard sh, const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob,
-                  const int use_smem, const unsigned int scratch_off, const long long slots,
-                  const __grid_constant__ DeviceOut out, const __grid_constant__ RoundBuffers rb) {
+struct alignas(16) ChainScratch {
+    Scratch<MAXS, MAXL> w;
+    CoopMail mail;
+};
+
+#ifndef METIS_CHAIN_MIN_BLOCKS
+#define METIS_CHAIN_MIN_BLOCKS 4
+#endif
+template <int MAXS, int MAXL>
+__global__ void __launch_bounds__(256, METIS_CHAIN_MIN_BLOCKS)
+het_chain_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
+                 const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob, const int use_smem,
+                 const unsigned int scratch_off, const __grid_constant__ DeviceOut out, const SearchLists ls,
+                 const int best_slot) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
-    __shared__ double s_cost[kThreads / 32];
-    __shared__ uint32_t s_ord[kThreads / 32], s_step[kThreads / 32], s_meta[kThreads / 32];
-    cg::grid_group grid = cg::this_grid();
-
     const uint8_t *base = blob;
     if (use_smem) {
         stage_blob_tma(smem, blob, lay.total, &mbar);
         base = smem;
     }
     const Tables T = make_tables(p, lay, base);
-
     DeviceSink sink(out);
-    {
-        Scratch<MAXS, MAXL> w;
-        Scratch<MAXS, MAXL> *wsh = reinterpret_cast<Scratch<MAXS, MAXL> *>(smem + scratch_off) + (threadIdx.x >> 5);
-#ifndef METIS_NO_OPAQUE
-        asm volatile("" : "+l"(wsh));        // opaque: keep the pointer in a register instead of re-deriving it at every use
-#endif
-        const int lane = threadIdx.x & 31;
-        const long long gwarp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-        const long long nwarps = (long long)gridDim.x * (kThreads / 32);
-        unsigned int round = 0;                              // global round counter (rotates the 3 counters)
-        for (long long wave0 = 0; wave0 < slots; wave0 += rb.wave) {
-            const long long wave1 = wave0 + rb.wave < slots ? wave0 + rb.wave : slots;
-            // ---- admission: every plan of the wave -> first strategy that can be valid ----------
-            sink.phase(0);
-            {
-                DeviceWarp warp(&rb.counts[(round + 1) % 3]);
-                if (blockIdx.x == 0 && threadIdx.x == 0) { rb.counts[(round + 2) % 3] = 0; rb.counts[4 + (round + 2) % 3] = 0; rb.counts[4 + (round + 1) % 3] = 0; }
-                for (long long b0 = wave0 + gwarp * 32; b0 < wave1; b0 += nwarps * 32) {
-                    const long long i = b0 + lane;
-                    PlanDesc pd;
-                    bool has = false;
-                    // tiles are multiples of 32, so a warp's 32 plans are consecutive ordinals
-                    const long long first = ((b0 / sh.tile) * sh.world + sh.rank) * sh.tile + (b0 % sh.tile);
-                    int hint = 0;
-                    if (lane == 0 && first < sp.num_plans) hint = find_block(sp, first);
-                    hint = __shfl_sync(0xFFFFFFFFu, hint, 0);
-                    if (i < wave1) {
-                        const long long ordinal = first + lane;
-                        has = decode_plan(sp, ordinal, pd, hint);
-                    }
-                    begin_task<MAXS, MAXL>(T, w, sink, warp, rb.buf[(round + 1) & 1], has, pd);
-                }
-            }
-            grid.sync();
-            ++round;
-            // ---- order the first task list by stage count (counting sort): the throughput mode runs 32
-            //      tasks per warp in lockstep and is ~20 % faster when they share loop trip counts ----------
-            {
-                const unsigned int n0 = *(volatile unsigned int *)&rb.counts[round % 3];
-                if ((long long)n0 >= rb.coop_below) {
-                    __shared__ unsigned int s_base[METIS_MAX_STAGES + 1];
-                    unsigned int *hist = rb.counts + 16, *cursor = rb.counts + 16 + 160;
-                    const TaskBuffers &src = rb.buf[round & 1], &dst = rb.buf[(round + 1) & 1];
-                    // (both passes aggregate per warp: neighbours in the admission order mostly share a count)
-                    const long long span = (long long)gridDim.x * kThreads;
-                    const long long upto = (((long long)n0 + 31) / 32) * 32;
-                    for (long long pos = (long long)blockIdx.x * kThreads + threadIdx.x; pos < upto; pos += span) {
-                        const int k = pos < (long long)n0 ? (int)((src.geo[pos] >> 32) & 0xFF) : -1;
-                        const unsigned int peers = __match_any_sync(0xFFFFFFFFu, k);
-                        if (k >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[k], (unsigned int)__popc(peers));
-                    }
-                    grid.sync();
-                    if (threadIdx.x == 0) {
-                        unsigned int acc = 0;
-                        for (int k = METIS_MAX_STAGES - 1; k >= 0; --k) { s_base[k] = acc; acc += *(volatile unsigned int *)&hist[k]; }   // longest first
-                    }
-                    __syncthreads();
-                    for (long long pos = (long long)blockIdx.x * kThreads + threadIdx.x; pos < upto; pos += span) {
-                        const bool live = pos < (long long)n0;
-                        const uint64_t g = live ? src.geo[pos] : 0;
-                        const int k = live ? (int)((g >> 32) & 0xFF) : -1;
-                        const unsigned int peers = __match_any_sync(0xFFFFFFFFu, k);
-                        const int leader = __ffs(peers) - 1, me = threadIdx.x & 31;
-                        unsigned int at = 0;
-                        if (live && me == leader) at = atomicAdd(&cursor[k], (unsigned int)__popc(peers));
-                        at = __shfl_sync(0xFFFFFFFFu, at, leader);
-                        if (!live) continue;
-                        const long long to = (long long)s_base[k] + at + __popc(peers & ((1u << me) - 1u));
-                        dst.hdr[to] = src.hdr[pos];
-                        dst.geo[to] = g;
-                        for (int st = 0; st <= k; ++st) dst.tpc[(long long)st * dst.cap + to] = src.tpc[(long long)st * src.cap + pos];
-                    }
-                    if (blockIdx.x == 0 && threadIdx.x == 0) { rb.counts[(round + 1) % 3] = n0; rb.counts[(round + 2) % 3] = 0; rb.counts[4 + (round + 2) % 3] = 0; }
-                    grid.sync();
-                    if (blockIdx.x == 0 && threadIdx.x < METIS_MAX_STAGES) { hist[threadIdx.x] = 0; cursor[threadIdx.x] = 0; }
-                    ++round;
-                }
-            }
-            // ---- rounds: one partition attempt per pending plan --------------------------------
-            for (;;) {
-                const unsigned int n = *(volatile unsigned int *)&rb.counts[round % 3];
-#ifdef METIS_PROFILE_PHASES
-                if (blockIdx.x == 0 && threadIdx.x == 0 && round < 512) {
-                    unsigned long long t;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                    rb.trace[2 * round] = n;
-                    rb.trace[2 * round + 1] = t;
-                }
-#endif
-                if (n == 0) break;
-                DeviceWarp warp(&rb.counts[(round + 1) % 3]);
-                if (blockIdx.x == 0 && threadIdx.x == 0) { rb.counts[(round + 2) % 3] = 0; rb.counts[4 + (round + 2) % 3] = 0; }
-                const TaskBuffers &in = rb.buf[round & 1], &nxt = rb.buf[(round + 1) & 1];
-                if ((long long)n >= rb.coop_below) {
-                    // throughput mode: one task per lane, 32 tasks per warp in lockstep
-                    // (batches are handed out dynamically: the list is ordered longest first)
-                    for (;;) {
-                        unsigned int fetched = 0;
-                        if (lane == 0) fetched = atomicAdd(&rb.counts[4 + round % 3], 1u);
-                        const long long b0 = 32LL * __shfl_sync(0xFFFFFFFFu, fetched, 0);
-                        if (b0 >= (long long)n) break;
-                        const long long pos = b0 + lane;
-                        PlanDesc pd;
-                        bool has = false;
-                        if (pos < (long long)n) { decode_task(sp, list_load(&in.hdr[pos]), list_load(&in.geo[pos]), pd); has = true; }
-                        run_task<MAXS, MAXL>(T, w, Serial(), sink, warp, in, nxt, has, pos, pd);
-                    }
-                } else {
-                    // latency mode: one task per warp on shared-memory scratch, no more barriers (QueueWarp)
-                    unsigned int *ctl = rb.counts + 8;
-                    const long long room = in.cap < (long long)n + 64 ? in.cap : (long long)n + 64;
-                    const unsigned int ring = (unsigned int)room;
-                    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < room; i += (long long)gridDim.x * kThreads)
-                        rb.seq[i] = i < (long long)n ? (unsigned int)i + 1u : (unsigned int)i;
-                    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[0] = 0; ctl[1] = n; ctl[2] = n; ctl[3] = 0; }
-                    grid.sync();
-                    QueueWarp qwarp{rb.seq, ctl, out.counters + 16, ring, 0u, 0u};
-                    WarpLanes lanes_coop;
-                    sink.leader = lane == 0;
-                    for (;;) {
-                        unsigned int h = 0;
-                        if (lane == 0) h = atomicAdd(&ctl[0], 1u);
-                        h = __shfl_sync(0xFFFFFFFFu, h, 0);
-                        // every chain is finite (tp only grows, <= 3 attempts per strategy): far more pops than that = runaway
-                        if (h > 4096u * METIS_MAX_STAGES + 64u * n) {
-                            if (lane == 0 && atomicExch(&ctl[3], 1u) == 0u) { out.counters[16] = 3; out.counters[17] = h; out.counters[20] = ctl[1]; out.counters[21] = ctl[2]; }
-                            break;
-                        }
-                        int ready = 0;
-                        unsigned int nap = 128;                   // back off to 2 us: idle warps share issue slots with working ones
-                        QueueWatch watch(ctl, out.counters + 16);
-                        for (;;) {                                // warp-uniform wait: lane 0 loads, everyone decides
-                            unsigned int v = 0, alive = 0;
-                            if (lane == 0) v = ld_relaxed_u32(&rb.seq[h % ring]);
-                            if (lane == 0) alive = ld_relaxed_u32(&ctl[2]);
-                            v = __shfl_sync(0xFFFFFFFFu, v, 0);
-                            alive = __shfl_sync(0xFFFFFFFFu, alive, 0);
-                            if (v == h + 1u) { ready = 1; break; }
-                            if (alive == 0u) break;               // nothing alive: ticket h will never exist
-                            if (watch.expired(2, h, v)) break;
-                            __nanosleep(nap);
-                            if (nap < 2048) nap <<= 1;
-                        }
-                        if (!ready) break;
-                        __threadfence();                          // acquire: the slot's words were written before its flag
-                        qwarp.taken = h;
-                        const long long pos = (long long)(h % ring);
-                        PlanDesc pd;
-                        decode_task(sp, list_load(&in.hdr[pos]), list_load(&in.geo[pos]), pd);
-                        run_task<MAXS, MAXL>(T, *wsh, lanes_coop, sink, qwarp, in, in, true, pos, pd);
-                        __threadfence();                          // the successor (if any) is published before the parent retires
-                        if (lane == 0) atomicSub(&ctl[2], 1u);
-                    }
-                    sink.leader = true;
-                    grid.sync();
-                    if (blockIdx.x == 0 && threadIdx.x == 0) {
-                        rb.counts[round % 3] = 0;                 // this wave is finished
-                        if (ctl[3]) atomicMin(&out.counters[4], (unsigned long long)METIS_FATAL_SCHEDULER << 24);
-                    }
-                    grid.sync();
-                    break;
-                }
-                grid.sync();
-                ++round;
-            }
-            // counts[round % 3] is 0 here and becomes this wave's successor "previous" counter; the
-            // admission of the next wave appends to counts[(round+1) % 3], which was zeroed one round ago
-        }
+    const int lane = threadIdx.x & 31;
+    sink.leader = lane == 0;
+    ChainScratch<MAXS, MAXL> *cs = reinterpret_cast<ChainScratch<MAXS, MAXL> *>(smem + scratch_off) + (threadIdx.x >> 5);
+    const unsigned int n_adm = ls.ctl[0];
+    const bool bulk = (long long)n_adm >= ls.bulk_min;
+    const uint4 *list = bulk ? ls.a : ls.b;
+    const unsigned int n = bulk ? ls.ctl[2] : n_adm;
+    WarpCoop lanes;
+    CoopEvaluator<MAXS, MAXL, WarpCoop> ev(T, cs->w, cs->mail, lanes);
+    for (;;) {
+        unsigned int i = 0;
+        if (lane == 0) i = atomicAdd(&ls.ctl[3], 1u);
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i >= n) break;
+        const uint4 e = __ldcg(&list[i]);
+        PlanDesc pd;
+        decode_entry(sp, e, pd);
+        lanes.mark(1);
+        ev.run_chain(pd, sink, (e.y & 1u) != 0u);
+        lanes.mark(0);
     }
-
-#ifdef METIS_PROFILE_PHASES
-    if ((threadIdx.x & 31) == 0)
-        for (int k = 0; k < 5; ++k) atomicAdd(&out.counters[8 + k], (unsigned long long)sink.acc[k]);
-#endif
-    // counters: warp reduce, one atomic per warp
-    const unsigned full = 0xFFFFFFFFu;
-    const unsigned np = __reduce_add_sync(full, sink.n_part);
-    const unsigned nr = __reduce_add_sync(full, sink.n_run);
-    const unsigned nk = __reduce_add_sync(full, sink.n_key);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-        if (np) atomicAdd(&out.counters[1], (unsigned long long)np);
-        if (nr) atomicAdd(&out.counters[2], (unsigned long long)nr);
-        if (nk) atomicAdd(&out.counters[3], (unsigned long long)nk);
-    }
-    // argmin (cost, ordinal, step): __shfl_sync butterfly inside the warp, then across warps
-    double c = sink.best_cost;
-    uint32_t o = sink.best_ord, st = sink.best_step, mt = sink.best_meta;
-    for (int d = 16; d > 0; d >>= 1) {
-        const double c2 = __shfl_xor_sync(full, c, d);
-        const uint32_t o2 = __shfl_xor_sync(full, o, d), s2 = __shfl_xor_sync(full, st, d),
-                       m2 = __shfl_xor_sync(full, mt, d);
-        if (rec_less(c2, o2, s2, c, o, st)) { c = c2; o = o2; st = s2; mt = m2; }
-    }
-    if (lane == 0) { s_cost[warp] = c; s_ord[warp] = o; s_step[warp] = st; s_meta[warp] = mt; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int wi = 1; wi < kThreads / 32; ++wi)
-            if (rec_less(s_cost[wi], s_ord[wi], s_step[wi], c, o, st)) { c = s_cost[wi]; o = s_ord[wi]; st = s_step[wi]; mt = s_meta[wi]; }
-        MetisRecord r;
-        r.cost = c; r.ordinal = o; r.step = (uint16_t)st; r.num_repartition = (uint8_t)(mt >> 8); r.num_stage = (uint8_t)mt;
-        out.block_best[blockIdx.x] = r;
-    }
+    sink.leader = true;                                      // lanes 1-31 carry empty counters / bests
+    if (lane != 0) { sink.n_part = sink.n_run = sink.n_key = 0; }
+    finish_block(sink, out, best_slot + blockIdx.x);
 }
 
 __global__ void het_finalize_kernel(const MetisRecord *block_best, int nblocks, const unsigned long long *counters,
-                                    MetisSearchSummary *summary) {
+                                    const unsigned int *ctl, MetisSearchSummary *summary) {
     __shared__ double s_cost[32];
     __shared__ uint32_t s_ord[32], s_step[32], s_meta[32];
     double c = INFINITY;
@@ -703,10 +587,8 @@ __global__ void het_finalize_kernel(const MetisRecord *block_best, int nblocks, 
         else { s.fatal_ordinal = fk >> 32; s.fatal_code = (uint32_t)((fk >> 24) & 0xFF); s.fatal_aux = (uint32_t)(fk & 0xFFFFFF); }
         s.best.cost = c; s.best.ordinal = o; s.best.step = (uint16_t)st;
         s.best.num_repartition = (uint8_t)(mt >> 8); s.best.num_stage = (uint8_t)mt;
-        s.reserved[0] = counters[8]; s.reserved[1] = counters[9];        // profiling builds: phase clocks
-        s.reserved[2] = counters[10]; s.reserved[3] = counters[11]; s.reserved[4] = counters[12];
-        if (s.fatal_code == METIS_FATAL_SCHEDULER)                       // watchdog diagnostics (QueueWatch)
-            for (int k = 0; k < 6; ++k) s.reserved[k] = counters[16 + k];
+        s.reserved[0] = ctl[0];                                          // plans admitted
+        s.reserved[1] = ctl[2];                                          // plans handed to the chain kernel by the bulk round
         *summary = s;
     }
 }
@@ -823,44 +705,26 @@ static int64_t shard_plan_slots(int64_t num_plans, const MetisShard *sh) {
     return rounds * tile;
 }
 
-constexpr int64_t kFixedWs = 16384;                // summary + counters + round counters + round trace
-constexpr int64_t kMaxBlocks = 4096;               // per-block best records
-// Bytes of task-list storage before the plan space is cut into waves.  Every wave pays one latency-bound
-// tail of near-empty rounds, so the default spends HBM (32 of the B200's 180 GB) to keep the spaces of
-// BASELINE.json in one wave; METIS_TASK_MIB overrides it (the tests use it to force many waves).
-static int64_t round_budget() {
-    const char *e = getenv("METIS_TASK_MIB");
-    const long long m = e ? atoll(e) : 0;
-    return (int64_t)((m >= 1 && m <= 160 * 1024 ? m : 32 * 1024) << 20);
-}
-
-static int64_t task_slot_bytes(int max_stage) { return 16 + (int64_t)max_stage + 8 * (int64_t)max_stage; }
-
-static int64_t wave_size(int64_t slots, int max_stage) {
-    int64_t cap = round_budget() / (2 * task_slot_bytes(max_stage));
-    cap &= ~(int64_t)127;
-    if (cap < 65536) cap = 65536;
-    if (cap > slots) cap = (slots + 127) & ~(int64_t)127;
-    return cap < 128 ? 128 : cap;
-}
+constexpr int64_t kFixedWs = 16384;                // summary + counters + list control words
+constexpr int64_t kMaxBlocks = 4096;               // per-block best records (bulk round + chain kernel)
 
 int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans, int32_t max_stage) {
     if (check_problem(problem)) return METIS_E_ARG;
-    if (max_stage < 1) max_stage = 1;
-    if (max_stage > METIS_MAX_STAGES) max_stage = METIS_MAX_STAGES;
+    (void)max_stage;
+    if (num_plans < 0) return METIS_E_ARG;
     const BlobLayout lay = make_layout(*problem);
-    const int64_t cap = wave_size(num_plans, max_stage);
+    const int64_t cap = (num_plans + 127) & ~(int64_t)127;      // worst case: every plan of the shard is admitted
     return 256 + kFixedWs + (int64_t)align16(lay.total) + kMaxBlocks * (int64_t)sizeof(MetisRecord) +
-           2 * cap * task_slot_bytes(max_stage) + cap * 4 + 1024;
+           2 * cap * (int64_t)sizeof(uint4) + 1024;
 }
 
 struct Workspace {
     MetisSearchSummary *summary;
     unsigned long long *counters;
-    unsigned int *round_counts;
+    unsigned int *ctl;
     uint8_t *blob;
     MetisRecord *block_best;
-    uint8_t *tasks;
+    uint8_t *lists;
 };
 
 static Workspace carve(void *ws, const BlobLayout &lay) {
@@ -870,22 +734,120 @@ static Workspace carve(void *ws, const BlobLayout &lay) {
     Workspace w;
     w.summary = reinterpret_cast<MetisSearchSummary *>(b);
     w.counters = reinterpret_cast<unsigned long long *>(b + 1024);
-    w.round_counts = reinterpret_cast<unsigned int *>(b + 2048);
+    w.ctl = reinterpret_cast<unsigned int *>(b + 2048);
     w.blob = b + kFixedWs;
     w.block_best = reinterpret_cast<MetisRecord *>(b + kFixedWs + align16(lay.total));
-    w.tasks = reinterpret_cast<uint8_t *>(w.block_best + kMaxBlocks);
+    w.lists = reinterpret_cast<uint8_t *>(w.block_best + kMaxBlocks);
     return w;
 }
 
-static TaskBuffers carve_tasks(uint8_t *&p, int64_t cap, int max_stage) {
-    TaskBuffers t;
-    t.cap = cap;
-    t.hdr = reinterpret_cast<uint64_t *>(p);   p += cap * 8;
-    t.geo = reinterpret_cast<uint64_t *>(p);   p += cap * 8;
-    t.perf = reinterpret_cast<double *>(p);    p += cap * 8 * (int64_t)max_stage;
-    t.tpc = p;                                 p += cap * (int64_t)max_stage;
-    return t;
+static int env_int(const char *name, int lo, int hi, int dflt) {
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    char *end = nullptr;
+    const long v = strtol(e, &end, 10);
+    if (end == e || *end != '\0' || v < lo || v > hi) return dflt;     // malformed or out of range: ignored
+    return (int)v;
 }
+
+}  // extern "C"
+
+// Launch configuration of one search: which instantiation, how the tables are staged, block shapes.
+template <int MAXS, int MAXL>
+static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg, const MetisShard &sh,
+                         const BlobLayout &lay, const Workspace &ws, const DeviceOut &out, int64_t slots,
+                         cudaStream_t stream) {
+    cudaError_t e;
+    int dev = 0, sms = 0, smem_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (sms < 1 || smem_optin < 48 * 1024) return cuda_fail(cudaErrorInvalidDevice, "device attributes");
+    const int blob_max = env_int("METIS_SMEM_BLOB_MAX", 0, kSmemBlobMax, kSmemBlobMax);   // larger tables stay in global memory
+    const unsigned int blob_pad = (lay.total + 127u) & ~127u;
+
+    SearchLists ls;
+    const int64_t cap = (slots + 127) & ~(int64_t)127;
+    ls.a = reinterpret_cast<uint4 *>(ws.lists);
+    ls.b = ls.a + cap;
+    ls.ctl = ws.ctl;
+
+    // ---- chain kernel: warps per block chosen so that tables + per-warp scratch fill the SM with warps ----
+    auto chain = het_chain_kernel<MAXS, MAXL>;
+    const size_t per_warp = sizeof(ChainScratch<MAXS, MAXL>);
+    int chain_smem_tables = (int)lay.total <= blob_max;
+    int chain_threads = 0, chain_per_sm = 0;
+    size_t chain_dyn = 0;
+    unsigned int chain_off = 0;
+    const int forced = env_int("METIS_CHAIN_THREADS", 32, 256, 0);
+    for (int pass = 0; pass < 2 && chain_threads == 0; ++pass) {       // second pass: tables in global memory
+        int best_warps = 0;
+        for (int threads = 64; threads <= 256; threads *= 2) {
+            if (forced && threads != ((forced + 31) & ~31)) continue;
+            const unsigned int off = chain_smem_tables ? blob_pad : 0u;
+            const size_t dyn = off + (size_t)(threads / 32) * per_warp;
+            if (dyn > (size_t)smem_optin) continue;
+            if (dyn > 48 * 1024) {
+                e = cudaFuncSetAttribute(chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+                if (e != cudaSuccess) { cudaGetLastError(); continue; }
+            }
+            int per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain, threads, dyn);
+            if (e != cudaSuccess || per_sm < 1) { cudaGetLastError(); continue; }
+            const int warps = per_sm * threads / 32;
+            if (warps > best_warps) { best_warps = warps; chain_threads = threads; chain_per_sm = per_sm; chain_dyn = dyn; chain_off = off; }
+        }
+        if (chain_threads == 0) chain_smem_tables = 0;
+    }
+    if (chain_threads == 0) return arg_fail("chain kernel does not fit this device (shared memory)");
+    if (chain_dyn > 48 * 1024) {
+        e = cudaFuncSetAttribute(chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_dyn);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(chain)");
+    }
+    int64_t chain_grid = (int64_t)sms * chain_per_sm;
+
+    // ---- bulk round ----
+    auto first = het_first_kernel<MAXS, MAXL>;
+    int first_smem_tables = (int)lay.total <= blob_max && blob_pad <= (unsigned int)smem_optin;
+    size_t first_dyn = first_smem_tables ? blob_pad : 0;
+    if (first_dyn > 48 * 1024) {
+        e = cudaFuncSetAttribute(first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_dyn);
+        if (e != cudaSuccess) { cudaGetLastError(); first_smem_tables = 0; first_dyn = 0; }
+    }
+    int first_per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&first_per_sm, first, kThreads, first_dyn);
+    if (e != cudaSuccess || first_per_sm < 1) return cuda_fail(e, "occupancy query (bulk round)");
+    int64_t first_grid = (int64_t)sms * first_per_sm;
+    if (first_grid + chain_grid > kMaxBlocks) return arg_fail("grid exceeds the per-block best table");
+
+    // MetisShard.reserved: minimum list length for the bulk round (0 = default: 12 lists' worth of chain warps)
+    ls.bulk_min = sh.reserved > 0 ? (long long)sh.reserved : 12LL * chain_grid * (chain_threads / 32);
+
+    if (g_ev_before) cudaEventRecord(g_ev_before, stream);
+    if (slots > 0) {
+        const int64_t admit_blocks = (slots + 255) / 256;
+        if (admit_blocks > 0x7FFFFFFFLL) return arg_fail("too many plans for one launch");
+        het_admit_kernel<<<(unsigned)admit_blocks, 256, 0, stream>>>(s_arg, sh, (long long)slots, p_arg.gbs, p_arg.max_bs,
+                                                                     p_arg.max_tp, ls);
+        int64_t scatter_blocks = (slots + 255) / 256;
+        if (scatter_blocks > 8LL * sms) scatter_blocks = 8LL * sms;
+        het_scatter_kernel<<<(unsigned)scatter_blocks, 256, 0, stream>>>(ls);
+        first<<<(unsigned)first_grid, kThreads, first_dyn, stream>>>(p_arg, s_arg, lay, ws.blob, first_smem_tables, out, ls, 0);
+        chain<<<(unsigned)chain_grid, chain_threads, chain_dyn, stream>>>(p_arg, s_arg, lay, ws.blob, chain_smem_tables,
+                                                                         chain_off, out, ls, (int)first_grid);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "search kernels");
+    }
+    if (g_ev_after) cudaEventRecord(g_ev_after, stream);
+    g_ev_before = g_ev_after = nullptr;
+    het_finalize_kernel<<<1, 256, 0, stream>>>(ws.block_best, (int)(slots > 0 ? first_grid + chain_grid : 0), ws.counters,
+                                               ws.ctl, ws.summary);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "het_finalize_kernel");
+    return METIS_OK;
+}
+
+extern "C" {
 
 int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, const MetisShard *shard,
                      MetisRecord *records, int64_t capacity, uint8_t *detail, int32_t detail_stride,
@@ -898,6 +860,10 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     if (space->num_plans > 0xFFFFFFF0LL) return arg_fail("more than 2^32 plans");
     if (space->max_stage < 1 || space->max_stage > METIS_MAX_STAGES) return arg_fail("max_stage out of range (METIS_MAX_STAGES)");
     if (space->num_div < 1 || space->num_div > 256) return arg_fail("more than 256 divisors of gbs");
+    // the geometry word of a list entry keeps ns_idx in 8 bits and the byte offset of the row in 32
+    if (problem->num_node_sequences < 1 || problem->num_node_sequences > 256)
+        return arg_fail("more than 256 node sequences (geometry word)");
+    if (space->rows_bytes < 0 || space->rows_bytes > 0xFFFFFFFFLL) return arg_fail("row tables must be smaller than 4 GiB (geometry word)");
     if (detail && detail_stride < 3 * METIS_MAX_STAGES + 1) return arg_fail("detail_stride too small");
     if (capacity < 0 || (capacity > 0 && !records)) return arg_fail("records/capacity mismatch");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -908,7 +874,7 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     const Workspace ws = carve(workspace, lay);
 
     cudaError_t e;
-    e = cudaMemsetAsync(ws.counters, 0, kFixedWs - 1024, stream);   // counters, round counters, trace
+    e = cudaMemsetAsync(ws.counters, 0, kFixedWs - 1024, stream);   // counters, list control words
     if (e != cudaSuccess) return cuda_fail(e, "memset counters");
     e = cudaMemsetAsync(ws.counters + 4, 0xFF, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset fatal key");
@@ -916,59 +882,18 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "pack_tables_kernel");
 
-    static const uint32_t blob_max = []() {
-        const char *env = getenv("METIS_SMEM_BLOB_MAX");        // tuning knob: tables larger than this stay in global memory
-        return env ? (uint32_t)atoi(env) : (uint32_t)kSmemBlobMax;
-    }();
-    int use_smem = lay.total <= blob_max;
-    unsigned int scratch_off = use_smem ? ((lay.total + 127u) & ~127u) : 0u;
-    // two instantiations: the small one (S <= 64, L <= 128) halves the per-warp scratch -> more resident warps
-    const bool small = space->max_stage <= 64 && problem->num_layers <= 128;
-    size_t dyn = scratch_off + (kThreads / 32) * (small ? sizeof(Scratch<64, 128>) : sizeof(Scratch<kMaxS, kMaxL>));
-    auto kern = small ? het_search_kernel<64, 128> : het_search_kernel<kMaxS, kMaxL>;
-    if (dyn > 48 * 1024) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
     DeviceOut out;
     out.records = records; out.capacity = capacity; out.detail = detail; out.detail_stride = detail_stride;
     out.counters = ws.counters; out.block_best = ws.block_best;
-    RoundBuffers rb;
-    uint8_t *tp = ws.tasks;
-    rb.wave = wave_size(slots, space->max_stage);
-    rb.buf[0] = carve_tasks(tp, rb.wave, space->max_stage);
-    rb.buf[1] = carve_tasks(tp, rb.wave, space->max_stage);
-    rb.seq = reinterpret_cast<unsigned int *>(tp);
-    rb.counts = ws.round_counts;
-    rb.trace = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(ws.summary) + 4096);
-    // cooperative persistent grid: every block is resident, rounds are separated by grid.sync()
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, dyn);
-    if (e != cudaSuccess || per_sm < 1 || sms < 1) return cuda_fail(e, "occupancy query");
-    int64_t grid = (int64_t)sms * per_sm;
-    const int64_t useful = (slots + kThreads - 1) / kThreads;
-    if (grid > useful) grid = useful;
-    if (grid > kMaxBlocks) grid = kMaxBlocks;
-    if (slots > 0) {
-        MetisProblem p_arg = *problem;
-        MetisPlanSpace s_arg = *space;
-        MetisShard sh_arg = *shard;
-        BlobLayout lay_arg = lay;
-        const uint8_t *blob_arg = ws.blob;
-        long long slots_arg = slots;
-        rb.coop_below = (long long)(shard->reserved > 0 ? shard->reserved : 12) * grid * (kThreads / 32);
-        void *args[] = {&p_arg, &s_arg, &sh_arg, &lay_arg, &blob_arg, &use_smem, &scratch_off, &slots_arg, &out, &rb};
-        if (g_ev_before) cudaEventRecord(g_ev_before, stream);
-        e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(kThreads), args, dyn, stream);
-        if (g_ev_after) cudaEventRecord(g_ev_after, stream);
-        g_ev_before = g_ev_after = nullptr;
-        if (e != cudaSuccess) return cuda_fail(e, "het_search_kernel (cooperative launch)");
-    }
-    het_finalize_kernel<<<1, 256, 0, stream>>>(ws.block_best, (int)(slots > 0 ? grid : 0), ws.counters, ws.summary);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "het_finalize_kernel");
+    // three instantiations: per-warp scratch of the chain kernel (and per-thread scratch of the bulk round)
+    // sized for S <= 64 / L <= 128, S <= 96 / L <= 128, and the compiled limits
+    if (space->max_stage <= 64 && problem->num_layers <= 128)
+        rc = launch_search<64, 128>(*problem, *space, *shard, lay, ws, out, slots, stream);
+    else if (space->max_stage <= 96 && problem->num_layers <= 128)
+        rc = launch_search<96, 128>(*problem, *space, *shard, lay, ws, out, slots, stream);
+    else
+        rc = launch_search<kMaxS, kMaxL>(*problem, *space, *shard, lay, ws, out, slots, stream);
+    if (rc) return rc;
     e = cudaMemcpyAsync(summary, ws.summary, sizeof(MetisSearchSummary), cudaMemcpyDeviceToHost, stream);
     if (e != cudaSuccess) return cuda_fail(e, "copy summary");
     return METIS_OK;

@@ -257,6 +257,7 @@ class FlatPlanSpace:
     def as_struct(self, ptr_of: Callable[[str], int]) -> native.MetisPlanSpace:
         s = native.MetisPlanSpace()
         s.num_plans = self.num_plans
+        s.rows_bytes = int(self.rows.size)
         s.num_blocks = len(self.blocks)
         s.num_div = len(self.batches)
         s.max_stage = int(self.blocks['num_stage'].max()) if len(self.blocks) else 1

@@ -17,8 +17,7 @@ METIS_MAX_STAGES = 128
 METIS_MAX_LAYERS = 256
 DETAIL_STRIDE = 3 * METIS_MAX_STAGES + 1
 
-FATAL_NAMES = {1: 'KEY_EXEC', 2: 'KEY_MEMORY', 3: 'INDEX', 4: 'HANG', 5: 'SCRATCH', 6: 'ZERODIV', 7: 'SCHEDULER'}
-FATAL_SCHEDULER = 7
+FATAL_NAMES = {1: 'KEY_EXEC', 2: 'KEY_MEMORY', 3: 'INDEX', 4: 'HANG', 5: 'SCRATCH', 6: 'ZERODIV'}
 
 
 class MetisProblem(C.Structure):
@@ -46,7 +45,7 @@ class MetisPlanBlock(C.Structure):
 
 
 class MetisPlanSpace(C.Structure):
-    _fields_ = [('num_plans', C.c_int64), ('num_blocks', C.c_int32), ('num_div', C.c_int32),
+    _fields_ = [('num_plans', C.c_int64), ('rows_bytes', C.c_int64), ('num_blocks', C.c_int32), ('num_div', C.c_int32),
                 ('max_stage', C.c_int32), ('reserved', C.c_int32),
                 ('blocks', C.c_void_p), ('batches', C.c_void_p), ('rows', C.c_void_p)]
 
@@ -124,7 +123,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.metis_sort_workspace_bytes.argtypes = [C.c_int64]
     lib.metis_sort_records.restype = C.c_int
     lib.metis_sort_records.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-    if lib.metis_abi_version() != 1:
+    if lib.metis_abi_version() != 2:
         raise MetisNativeError('libmetis_b200.so ABI version mismatch; rebuild')
     if path == LIB_PATH:
         _lib = lib

@@ -23,55 +23,94 @@ def _require_cuda(device) -> torch.device:
     return torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
 
 
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+_PROBLEM_ARRAYS = ('key_index', 'layer_compute', 'layer_memory', 'exec_full', 'fb_sync', 'norm_lc', 'type_memory',
+                   'type_bw_first', 'type_bw_min', 'ns_run_type', 'ns_run_end')
+_ARENA_ORDER = _PROBLEM_ARRAYS + ('blocks', 'batches', 'rows')
+
+
 class DeviceProblem:
-    """A flattened problem + candidate space resident in HBM (one upload, many searches)."""
+    """A flattened problem + candidate space resident in HBM (one upload, many searches).
+
+    All tables live in ONE pinned host arena and ONE device arena at the same offsets, so an upload is a single
+    host -> device copy; ``reload`` puts another problem / space of compatible size into the same buffers."""
 
     def __init__(self, problem: flatten.FlatProblem, space: flatten.FlatPlanSpace, device=None,
-                 pinned: bool = True):
+                 pinned: bool = True, rows_capacity: int = 0):
         self.device = _require_cuda(device)
         self.lib = native.load_library()
-        self.problem = problem
-        self.space = space
-        self._host: Dict[str, torch.Tensor] = {}
-        self._dev: Dict[str, torch.Tensor] = {}
-        arrays = dict(problem.arrays)
-        arrays.update(blocks=space.blocks.view(np.uint8).reshape(-1), batches=space.batches, rows=space.rows)
-        self.h2d_bytes = 0
-        for name, arr in arrays.items():
-            flat = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
-            host = torch.from_numpy(flat.copy() if flat.size else np.zeros(16, dtype=np.uint8))
-            if pinned:
-                host = host.pin_memory()
-            self._host[name] = host
-            self.h2d_bytes += host.numel()
+        self.pinned = pinned
+        self._host = self._dev = None
+        self._off: Dict[str, Tuple[int, int]] = {}           # name -> (offset, capacity)
+        self._used: Dict[str, int] = {}
+        self._allocate(self._arrays(problem, space), rows_capacity)
+        self.reload(problem, space)
         self.upload()
 
+    @staticmethod
+    def _arrays(problem: flatten.FlatProblem, space: flatten.FlatPlanSpace) -> Dict[str, np.ndarray]:
+        arrays = {k: problem.arrays[k] for k in _PROBLEM_ARRAYS}
+        arrays.update(blocks=space.blocks.view(np.uint8).reshape(-1), batches=space.batches, rows=space.rows)
+        return {k: np.ascontiguousarray(v).view(np.uint8).reshape(-1) for k, v in arrays.items()}
+
+    def _allocate(self, flat: Dict[str, np.ndarray], rows_capacity: int) -> None:
+        off = 0
+        self._off = {}
+        for name in _ARENA_ORDER:
+            need = max(int(flat[name].size), 16)
+            cap = _align(need + need // 4 if name in ('rows', 'blocks') else need)
+            if name == 'rows':
+                cap = max(cap, _align(rows_capacity))
+            self._off[name] = (off, cap)
+            off += cap
+        host = torch.zeros(off, dtype=torch.uint8)
+        self._host = host.pin_memory() if self.pinned else host
+        with torch.cuda.device(self.device):
+            self._dev = torch.zeros(off, dtype=torch.uint8, device=self.device)
+
+    def fits(self, problem: flatten.FlatProblem, space: flatten.FlatPlanSpace) -> bool:
+        flat = self._arrays(problem, space)
+        return all(flat[n].size <= self._off[n][1] for n in _ARENA_ORDER)
+
+    def reload(self, problem: flatten.FlatProblem, space: flatten.FlatPlanSpace) -> None:
+        """Stage another problem / space (host side only; call upload()).  Tables that already live in the staging
+        arena (``build_plan_space(rows_out=staging('rows'))``) are not copied again."""
+        flat = self._arrays(problem, space)
+        if not all(flat[n].size <= self._off[n][1] for n in _ARENA_ORDER):
+            keep = {n: flat[n].copy() for n in _ARENA_ORDER}     # a view into the old arena must survive the swap
+            self._allocate(keep, 0)
+            flat = keep
+        host = self._host.numpy()
+        for name in _ARENA_ORDER:
+            src = flat[name]
+            off, _cap = self._off[name]
+            dst = host[off:off + src.size]
+            if src.size and not np.shares_memory(src, dst):
+                dst[:] = src
+            self._used[name] = int(src.size)
+        self.problem, self.space = problem, space
+        base = self._dev.data_ptr()
+        self.p_struct = problem.as_struct(lambda n: base + self._off[n][0])
+        self.s_struct = space.as_struct(lambda n: base + self._off[n][0])
+        self.h2d_bytes = self._off['rows'][0] + self._used['rows']
+
     def staging(self, name: str) -> np.ndarray:
-        """The pinned host copy of one table (numpy view): fill it in place, then upload()."""
-        return self._host[name].numpy()
+        """The pinned host region of one table (numpy view, full capacity): fill it in place, then upload()."""
+        off, cap = self._off[name]
+        return self._host.numpy()[off:off + cap]
 
     def restage_space(self, space: flatten.FlatPlanSpace) -> None:
-        """Put a freshly enumerated space of the same shape into the staging buffers; tables that
-        build_plan_space(rows_out=staging('rows')) already wrote in place are not copied again."""
-        rows, blocks = self.staging('rows'), self.staging('blocks')
-        if space.rows.size > rows.size or space.blocks.nbytes != blocks.size:
-            raise ValueError('space does not fit the staging buffers of this DeviceProblem')
-        if space.rows.size and not np.shares_memory(space.rows, rows):
-            rows[:space.rows.size] = space.rows
-        blocks[:] = space.blocks.view(np.uint8).reshape(-1)
-        self.space = space
+        """Put a freshly enumerated space into the staging arena (same problem)."""
+        self.reload(self.problem, space)
 
     def upload(self, stream: Optional[torch.cuda.Stream] = None) -> None:
-        """Host -> HBM copy of every table (part of the end-to-end timed region)."""
+        """Host -> HBM: ONE copy of the arena's used prefix (part of the end-to-end timed region)."""
+        n = self.h2d_bytes
         with torch.cuda.device(self.device), torch.cuda.stream(stream or torch.cuda.current_stream(self.device)):
-            for name, host in self._host.items():
-                dev = self._dev.get(name)
-                if dev is None:
-                    self._dev[name] = host.to(self.device, non_blocking=True)
-                else:
-                    dev.copy_(host, non_blocking=True)
-        self.p_struct = self.problem.as_struct(lambda n: self._dev[n].data_ptr())
-        self.s_struct = self.space.as_struct(lambda n: self._dev[n].data_ptr())
+            self._dev[:n].copy_(self._host[:n], non_blocking=True)
 
     def workspace_bytes(self, num_plans: int) -> int:
         n = self.lib.metis_het_workspace_bytes(C.byref(self.p_struct), num_plans, self.s_struct.max_stage)
@@ -82,13 +121,16 @@ class DeviceProblem:
 
 @dataclass
 class HetSearchOutput:
-    """Result of one shard's search (numpy, host)."""
+    """Result of one shard's search.  ``records`` (host, numpy) are in estimate_costs order; ``detail`` rows are
+    aligned with them: a numpy array when the searcher copies them to the host, else only ``detail_dev``."""
     summary: Dict[str, int]
     best: Optional[Tuple[float, int, int, int, int]]      # cost, ordinal, step, num_repartition, num_stage
     records: Optional[np.ndarray]                         # native.RECORD_DTYPE sorted by (ordinal, step)
-    detail: Optional[np.ndarray]                          # uint8 [n, DETAIL_STRIDE] aligned with records
+    detail: Optional[np.ndarray]                          # uint8 [n, stride] aligned with records
     d2h_bytes: int = 0
     rank_order: Optional[np.ndarray] = None               # uint32: records[rank_order] = sorted(..., key=cost), stable
+    detail_dev: Optional[torch.Tensor] = None             # uint8 [n, stride] on the device
+    records_dev: Optional[torch.Tensor] = None            # int64 [2n]: the sorted records on the device
 
 
 class HetSearcher:
@@ -96,29 +138,43 @@ class HetSearcher:
 
     def __init__(self, dp: DeviceProblem, rank: int = 0, world: int = 1, tile: int = 128,
                  want_records: bool = True, want_detail: bool = False, capacity: Optional[int] = None,
-                 want_ranking: bool = False):
+                 want_ranking: bool = False, detail_to_host: bool = True, detail_stride: Optional[int] = None):
         self.dp = dp
         self.want_ranking = want_ranking and want_records
         self._sort_ws = None
         self.shard = native.MetisShard(rank, world, tile, 0)
         self.want_records = want_records
         self.want_detail = want_detail and want_records
+        self.detail_to_host = detail_to_host
+        self.detail_stride = int(detail_stride or native.DETAIL_STRIDE)
+        self.capacity = 0
+        self.workspace = None
+        self.summary_host = torch.zeros(C.sizeof(native.MetisSearchSummary), dtype=torch.uint8).pin_memory()
+        self._host_buf: Dict[str, torch.Tensor] = {}
+        self.records = self.detail = None
+        self._fixed_capacity = capacity
+        self.rebind()
+
+    def rebind(self) -> None:
+        """(Re)size the buffers for the DeviceProblem's current space (after DeviceProblem.reload)."""
+        dp = self.dp
+        tile, world = self.shard.tile, self.shard.world
         rounds = -(-dp.space.num_plans // (tile * world))
         self.shard_plans = rounds * tile
-        self.capacity = 0
-        dev = dp.device
-        self.workspace = torch.empty(dp.workspace_bytes(self.shard_plans), dtype=torch.uint8, device=dev)
-        self.summary_host = torch.zeros(C.sizeof(native.MetisSearchSummary), dtype=torch.uint8).pin_memory()
-        self.records = self.detail = None
-        if want_records:
-            self._alloc(capacity if capacity is not None else self.shard_plans + 4096)
+        need = dp.workspace_bytes(self.shard_plans)
+        if self.workspace is None or self.workspace.numel() < need:
+            with torch.cuda.device(dp.device):
+                self.workspace = torch.empty(need + need // 8, dtype=torch.uint8, device=dp.device)
+        if self.want_records and self.records is None:
+            self._alloc(self._fixed_capacity if self._fixed_capacity is not None else min(self.shard_plans + 4096, 1 << 18))
 
     def _alloc(self, capacity: int) -> None:
         dev = self.dp.device
         self.capacity = capacity
-        self.records = torch.empty(capacity * 2, dtype=torch.int64, device=dev)
-        self.detail = (torch.empty((capacity, native.DETAIL_STRIDE), dtype=torch.uint8, device=dev)
-                       if self.want_detail else None)
+        with torch.cuda.device(dev):
+            self.records = torch.empty(capacity * 2, dtype=torch.int64, device=dev)
+            self.detail = (torch.empty((capacity, self.detail_stride), dtype=torch.uint8, device=dev)
+                           if self.want_detail else None)
 
     def launch(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Enqueue pack + search + finalize + summary copy on ``stream`` (asynchronous)."""
@@ -127,13 +183,25 @@ class HetSearcher:
         rc = dp.lib.metis_het_search(
             C.byref(dp.p_struct), C.byref(dp.s_struct), C.byref(self.shard),
             C.c_void_p(self.records.data_ptr() if self.records is not None else 0), C.c_int64(self.capacity),
-            C.c_void_p(self.detail.data_ptr() if self.detail is not None else 0), C.c_int32(native.DETAIL_STRIDE),
+            C.c_void_p(self.detail.data_ptr() if self.detail is not None else 0), C.c_int32(self.detail_stride),
             C.c_void_p(self.workspace.data_ptr()), C.c_int64(self.workspace.numel()),
             C.c_void_p(self.summary_host.data_ptr()), C.c_void_p(s.cuda_stream))
         native.check(rc, 'metis_het_search')
 
     def summary(self) -> native.MetisSearchSummary:
         return native.MetisSearchSummary.from_buffer_copy(self.summary_host.numpy().tobytes())
+
+    def _to_host(self, name: str, dev_tensor: torch.Tensor, stream: torch.cuda.Stream) -> np.ndarray:
+        """Device -> pinned host buffer (grow-only, reused per output) -> fresh numpy array."""
+        n = dev_tensor.numel() * dev_tensor.element_size()
+        buf = self._host_buf.get(name)
+        if buf is None or buf.numel() < n:
+            buf = self._host_buf[name] = torch.empty(max(n + n // 8, 1 << 16), dtype=torch.uint8).pin_memory()
+        view = buf[:n]
+        with torch.cuda.stream(stream):
+            view.copy_(dev_tensor.reshape(-1).view(torch.uint8), non_blocking=True)
+        stream.synchronize()
+        return view.numpy().copy()
 
     def run(self, stream: Optional[torch.cuda.Stream] = None) -> HetSearchOutput:
         """launch + synchronise + bring results to the host; grows the record buffer if needed."""
@@ -143,48 +211,50 @@ class HetSearcher:
             self.launch(s)
             s.synchronize()
             sm = self.summary()
-            if sm.fatal_code == native.FATAL_SCHEDULER:
-                raise native.MetisNativeError('device task queue watchdog fired (loop, ticket, slot value, head, tail, '
-                                              f'alive) = {[int(v) for v in sm.reserved]}')
             if self.want_records and sm.num_records > self.capacity:
-                self._alloc(int(sm.num_records) + 1024)
+                # C is not known before the first search of a space: size the buffers and search again
+                self._alloc(int(sm.num_records) + max(1024, int(sm.num_records) // 64))
                 self.launch(s)
                 s.synchronize()
                 sm = self.summary()
             out_summary = dict(num_records=int(sm.num_records), num_partition_calls=int(sm.num_partition_calls),
                                num_balancer_runs=int(sm.num_balancer_runs), num_keyerror=int(sm.num_keyerror),
                                fatal_ordinal=int(sm.fatal_ordinal), fatal_code=int(sm.fatal_code),
-                               fatal_aux=int(sm.fatal_aux))
+                               fatal_aux=int(sm.fatal_aux), num_admitted=int(sm.reserved[0]),
+                               num_chained=int(sm.reserved[1]))
             best = None
             if sm.num_records > 0:
                 b = sm.best
                 best = (float(b.cost), int(b.ordinal), int(b.step), int(b.num_repartition), int(b.num_stage))
-            records = detail = rank_order = None
+            records = detail = rank_order = detail_dev = records_dev = None
             d2h = C.sizeof(native.MetisSearchSummary)
             if self.want_records:
                 n = int(sm.num_records)
                 # estimate_costs order = (ordinal, step): rank_records_kernel, in place
                 order = self.sort_records(n, native.SORT_POSITION, s, want_perm=self.want_detail)
-                records = self.records[:2 * n].cpu().numpy().view(np.uint8).reshape(-1).view(native.RECORD_DTYPE)
+                records_dev = self.records[:2 * n]
+                records = self._to_host('records', records_dev, s).view(native.RECORD_DTYPE)
                 d2h += n * 16
                 if self.want_detail:
-                    detail = self.detail[:n].index_select(0, order.long()).cpu().numpy()
-                    d2h += n * native.DETAIL_STRIDE
+                    detail_dev = self.detail[:n].index_select(0, order.long())
+                    if self.detail_to_host:
+                        detail = self._to_host('detail', detail_dev, s).reshape(n, self.detail_stride)
+                        d2h += n * self.detail_stride
                 if self.want_ranking:
                     # sorted(estimate_costs, key=cost): stable by cost on a copy of the ordered records
                     by_cost = self.records[:2 * n].clone()
-                    rank_order = self.sort_records(n, native.SORT_BY_COST_STABLE, s, want_perm=True,
-                                                   buf=by_cost).cpu().numpy().view(np.uint32)
+                    perm = self.sort_records(n, native.SORT_BY_COST_STABLE, s, want_perm=True, buf=by_cost)
+                    rank_order = self._to_host('rank', perm, s).view(np.uint32)
                     d2h += n * 4
-        return HetSearchOutput(out_summary, best, records, detail, d2h, rank_order)
+        return HetSearchOutput(out_summary, best, records, detail, d2h, rank_order, detail_dev, records_dev)
 
     def sort_records(self, n: int, mode: int, stream: torch.cuda.Stream, want_perm: bool = False, buf=None):
-        """metis_sort_records on the first n records (device, in place); returns the permutation tensor
-        (int32 view of the uint32 indices) when asked."""
+        """metis_sort_records on the first n records (device, in place, asynchronous on ``stream``); returns the
+        permutation tensor (int32 view of the uint32 indices) when asked."""
         dp = self.dp
         need = int(dp.lib.metis_sort_workspace_bytes(C.c_int64(n)))
         if self._sort_ws is None or self._sort_ws.numel() < need:
-            self._sort_ws = torch.empty(need, dtype=torch.uint8, device=dp.device)
+            self._sort_ws = torch.empty(need + need // 8, dtype=torch.uint8, device=dp.device)
         perm = torch.empty(max(n, 1), dtype=torch.int32, device=dp.device) if want_perm else None
         buf = self.records if buf is None else buf
         rc = dp.lib.metis_sort_records(C.c_void_p(buf.data_ptr()), C.c_int64(n), C.c_int32(mode),
@@ -192,7 +262,6 @@ class HetSearcher:
                                        C.c_void_p(self._sort_ws.data_ptr()), C.c_int64(self._sort_ws.numel()),
                                        C.c_void_p(stream.cuda_stream))
         native.check(rc, 'metis_sort_records')
-        stream.synchronize()
         return perm[:n] if perm is not None else None
 
     def detail_for(self, picks: np.ndarray, stream: Optional[torch.cuda.Stream] = None) -> np.ndarray:
@@ -229,33 +298,84 @@ def raise_fatal(summary: Dict[str, int], problem: flatten.FlatProblem) -> None:
                        f'(the reference does not complete this search either)')
 
 
+class Candidates:
+    """Vectorised view of the costed candidates: every column of the reference's 7-tuples
+    (cost_het_cluster.py:44-46) as a numpy array, the tuples themselves built on demand.
+
+    ``detail`` rows hold dp codes[S], tp codes[S] (log2) and layer_partition[S+1]; they may still be on the device
+    (``detail_dev``): rows are then fetched per request (a ranked slice costs one small gather + copy), or all at
+    once the first time more than a few thousand are needed."""
+
+    _BULK = 4096
+
+    def __init__(self, records: np.ndarray, detail: Optional[np.ndarray], space: flatten.FlatPlanSpace,
+                 node_sequences: Sequence[Tuple], detail_dev: Optional[torch.Tensor] = None):
+        self.records = records
+        self.space = space
+        self.node_sequences = [tuple(s) for s in node_sequences]
+        self._detail = detail
+        self._detail_dev = detail_dev
+        n = len(records)
+        ordinal = records['ordinal'].astype(np.int64)
+        blocks = space.blocks
+        blk = (np.searchsorted(blocks['first_ordinal'], ordinal, side='right') - 1) if n else np.zeros(0, dtype=np.int64)
+        rel = ordinal - blocks['first_ordinal'][blk]
+        ndiv = len(space.batches)
+        self.row = rel // ndiv
+        self.batches = space.batches[rel % ndiv].astype(np.int64)
+        self.ns_idx = blocks['ns_idx'][blk].astype(np.int64)
+        self.num_stage = blocks['num_stage'][blk].astype(np.int64)
+        self.cost = records['cost']
+        self.num_repartition = records['num_repartition'].astype(np.int64)
+
+    def __len__(self) -> int:
+        return len(self.records)
+
+    def detail_rows(self, idx: np.ndarray) -> np.ndarray:
+        if self._detail is None:
+            if self._detail_dev is None:
+                raise ValueError('the search was run without detail rows')
+            if len(idx) > self._BULK:
+                self._detail = self._detail_dev.cpu().numpy()
+                self._detail_dev = None
+            else:
+                sel = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(self._detail_dev.device)
+                return self._detail_dev.index_select(0, sel).cpu().numpy()
+        return self._detail[idx]
+
+    def tuples(self, idx) -> List[Tuple]:
+        """The reference's 7-tuples of the candidates ``idx`` (any integer sequence)."""
+        idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+        if not len(idx):
+            return []
+        det = self.detail_rows(idx)
+        out = []
+        tables = self.space.tables
+        for k, i in enumerate(idx.tolist()):
+            S = int(self.num_stage[i])
+            d = det[k]
+            codes = tables[S][1][int(self.row[i])]
+            groups = (1 << codes.astype(np.int64)).tolist()
+            dp = (1 << d[:S].astype(np.int64)).tolist()
+            tp = (1 << d[S:2 * S].astype(np.int64)).tolist()
+            part = d[2 * S:3 * S + 1].astype(np.int64).tolist()
+            out.append((self.node_sequences[int(self.ns_idx[i])], groups, list(zip(dp, tp)), int(self.batches[i]), part,
+                        int(self.num_repartition[i]), float(self.cost[i])))
+        return out
+
+
 def materialize(records: np.ndarray, detail: np.ndarray, space: flatten.FlatPlanSpace,
                 node_sequences: Sequence[Tuple]) -> List[Tuple]:
-    """Records -> the reference's 7-tuples (cost_het_cluster.py:44-46)."""
-    out = []
-    ndiv = len(space.batches)
-    firsts = space.blocks['first_ordinal']
-    blk_of = np.searchsorted(firsts, records['ordinal'].astype(np.int64), side='right') - 1
-    for i in range(len(records)):
-        blk = space.blocks[blk_of[i]]
-        rel = int(records['ordinal'][i]) - int(blk['first_ordinal'])
-        row, div = divmod(rel, ndiv)
-        S = int(blk['num_stage'])
-        table = space.tables[S][1]
-        d = detail[i]
-        groups = [1 << int(c) for c in table[row]]
-        strategies = [(1 << int(d[s]), 1 << int(d[S + s])) for s in range(S)]
-        part = [int(x) for x in d[2 * S:3 * S + 1]]
-        out.append((node_sequences[int(blk['ns_idx'])], groups, strategies, int(space.batches[div]), part,
-                    int(records['num_repartition'][i]), float(records['cost'][i])))
-    return out
+    """Records -> the reference's 7-tuples (cost_het_cluster.py:44-46), all of them, eagerly."""
+    cand = Candidates(records, detail, space, node_sequences)
+    return cand.tuples(np.arange(len(records)))
 
 
 # ---------------------------------------------------------------------------------------------
 # multi-GPU: shard by plan ordinal, one collective at the end (SURVEY.md section 8e)
 # ---------------------------------------------------------------------------------------------
 def global_best(local_best: Optional[Tuple[float, int, int, int, int]], device) -> Optional[Tuple]:
-    """all_gather of one 16-byte (cost, ordinal/step) record per rank, then exact lexicographic min."""
+    """all_gather of one 32-byte (cost, ordinal, step, meta) record per rank, then exact lexicographic min."""
     import torch.distributed as dist
     world = dist.get_world_size()
     mine = torch.zeros(4, dtype=torch.float64, device=device)
@@ -274,17 +394,71 @@ def global_best(local_best: Optional[Tuple[float, int, int, int, int]], device) 
     return (c, int(o), int(s), int(m) // 256, int(m) % 256)
 
 
-def global_counters(summary: Dict[str, int], device) -> Dict[str, int]:
+def global_counters(summary: Dict[str, int], device, local_error: int = 0) -> Dict[str, int]:
+    """Sum of the counters over the ranks, the lowest fatal ordinal with ITS code and aux, and an error flag
+    (``any_rank_failed``) so that a rank whose search raised can make every rank raise instead of hanging."""
     import torch.distributed as dist
     keys = ['num_records', 'num_partition_calls', 'num_balancer_runs', 'num_keyerror']
-    t = torch.tensor([summary[k] for k in keys], dtype=torch.int64, device=device)
+    t = torch.tensor([summary.get(k, 0) for k in keys] + [int(local_error != 0)], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    vals = t.cpu().tolist()
     out = dict(summary)
-    out.update({k: int(v) for k, v in zip(keys, t.cpu().tolist())})
-    f = torch.tensor([min(summary['fatal_ordinal'], 2 ** 62)], dtype=torch.int64, device=device)
+    out.update({k: int(v) for k, v in zip(keys, vals)})
+    out['any_rank_failed'] = int(vals[-1])
+    none = 2 ** 40
+    fo = min(summary.get('fatal_ordinal', 2 ** 64 - 1), none)
+    packed = (fo << 8) | (summary.get('fatal_code', 0) & 0xFF)          # MIN: lowest ordinal, with its code
+    f = torch.tensor([packed], dtype=torch.int64, device=device)
     dist.all_reduce(f, op=dist.ReduceOp.MIN)
-    out['global_fatal_ordinal'] = int(f.item())
+    g = int(f.item())
+    gfo = g >> 8
+    aux = torch.tensor([summary.get('fatal_aux', 0) if (fo == gfo and fo < none) else 0], dtype=torch.int64, device=device)
+    dist.all_reduce(aux, op=dist.ReduceOp.MAX)
+    out['global_fatal_ordinal'] = gfo if gfo < none else 2 ** 62
+    out['global_fatal_code'] = g & 0xFF if gfo < none else 0
+    out['global_fatal_aux'] = int(aux.item())
     return out
+
+
+def gather_records(out: HetSearchOutput, searcher: HetSearcher) -> HetSearchOutput:
+    """Every rank receives every rank's records (+ detail rows): padded tensor all_gathers over NCCL (no pickling),
+    then the merged list is put into estimate_costs order and ranked by the device sort."""
+    import torch.distributed as dist
+    dev = searcher.dp.device
+    world = dist.get_world_size()
+    n_local = len(out.records)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    counts[dist.get_rank()] = n_local
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    counts = counts.cpu().tolist()
+    cap = max(max(counts), 1)
+    stride = searcher.detail_stride
+    with torch.cuda.device(dev):
+        rec_pad = torch.zeros(cap * 2, dtype=torch.int64, device=dev)
+        rec_pad[:2 * n_local] = out.records_dev
+        rec_g = torch.empty(world * cap * 2, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(rec_g, rec_pad)
+        rec_all = torch.cat([rec_g[2 * cap * r:2 * cap * r + 2 * counts[r]] for r in range(world)]).contiguous()
+        det_all = None
+        if out.detail_dev is not None:
+            det_pad = torch.zeros((cap, stride), dtype=torch.uint8, device=dev)
+            det_pad[:n_local] = out.detail_dev
+            det_g = torch.empty((world * cap, stride), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(det_g, det_pad)
+            det_all = torch.cat([det_g[cap * r:cap * r + counts[r]] for r in range(world)])
+        n = sum(counts)
+        s = torch.cuda.current_stream(dev)
+        perm = searcher.sort_records(n, native.SORT_POSITION, s, want_perm=True, buf=rec_all)
+        records = searcher._to_host('records_all', rec_all[:2 * n], s).view(native.RECORD_DTYPE)
+        detail_dev = det_all.index_select(0, perm.long()) if det_all is not None else None
+        by_cost = rec_all[:2 * n].clone()
+        rank = searcher.sort_records(n, native.SORT_BY_COST_STABLE, s, want_perm=True, buf=by_cost)
+        rank_order = searcher._to_host('rank_all', rank, s).view(np.uint32)
+        detail = None
+        if detail_dev is not None and searcher.detail_to_host:
+            detail = searcher._to_host('detail_all', detail_dev, s).reshape(n, stride)
+    return HetSearchOutput(out.summary, out.best, records, detail, out.d2h_bytes, rank_order, detail_dev,
+                           rec_all[:2 * n])
 
 
 # ---------------------------------------------------------------------------------------------

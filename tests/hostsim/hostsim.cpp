@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../metis_b200/csrc/metis_eval.cuh"
+#include "../../metis_b200/csrc/metis_coop.cuh"
 
 using namespace metis;
 
@@ -120,55 +121,30 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
             PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> ev(T, w);
             ev.run(pd, sink);
         }
-    } else {                              // the search kernel's round schedule with one-lane "warps"
-        struct HostWarp {
-            int64_t *count;
-            int64_t append(bool want) const { return want ? (*count)++ : -1; }
-            void consumed(int64_t) const {}
-            void publish(int64_t, bool) const {}
-        };
-        const int smax = sp->max_stage > 0 ? sp->max_stage : METIS_MAX_STAGES;
-        int64_t cap = 1;                  // count the admitted plans first so the lists are sized exactly
+    } else {
+        // the search kernel's schedule: mode 1 = first-task round (one plan per thread) + chain evaluator for the
+        // plans that continue; mode 2 = chain evaluator for every admitted plan; mode 3 = mode 2 with the
+        // iterations of every PAR section visited in reverse order (they must be independent)
+        static thread_local CoopMail mail;
+        OneLane lanes;
+        lanes.reverse = mode == 3;
         for (int64_t i = 0; i < rounds * tile; ++i) {
             const int64_t ordinal = ((i / tile) * world + sh->rank) * tile + (i % tile);
             PlanDesc pd;
             if (!decode(*sp, ordinal, pd)) continue;
-            PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> ev(T, w);
-            if (ev.begin(pd) == 1) ++cap;
-        }
-        std::vector<uint64_t> hdr[2] = {std::vector<uint64_t>(cap), std::vector<uint64_t>(cap)};
-        std::vector<uint64_t> geo[2] = {std::vector<uint64_t>(cap), std::vector<uint64_t>(cap)};
-        std::vector<uint8_t> tpc[2] = {std::vector<uint8_t>(cap * smax), std::vector<uint8_t>(cap * smax)};
-        std::vector<double> perf[2] = {std::vector<double>(cap * smax), std::vector<double>(cap * smax)};
-        TaskBuffers buf[2];
-        for (int k = 0; k < 2; ++k) buf[k] = TaskBuffers{hdr[k].data(), geo[k].data(), tpc[k].data(), perf[k].data(), cap};
-        int64_t n = 0;
-        HostWarp warp{&n};
-        for (int64_t i = 0; i < rounds * tile; ++i) {
-            const int64_t ordinal = ((i / tile) * world + sh->rank) * tile + (i % tile);
-            PlanDesc pd;
-            const bool has = decode(*sp, ordinal, pd);
-            begin_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, warp, buf[0], has, pd);
-        }
-        for (int r = 0; n > 0; ++r) {
-            const int64_t cur = n;
-            n = 0;
-            for (int64_t pos = 0; pos < cur; ++pos) {
-                PlanDesc pd;                                  // rebuilt from the geometry word like the kernel does
-                const uint64_t g = buf[r & 1].geo[pos];
-                pd.ordinal = (uint32_t)buf[r & 1].hdr[pos];
-                pd.geo = g;
-                pd.row = sp->rows + (g & 0xFFFFFFFFULL);
-                pd.S = (int)((g >> 32) & 0xFF) + 1;
-                pd.label = (int)((g >> 40) & 0xFF) + 1;
-                pd.ns = (int)((g >> 48) & 0xFF);
-                pd.batches = sp->batches[(g >> 56) & 0xFF];
-                const bool has = true;
-                if (mode == 2)
-                    run_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, SerialUniform(), sink, warp, buf[r & 1], buf[(r + 1) & 1], has, pos, pd);
-                else
-                    run_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, Serial(), sink, warp, buf[r & 1], buf[(r + 1) & 1], has, pos, pd);
+            {
+                PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> probe(T, w);     // admission
+                const int ok = probe.begin(pd);
+                if (ok < 0) { sink.fatal(pd.ordinal, METIS_FATAL_SCRATCH, 0); continue; }
+                if (ok == 0) continue;
             }
+            bool skip_first = false;
+            if (mode == 1) {
+                if (!first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, true, pd)) continue;
+                skip_first = true;
+            }
+            CoopEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS, OneLane> ev(T, w, mail, lanes);
+            ev.run_chain(pd, sink, skip_first);
         }
     }
     return 0;

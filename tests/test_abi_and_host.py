@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(native.SYMBOLS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.metis_abi_version() == 1
+    assert lib.metis_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -195,7 +195,6 @@ def test_python_constants_match_header():
     defs = {m.group(1): int(m.group(2)) for m in re.finditer(r'#define\s+(METIS_[A-Z_0-9]+)\s+(-?\d+)\b', text)}
     assert (defs['METIS_SORT_POSITION'], defs['METIS_SORT_RANKED'], defs['METIS_SORT_BY_COST_STABLE']) == \
         (native.SORT_POSITION, native.SORT_RANKED, native.SORT_BY_COST_STABLE)
-    assert defs['METIS_FATAL_SCHEDULER'] == native.FATAL_SCHEDULER
     for code, name in native.FATAL_NAMES.items():
         assert defs['METIS_FATAL_' + name] == code
     assert native.DETAIL_STRIDE == 3 * defs['METIS_MAX_STAGES'] + 1

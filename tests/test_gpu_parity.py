@@ -148,13 +148,17 @@ def test_full_size_c3_vs_golden(name, workload_dir):
     assert out.best[:3] == (float(arr['cost'][i]), int(arr['ordinal'][i]), int(arr['step'][i]))
 
 
-def test_many_waves_give_the_same_records(workload_dir, monkeypatch):
-    """Task-list storage cut to 64 MiB: the 7.7e5-plan space runs as ~12 waves (each with its own sorted first
-    list and tail rounds) and must still produce every golden candidate."""
+@pytest.mark.parametrize('env', [{'METIS_CHAIN_THREADS': '64'}, {'METIS_SMEM_BLOB_MAX': '0'},
+                                 {'METIS_CHAIN_THREADS': '128', 'METIS_SMEM_BLOB_MAX': '0'}],
+                         ids=['chain_blocks_of_2_warps', 'tables_in_global_memory', 'both'])
+def test_launch_shapes_give_the_same_records(env, workload_dir, monkeypatch):
+    """Other block shapes of the chain kernel and tables left in global memory (instead of the TMA-staged shared
+    copy) must still produce every golden candidate of the 8.3e4-plan space."""
     _gpu()
-    monkeypatch.setenv('METIS_TASK_MIB', '64')
-    meta, arr = load_golden('c3_homo64_mpl6')
-    w, root, _ = workload_dir('c3_homo64_mpl6')
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    meta, arr = load_golden('c3_homo64_mpl4')
+    w, root, _ = workload_dir('c3_homo64_mpl4')
     problem, space, out = _device_search(meta, root, 'profile', _cfg(w))
     c = meta['counters']
     s = out.summary
@@ -389,12 +393,13 @@ def test_ranked_listing_is_sorted_estimate_costs(workload_dir):
     assert (out.records['cost'].view(np.uint64) == gold_cost.view(np.uint64)).all()
 
 
-@pytest.mark.parametrize('name', ['mix32', 'het32_tight', 'c2_het16'])
-@pytest.mark.parametrize('factor', [1, 1000], ids=['throughput_first', 'latency_only'])
+@pytest.mark.parametrize('name', ['mix32', 'het32_tight', 'c2_het16', 'c3_homo64_mpl4'])
+@pytest.mark.parametrize('factor', [1, 2 ** 31 - 1], ids=['bulk_round_then_chains', 'chain_kernel_only'])
 def test_scheduler_modes_agree(name, factor, workload_dir):
-    """The two execution modes of the round scheduler (32 tasks per warp in lockstep / one task per warp fed by
-    the barrier-free queue) are forced in turn (MetisShard.reserved); both must reproduce every golden candidate,
-    including the re-partition counts of mixed-type and memory-tight plans."""
+    """The two schedules of a search are forced in turn (MetisShard.reserved): the bulk round (first partition
+    attempt of every plan, one plan per thread) followed by the chain kernel for the plans that ran out of memory,
+    and the chain kernel alone (one warp per plan from the first attempt on).  Both must reproduce every golden
+    candidate, including the re-partition counts of mixed-type and memory-tight plans."""
     _gpu()
     from metis_b200 import flatten, search
     meta, arr = load_golden(name)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Small searches for compute-sanitizer (memcheck / racecheck): forces both scheduler modes."""
+"""Small searches for compute-sanitizer (memcheck / racecheck): forces both schedules (bulk round + chains, chains only)."""
 import itertools, os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from metis_b200 import flatten, search
@@ -18,7 +18,7 @@ for name in sys.argv[1:] or ['c2_v100', 'mix32']:
     problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
     space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance, w.max_permute_len)
     dp = search.DeviceProblem(problem, space, 'cuda:0')
-    for coop in (1, 1000):
+    for coop in (1, 2 ** 31 - 1):
         s = search.HetSearcher(dp, want_records=True, want_detail=True, want_ranking=True)
         s.shard.reserved = coop
         out = s.run()

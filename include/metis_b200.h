@@ -178,7 +178,7 @@ int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans
  *                estimate_costs order); may be NULL with capacity 0 when only the best is wanted
  *   detail       [device] optional, capacity * detail_stride bytes: per record
  *                dp code[num_stage], tp code[num_stage] (log2) then layer_partition[num_stage+1]
- *                (uint8 each); detail_stride >= 3*METIS_MAX_STAGES+1, or NULL
+ *                (uint8 each); detail_stride >= 3*space->max_stage+1, or NULL
  *   workspace    [device] metis_het_workspace_bytes(problem, plans in shard, space->max_stage) bytes
  *   summary      [host]   filled asynchronously (use pinned memory)
  */

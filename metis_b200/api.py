@@ -22,7 +22,8 @@ import argparse
 import time
 from dataclasses import dataclass
 from itertools import permutations
-from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+from collections.abc import Sequence
+from typing import Dict, Iterator, List, Optional, Tuple
 
 import numpy as np
 
@@ -159,22 +160,71 @@ class InterStagePlanGenerator:
                                  gbs=self.gbs)
 
 
-class HetSearchResult(list):
-    """List of the reference's 7-tuples plus the counters of the run.  ``rank_order`` is the permutation
-    that ``sorted(result, key=lambda kv: kv[6])`` applies (cost_het_cluster.py:76), computed on the device by
-    the stable record sort."""
-    summary: Dict[str, int]
-    timings: Dict[str, float]
-    rank_order: Optional[np.ndarray] = None
+class HetSearchResult(Sequence):
+    """What cost_het_cluster() returns: the reference's list of 7-tuples
+    ``(node_sequence, device_groups, strategies, batches, layer_partition, num_repartition, cost)`` in
+    ``estimate_costs`` order (cost_het_cluster.py:44-46), as a read-only sequence whose tuples are built when they
+    are asked for (the columns live in numpy arrays; strategies / partitions stay on the GPU until needed).
+    ``len()``, indexing, slicing, iteration, ``sorted(result, key=...)`` and comparison with a list behave like the
+    reference's list.  ``ranked()`` is ``sorted(result, key=lambda kv: kv[6])`` (cost_het_cluster.py:76, a stable
+    sort) taken from the device sort's permutation instead of sorting Python objects."""
 
-    def ranked(self) -> list:
-        if self.rank_order is None:
-            return sorted(self, key=lambda kv: kv[6])
-        return [self[int(i)] for i in self.rank_order]
+    def __init__(self, candidates, rank_order: Optional[np.ndarray], summary: Dict[str, int],
+                 timings: Optional[Dict[str, float]] = None):
+        self.candidates = candidates
+        self.rank_order = rank_order
+        self.summary = summary
+        self.timings = timings or {}
+
+    def __len__(self) -> int:
+        return len(self.candidates)
+
+    def __getitem__(self, i):
+        n = len(self)
+        if isinstance(i, slice):
+            return self.candidates.tuples(np.arange(n)[i])
+        i = int(i)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError('list index out of range')
+        return self.candidates.tuples([i])[0]
+
+    def __iter__(self) -> Iterator[Tuple]:
+        n = len(self)
+        for lo in range(0, n, 8192):
+            yield from self.candidates.tuples(np.arange(lo, min(n, lo + 8192)))
+
+    def __eq__(self, other) -> bool:
+        if not isinstance(other, (list, tuple, Sequence)) or len(other) != len(self):
+            return False
+        return all(a == b for a, b in zip(self, other))
+
+    __hash__ = None
+
+    @property
+    def costs(self) -> np.ndarray:
+        """fp64 cost of every candidate, estimate_costs order (no tuples built)."""
+        return self.candidates.cost
+
+    def ranked(self, k: Optional[int] = None) -> List[Tuple]:
+        """The first ``k`` (default: all) entries of ``sorted(result, key=lambda kv: kv[6])``."""
+        order = self.rank_order
+        if order is None:
+            order = np.argsort(self.candidates.cost, kind='stable')
+        if k is not None:
+            order = order[:k]
+        return self.candidates.tuples(order)
+
+    def best(self) -> Optional[Tuple]:
+        """argmin (cost, position): the first entry of the ranked list."""
+        top = self.ranked(1)
+        return top[0] if top else None
 
 
 def het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer=None,
-                node_sequences: Optional[Sequence[Sequence]] = None, corrected: Sequence[str] = ()):
+                node_sequences: Optional[Sequence[Sequence]] = None, corrected: Sequence[str] = (),
+                rows_out: Optional[np.ndarray] = None):
     """Flatten the inputs of cost_het_cluster() (order of ``set(device_types)`` = quirk Q4)."""
     if node_sequences is None:
         node_sequences = list(permutations(set(gpu_cluster.get_device_types())))
@@ -184,18 +234,49 @@ def het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balanc
                                     norm, corrected=corrected)
     space = flatten.build_plan_space(len(node_sequences), gpu_cluster.get_total_num_devices(), args.gbs,
                                      args.num_layers, args.min_group_scale_variance, args.max_permute_len,
-                                     corrected=corrected)
+                                     corrected=corrected, rows_out=rows_out)
     return problem, space, [tuple(s) for s in node_sequences]
+
+
+# One engine per (device, rank, world): pinned staging arena, device arena, workspace, record / detail buffers.
+# cost_het_cluster() is called once per process by the reference's CLI, but a planner service calls it repeatedly;
+# the buffers grow to the largest problem seen and are reused (a pinned allocation costs more than a search).
+_ENGINES: Dict[Tuple, Tuple] = {}
+
+
+def _engine(problem, space, device, rank: int, world: int, stride: int):
+    from . import search
+    dev = search._require_cuda(device)
+    key = (dev.index if dev.index is not None else -1, rank, world)
+    eng = _ENGINES.get(key)
+    if eng is None:
+        dp = search.DeviceProblem(problem, space, dev)
+        searcher = search.HetSearcher(dp, rank, world, want_records=True, want_detail=True, want_ranking=world == 1,
+                                      detail_to_host=False, detail_stride=stride)
+        _ENGINES[key] = (dp, searcher)
+        return dp, searcher
+    dp, searcher = eng
+    dp.reload(problem, space)
+    if searcher.detail_stride != stride:
+        searcher.detail_stride = stride
+        searcher.records = searcher.detail = None
+    searcher.rebind()
+    return dp, searcher
+
+
+def release_engines() -> None:
+    """Drop the cached device / pinned buffers of cost_het_cluster()."""
+    _ENGINES.clear()
 
 
 def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, model_config: ModelConfig,
                      cost_estimator: HeteroCostEstimator, layer_load_balancer: LayerLoadBalancer,
                      node_sequences: Optional[Sequence[Sequence]] = None, device=None,
                      corrected: Sequence[str] = ()) -> HetSearchResult:
-    """cost_het_cluster.py:21-50 on the GPU.  Returns the same list of
+    """cost_het_cluster.py:21-50 on the GPU.  Returns the same sequence of
     (node_sequence, device_groups, strategies, batches, layer_partition, num_repartition, cost) in the
-    same order.  With torch.distributed initialised the plans are sharded over the ranks and every
-    rank returns the full list.
+    same order (see HetSearchResult).  With torch.distributed initialised the plans are sharded over the ranks and
+    every rank returns the full list.
 
     ``corrected`` (opt-in, default = strict parity with the reference): a subset of ('Q1', 'Q2') - 'Q1' drops the
     mislabelled one-stage block of every node sequence after the first (plan.py:144-148), 'Q2' uses the
@@ -207,39 +288,47 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
     import torch
     from . import search
     t0 = time.perf_counter()
-    problem, space, seqs = het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer,
-                                       node_sequences, corrected=tuple(corrected))
-    t1 = time.perf_counter()
     dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
-    dp = search.DeviceProblem(problem, space, device)
-    searcher = search.HetSearcher(dp, rank, world, want_records=True, want_detail=True, want_ranking=not dist)
-    out = searcher.run()
-    summary, records, detail, rank_order = out.summary, out.records, out.detail, out.rank_order
+    dev = search._require_cuda(device)
+    cached = _ENGINES.get((dev.index if dev.index is not None else -1, rank, world))
+    rows_out = cached[0].staging('rows') if cached is not None else None       # enumerate straight into pinned staging
+    problem, space, seqs = het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer,
+                                       node_sequences, corrected=tuple(corrected), rows_out=rows_out)
+    t1 = time.perf_counter()
+    stride = 3 * int(space.blocks['num_stage'].max()) + 1
+    dp, searcher = _engine(problem, space, dev, rank, world, stride)
+    dp.upload()
+    failure = None
+    out = None
+    try:
+        out = searcher.run()
+    except Exception as exc:                                  # noqa: BLE001 - re-raised below on every rank
+        if not dist:
+            raise
+        failure = exc
     if dist:
-        summary = search.global_counters(summary, dp.device)
-        summary['fatal_ordinal'] = summary['global_fatal_ordinal'] if summary['global_fatal_ordinal'] < 2 ** 62 \
-            else 2 ** 64 - 1
-        gathered: List = [None] * world
-        dist.all_gather_object(gathered, (records, detail, out.summary['fatal_code'], out.summary['fatal_aux'],
-                                          out.summary['fatal_ordinal']))
-        records = np.concatenate([g[0] for g in gathered])
-        detail = np.concatenate([g[1] for g in gathered])
-        order = np.lexsort((records['step'], records['ordinal']))
-        records, detail = records[order], detail[order]
-        rank_order = np.argsort(records['cost'], kind='stable').astype(np.uint32)   # merged shards: ranked on the host
-        for g in gathered:
-            if g[4] == summary['fatal_ordinal']:
-                summary['fatal_code'], summary['fatal_aux'] = g[2], g[3]
+        # a rank whose search raised must not leave the others waiting in a collective
+        summary = search.global_counters(out.summary if out is not None else {}, dp.device, int(failure is not None))
+        if summary['any_rank_failed']:
+            raise failure if failure is not None else native.MetisNativeError('the search failed on another rank')
+        if summary['global_fatal_ordinal'] < 2 ** 62:
+            summary.update(fatal_ordinal=summary['global_fatal_ordinal'], fatal_code=summary['global_fatal_code'],
+                           fatal_aux=summary['global_fatal_aux'])
+        else:
+            summary['fatal_ordinal'] = 2 ** 64 - 1
+            out = search.gather_records(out, searcher)
+    else:
+        summary = out.summary
     if summary['fatal_ordinal'] != 2 ** 64 - 1:
         # the reference dies at that plan: nothing is returned (quirk Q8)
         search.raise_fatal(summary, problem)
     t2 = time.perf_counter()
-    result = HetSearchResult(search.materialize(records, detail, space, seqs))
-    result.summary = dict(summary, num_plans=space.num_plans, corrected=tuple(sorted(corrected)))
-    result.rank_order = rank_order
+    cand = search.Candidates(out.records, out.detail, space, seqs, detail_dev=out.detail_dev)
+    result = HetSearchResult(cand, out.rank_order,
+                             dict(summary, num_plans=space.num_plans, corrected=tuple(sorted(corrected))))
     result.timings = {'flatten_enumerate_s': t1 - t0, 'gpu_search_s': t2 - t1,
-                      'materialize_s': time.perf_counter() - t2}
+                      'decode_columns_s': time.perf_counter() - t2}
     return result
 
 

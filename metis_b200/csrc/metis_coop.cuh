@@ -28,6 +28,10 @@
 
 #include "metis_eval.cuh"
 
+#ifdef METIS_HOST_STATS
+extern "C" void metis_host_stats(int slot, long add);
+#endif
+
 namespace metis {
 
 // Scalars a SEQ section hands to the following sections (per-warp scratch next to Scratch<>).
@@ -38,6 +42,10 @@ struct CoopMail {
     int pad;
     double val;   // generic fp64 result (totals)
     double val2;
+    int k;        // end of the forward pass: first sub-layer not offered to a forward stage
+    int s_top;    // last stage the forward pass touched
+    int top_skip; // 1 = that stage closed on a non-fitting sub-layer
+    int pad2;
 };
 
 // Host / test policy: one lane.  `reverse` visits PAR iterations last-to-first.
@@ -48,9 +56,19 @@ struct OneLane {
     MB_HD bool leader() const { return true; }
     MB_HD void sync() const {}
     MB_HD bool any(bool p) const { return p; }
+    MB_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+    MB_HD unsigned match_any(int) const { return 1u; }
+    // first i in [0, n] with P[i] >= t (P ascending), n + 1 if none
+    MB_HD int first_ge(const double *P, int n, double t) const {
+        int lo = 0, hi = n + 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (P[mid] >= t) hi = mid; else lo = mid + 1; }
+        return lo;
+    }
+    MB_HD int bcast_last(int v) const { return v; }
     MB_HD void argmax_first(double &, int &) const {}
     MB_HD void argmin_first(double &, int &) const {}
     MB_HD void imax_first(int &, int &) const {}
+    MB_HD void imin_first(int &, int &) const {}
     MB_HD double max_all(double v) const { return v; }
     MB_HD int incl_scan(int v) const { return v; }
     MB_HD int last_lane(int v) const { return v; }
@@ -67,50 +85,55 @@ MB_HD int par_index(const OneLane &x, int i, int n) { return x.reverse ? n - 1 -
          var##_i += (x).width(), var = par_index((x), var##_i, (n)))
 
 // ---------------------------------------------------------------------------------------------------------
-// Forward fill, backward fill and leftovers of LayerComputeBalancer.run (model/load_balancer.py:216-287) for
-// the leader lane: the compare-and-subtract chain in fp64.  Same state encoding as balance_run in metis_eval.cuh
-// (fe[] interval ends with kBroke / kTaken, lstk[], blk[], the per-layer packed stage map subw[]).
-// in : w.capa[0..S) = stage capacities, w.got[] = 0;  out: w.capa, w.fe, w.lstk, w.got, w.blk, w.subw, *m_out
+// Sequential pieces of LayerComputeBalancer.run (model/load_balancer.py:216-287) for the leader lane: the
+// compare-and-subtract chains in fp64.  Same state encoding as balance_run in metis_eval.cuh (fe[] interval ends
+// with kBroke / kTaken, lstk[], the per-layer packed stage map subw[]).
 // ---------------------------------------------------------------------------------------------------------
+struct FillState {
+    int k;          // first sub-layer not offered to a forward stage
+    int s_top;      // last stage the forward pass touched (-1: none)
+    bool top_skip;  // that stage closed on a non-fitting sub-layer
+};
+
+// forward pass (:216-231): stage s takes sub-layers while its capacity exceeds the next demand (strict compare,
+// every subtraction rounded like the reference's) and closes on the first one that does not fit, which is skipped.
+// Only the interval ends fe[] and the residual capacities are written; which stage owns a sub-layer follows from
+// fe[] (CoopEvaluator::vote_coop), so the loop body is a compare and a subtract.
 template <int MAXS, int MAXL>
-MB_HD int seq_fill(const Tables &T, int S, Scratch<MAXS, MAXL> &w, int &m_out) {
+MB_HD FillState seq_forward(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
     const int L = T.p.num_layers;
     const double *dlay = T.dlay;
     const int N = kH * L;
     const int lim = (N - 1 - kH) > 0 ? (N - 1 - kH) : 0;   // :218
     const int last = S - 1;
-
-    // ---- forward pass (:216-231) ----
-    int k = 0, sTop = -1;
-    bool topSkip = false;
+    FillState st{0, -1, false};
     if (S > 1) {
         int s = 0, j = 0;
         double c = w.capa[0];
-        uint8_t *subb = reinterpret_cast<uint8_t *>(w.subw);
+        bool done = false;
 #pragma unroll 1
-        for (int r = 0; r + 1 < L; ++r) {
+        for (int r = 0; r + 1 < L && !done; ++r) {
             const double d = dlay[r];
             const int nsub = (r == L - 2) ? kH - 1 : kH;     // the last 8 sub-layers are reserved
-            if (s >= last) break;
             if (nsub == kH && c > 9.0 * d) {
                 // whole layer fits with room to spare: all seven compare-and-subtract steps take the "fits"
                 // branch (c - 7d > d even after rounding), so only the subtractions remain
                 c -= d; c -= d; c -= d; c -= d; c -= d; c -= d; c -= d;
-                w.subw[r] = (uint64_t)s * kOnes;
                 j += kH;
                 continue;
             }
-            int q = 0;
-#pragma unroll 1
-            while (q < nsub && s < last) {
-#pragma unroll 1
-                while (q < nsub && c > d) { c -= d; subb[r * 8 + q] = (uint8_t)s; ++q; }
-                if (q < nsub) {                                      // sub-layer q does not fit: skipped
-                    w.capa[s] = c;
-                    w.fe[s] = (uint16_t)((j + q) | kBroke);
-                    ++s;
-                    c = w.capa[s];
-                    ++q;
+#pragma unroll
+            for (int q = 0; q < kH; ++q) {
+                if (q < nsub && !done) {
+                    if (c > d) {
+                        c -= d;
+                    } else {                                     // sub-layer j + q does not fit: skipped, stage closes
+                        w.capa[s] = c;
+                        w.fe[s] = (uint16_t)((j + q) | kBroke);
+                        ++s;
+                        if (s >= last) done = true;
+                        else c = w.capa[s];
+                    }
                 }
             }
             j += nsub;
@@ -120,122 +143,133 @@ MB_HD int seq_fill(const Tables &T, int S, Scratch<MAXS, MAXL> &w, int &m_out) {
             w.fe[s] = (uint16_t)lim;
 #pragma unroll 1
             for (int t = s + 1; t < last; ++t) w.fe[t] = (uint16_t)lim;
-            k = lim;
-            sTop = s;
+            st.k = lim;
+            st.s_top = s;
         } else {
-            k = (w.fe[last - 1] & kPos) + 1;
-            sTop = last - 1;
-            topSkip = true;
+            st.k = (w.fe[last - 1] & kPos) + 1;
+            st.s_top = last - 1;
+            st.top_skip = true;
         }
     }
+    return st;
+}
 
-    // ---- backward pass (:233-249): last stage takes a contiguous tail [m, N) ----
-    int m;
-    {
-        double c = w.capa[last];
-        const double dl = dlay[L - 1];
+// backward pass (:233-249): the last stage takes a contiguous tail [m, N); returns m
+template <int MAXS, int MAXL>
+MB_HD int seq_backward(const Tables &T, int S, Scratch<MAXS, MAXL> &w, int k) {
+    const int L = T.p.num_layers;
+    const double *dlay = T.dlay;
+    const int N = kH * L;
+    const int last = S - 1;
+    double c = w.capa[last];
+    int r = L - 1;
+    double d = dlay[r];
 #pragma unroll 1
-        for (int i = 0; i < kH; ++i) c -= dl;               // unconditional while len < hallucination (:237-241)
-        m = N - kH;
+    for (int i = 0; i < kH; ++i) c -= d;                    // unconditional while len < hallucination (:237-241)
+    int m = N - kH;
+    // above k every sub-layer is unassigned: only the capacity test of :246 decides (layer by layer, top down)
+    bool full = false;
+#pragma unroll 1
+    while (m > k && !full) {
+        --r;
+        d = dlay[r];
+        const int floor_j = kH * r > k ? kH * r : k;        // lowest sub-layer of this layer that is still >= k
+#pragma unroll 1
+        while (m > floor_j) {
+            if (!(c > d)) { full = true; break; }            // :246 fails; every later id fails :243
+            c -= d;
+            --m;
+        }
+    }
+    if (!full) {                                            // reached k: below it only skipped sub-layers are unassigned
         int sp = S - 2;
 #pragma unroll 1
         while (m > 0) {
             const int j = m - 1;
-            bool un = (j >= k);
-            if (!un) {                                       // below k only skipped sub-layers are unassigned
 #pragma unroll 1
-                while (sp >= 0 && (!(w.fe[sp] & kBroke) || (int)(w.fe[sp] & kPos) > j)) --sp;
-                un = (sp >= 0 && (int)(w.fe[sp] & kPos) == j);
-            }
-            if (!un) break;                                  // (layer_id + 1) != min(...) from here on (:243)
-            const double d = dlay[j / kH];
-            if (!(c > d)) break;                             // :246 fails; every later id fails :243
-            c -= d;
+            while (sp >= 0 && (!(w.fe[sp] & kBroke) || (int)(w.fe[sp] & kPos) > j)) --sp;
+            if (!(sp >= 0 && (int)(w.fe[sp] & kPos) == j)) break;   // (layer_id + 1) != min(...) from here on (:243)
+            const double dj = dlay[j / kH];
+            if (!(c > dj)) break;
+            c -= dj;
             m = j;
-            if (j < k) w.fe[sp] |= kTaken;
+            w.fe[sp] |= kTaken;
         }
-        w.capa[last] = c;
     }
+    w.capa[last] = c;
+    return m;
+}
 
-    // ---- leftovers (:251-287), ascending: first the skipped sub-layers, then the middle block ----
-    {
-        int start = 0;                                        // first sub-layer of stage s's forward interval
+// leftovers (:251-287), first part: the skipped sub-layers, ascending - general sequential form (any geometry:
+// empty stages, stages that already hold a leftover).  get_proper_stage: lo = stage of the largest assigned id
+// below j whose stage holds nothing above j, hi = stage of the smallest assigned id above j whose stage holds
+// nothing below j.
+template <int MAXS, int MAXL>
+MB_HD int seq_skipped(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
+    const double *dlay = T.dlay;
+    const int last = S - 1;
+    int start = 0;                                        // first sub-layer of stage s's forward interval
 #pragma unroll 1
-        for (int s = 0; s < last; ++s) {
-            const uint16_t e = w.fe[s];
-            const int pos = e & kPos;
-            const int next_start = pos + ((e & kBroke) ? 1 : 0);
-            if ((e & (kBroke | kTaken)) != kBroke) { start = next_start; continue; }
-            const int j = pos;
-            int lo = 0;
-            if (pos > start) {
-                lo = s;                                       // common case: stage s itself ends right below j
-            } else {
+    for (int s = 0; s < last; ++s) {
+        const uint16_t e = w.fe[s];
+        const int pos = e & kPos;
+        const int next_start = pos + ((e & kBroke) ? 1 : 0);
+        if ((e & (kBroke | kTaken)) != kBroke) { start = next_start; continue; }
+        const int j = pos;
+        int lo = 0;
+        if (pos > start) {
+            lo = s;                                       // common case: stage s itself ends right below j
+        } else {
 #pragma unroll 1
-                for (int u = s;; --u) {
-                    if (u < s) {                              // skipped sub-layer of stage u (already placed)
-                        const int t = w.lstk[u];
-                        const bool above = (t == last) || (fwd_nonempty(w, t) && fwd_start(w, t) > j);
-                        if (!above) { lo = t; break; }
-                    }
-                    if (fwd_nonempty(w, u)) { lo = u; break; }
-                    if (u == 0) break;
+            for (int u = s;; --u) {
+                if (u < s) {                              // skipped sub-layer of stage u (already placed)
+                    const int t = w.lstk[u];
+                    const bool above = (t == last) || (fwd_nonempty(w, t) && fwd_start(w, t) > j);
+                    if (!above) { lo = t; break; }
                 }
+                if (fwd_nonempty(w, u)) { lo = u; break; }
+                if (u == 0) break;
             }
-            int hi = s + 1;
-            if (hi < last && !((int)(w.fe[hi] & kPos) > next_start && !w.got[hi])) {
-                ++hi;                                         // stage s+1 is empty or already holds a leftover
-#pragma unroll 1
-                while (hi < last && (!fwd_nonempty(w, hi) || w.got[hi])) ++hi;
-            }
-            if (lo > hi) return METIS_FATAL_SCRATCH;
-            int pick = lo;
-            double best = w.capa[lo];
-#pragma unroll 1
-            for (int t = lo + 1; t <= hi; ++t)
-                if (w.capa[t] > best) { best = w.capa[t]; pick = t; }
-            w.capa[pick] -= dlay[j / kH];
-            w.lstk[s] = (uint8_t)pick;
-            w.got[pick] = 1;
-            sub_store(w.subw, j, pick);
-            start = next_start;
         }
-    }
-    if (m - k > Scratch<MAXS, MAXL>::kBlock) return METIS_FATAL_SCRATCH;
-    {
-        int below = -1;                                       // stage of the nearest block item not on `last`
+        int hi = s + 1;
+        if (hi < last && !((int)(w.fe[hi] & kPos) > next_start && !w.got[hi])) {
+            ++hi;                                         // stage s+1 is empty or already holds a leftover
 #pragma unroll 1
-        for (int t = 0; t < m - k; ++t) {
-            const int j = k + t;
-            int lo = 0;
-            if (below >= 0) lo = below;
-            else if (sTop >= 0) {
-#pragma unroll 1
-                for (int u = sTop;; --u) {
-                    if (u < sTop || topSkip) {
-                        const uint16_t eu = w.fe[u];
-                        if ((eu & (kBroke | kTaken)) == kBroke) {
-                            const int t2 = w.lstk[u];
-                            if (t2 != last) { lo = t2; break; }   // forward intervals all lie below the block
-                        }
-                    }
-                    if (fwd_nonempty(w, u)) { lo = u; break; }
-                    if (u == 0) break;
-                }
-            }
-            int pick = lo;
-            double best = w.capa[lo];
-#pragma unroll 1
-            for (int t2 = lo + 1; t2 <= last; ++t2)
-                if (w.capa[t2] > best) { best = w.capa[t2]; pick = t2; }
-            w.capa[pick] -= dlay[j / kH];
-            w.blk[t] = (uint8_t)pick;
-            if (pick != last) below = pick;
-            sub_store(w.subw, j, pick);
+            while (hi < last && (!fwd_nonempty(w, hi) || w.got[hi])) ++hi;
         }
+        if (lo > hi) return METIS_FATAL_SCRATCH;
+        int pick = lo;
+        double best = w.capa[lo];
+#pragma unroll 1
+        for (int t = lo + 1; t <= hi; ++t)
+            if (w.capa[t] > best) { best = w.capa[t]; pick = t; }
+        w.capa[pick] -= dlay[j / kH];
+        w.lstk[s] = (uint8_t)pick;
+        w.got[pick] = 1;
+        start = next_start;
     }
-    m_out = m;
     return METIS_FATAL_NONE;
+}
+
+// lower end of get_proper_stage's range for the first sub-layer of the middle block [k, m) (:252-275): the stage
+// holding the largest assigned id below k (forward intervals and placed skipped sub-layers all lie below it)
+template <int MAXS, int MAXL>
+MB_HD int middle_lo(int S, const Scratch<MAXS, MAXL> &w, const FillState &st) {
+    const int last = S - 1;
+    if (st.s_top < 0) return 0;
+#pragma unroll 1
+    for (int u = st.s_top;; --u) {
+        if (u < st.s_top || st.top_skip) {
+            const uint16_t eu = w.fe[u];
+            if ((eu & (kBroke | kTaken)) == kBroke) {
+                const int t2 = w.lstk[u];
+                if (t2 != last) return t2;
+            }
+        }
+        if (fwd_nonempty(w, u)) return u;
+        if (u == 0) break;
+    }
+    return 0;
 }
 
 // CPython sum() of w-resident values v[0..n) in index order, for the leader lane (rolled: code size)
@@ -385,6 +419,199 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
         return 0;
     }
 
+    // Forward pass of LayerComputeBalancer (model/load_balancer.py:216-231), predicted and then verified exactly.
+    //
+    // Sequentially, stage s can only start once stage s-1 has closed, and closing takes one compare-and-subtract per
+    // sub-layer.  Here the interval ends are first PREDICTED from the running sum psub of the demands: a stage with
+    // capacity c that starts at a ends at the first b with psub[b + 1] >= c + psub[a] (one warp-wide search per
+    // stage; what the real-number version of the pass would do).  Then every lane replays its stages' fills with
+    // the reference's own operations - the strict compare and the rounded subtraction for every sub-layer - from the
+    // predicted starts, which yields the exact residual capacities and VERIFIES the prediction: all compares up to
+    // the predicted end must succeed and the one at the end must fail.  If every stage verifies, stage 0 started at
+    // 0 and each next start follows from an exactly replayed fill, so the state equals the sequential pass
+    // (induction over the stages).  If any stage fails (a compare decided by the last bits), the leader runs the
+    // sequential pass.  returns true when the forward state (w.fe, w.capa, mail.k / s_top / top_skip) is final.
+    MB_HD bool forward_coop() {
+        const int S = pd.S, last = S - 1;
+        const int L = T.p.num_layers;
+        if (S < 4 || T.p.norm_len < L) return false;          // nothing to overlap: sequential pass
+        const int N = kH * L;
+        const int lim = (N - 1 - kH) > 0 ? (N - 1 - kH) : 0;  // :218
+        const double *dlay = T.dlay;
+        const double *P = T.psub;
+        // ---- prediction: uniform walk over the stages ----
+        int a = 0, first_open = -1;
+#pragma unroll 1
+        for (int s = 0; s < last; ++s) {
+            int b = lim;
+            bool closed = false;
+            if (a < lim) {
+                const int i = x.first_ge(P, N, w.perf[s] + P[a]);
+                b = i - 1 > a ? i - 1 : a;
+                if (b >= lim) b = lim; else closed = true;
+            }
+            if (x.leader()) { w.first[s] = (uint16_t)a; w.fe[s] = (uint16_t)(b | (closed ? kBroke : 0)); }
+            if (!closed && first_open < 0) first_open = s;
+            a = closed ? b + 1 : lim;
+        }
+        x.sync();
+        // ---- exact replay of every stage from its predicted start ----
+        bool bad = false;
+        METIS_PAR(x, s, last) {
+            const int st = w.first[s];
+            const uint16_t e = w.fe[s];
+            const int b = e & kPos;
+            double c = w.perf[s];
+            int j = st, r = st / kH, q = st - r * kH;
+#pragma unroll 1
+            while (j < b) {
+                const double d = dlay[r];
+                if (q == 0 && j + kH <= b && c > 9.0 * d) {   // whole layer fits with room to spare (see seq_forward)
+                    c -= d; c -= d; c -= d; c -= d; c -= d; c -= d; c -= d;
+                    j += kH; ++r;
+                    continue;
+                }
+                if (!(c > d)) { bad = true; break; }          // the reference would have closed the stage here
+                c -= d;
+                ++j;
+                if (++q == kH) { q = 0; ++r; }
+            }
+            if ((e & kBroke) && !bad && c > dlay[b / kH]) bad = true;   // the reference would have gone on
+            w.capa[s] = c;
+        }
+#ifdef METIS_HOST_STATS
+        metis_host_stats(2, 1);
+        if (bad) metis_host_stats(15, 1);
+#endif
+        if (x.any(bad)) {
+            x.sync();
+            METIS_PAR(x, s, last) w.capa[s] = w.perf[s];      // restore the input of the sequential pass
+            return false;
+        }
+        if (x.leader()) {
+            if (first_open < 0) { mail.k = a; mail.s_top = last - 1; mail.top_skip = 1; }   // a = end of stage last-1, + 1
+            else { mail.k = lim; mail.s_top = first_open; mail.top_skip = 0; }
+        }
+        return true;
+    }
+
+    // Forward pass, backward pass and leftovers of LayerComputeBalancer (model/load_balancer.py:216-287).
+    //   forward     leader: compare-and-subtract chain over the sub-layers (seq_forward)
+    //   backward    leader: the last stage's own compare-and-subtract chain
+    //   skipped     one sub-layer per closed stage, ascending.  In the regular geometry (every stage up to the last
+    //               touched one holds at least one sub-layer) get_proper_stage offers stage s's skipped sub-layer to
+    //               {s, s+1} and the decision for s depends on the one for s-1 only through capa[s]: pick_s = s+1 iff
+    //               capa[s+1] > capa[s] - [pick_{s-1} == s] * d_{s-1}.  Both outcomes are evaluated per stage; since
+    //               subtracting can only favour s+1, a stage is "always s", "always s+1" or "copies its input", and
+    //               the chain is resolved with two ballots (nearest constant stage below).  Any other geometry:
+    //               leader, general sequential form.
+    //   middle      the block [k, m) between forward and backward fills, ascending: arg-max over [lo, last] by the
+    //               whole warp per sub-layer.
+    // Writes w.capa, w.fe, w.lstk, w.blk, mail.k / m.  returns METIS_FATAL_* (0 = ok)
+    MB_HD int fill_coop() {
+        const int S = pd.S, last = S - 1;
+        const double *dlay = T.dlay;
+        x.sync();
+        const bool fwd = forward_coop();
+        x.sync();
+        if (x.leader()) {
+            if (!fwd) {
+                const FillState st = seq_forward<MAXS, MAXL>(T, S, w);
+                mail.k = st.k; mail.s_top = st.s_top; mail.top_skip = st.top_skip ? 1 : 0;
+            }
+            x.mark(11);
+            mail.m = seq_backward<MAXS, MAXL>(T, S, w, mail.k);
+            mail.err = 0;
+        }
+        x.sync();
+        x.mark(12);
+        const FillState st{mail.k, mail.s_top, mail.top_skip != 0};
+        const int m = mail.m;
+        // ---- skipped sub-layers ----
+        // stages 0 .. reach hold the forward intervals; regular = none of them is empty
+        const int reach = st.s_top;                           // -1 when S == 1
+        bool irregular = false;
+        METIS_PAR(x, s, reach + 1) {
+            const int start = s == 0 ? 0 : (int)(w.fe[s - 1] & kPos) + ((w.fe[s - 1] & kBroke) ? 1 : 0);
+            if (!((int)(w.fe[s] & kPos) > start)) irregular = true;
+        }
+        irregular = x.any(irregular);
+        if (irregular) {
+            if (x.leader()) mail.err = seq_skipped<MAXS, MAXL>(T, S, w);
+            x.sync();
+            if (mail.err) return mail.err;
+        } else if (reach >= 0) {
+            int carry = 0;                                    // did the previous stage's sub-layer go to this stage?
+#pragma unroll 1
+            for (int base = 0; base <= last; base += x.width()) {
+                const int s = base + x.lane();
+                bool has = false, o0 = false, o1 = false, has_prev = false;
+                double c = 0.0, d = 0.0, d_prev = 0.0;
+                int pos = 0;
+                if (s <= last) {
+                    c = w.capa[s];
+                    if (s > 0 && s - 1 < last) {
+                        const uint16_t ep = w.fe[s - 1];
+                        has_prev = (ep & (kBroke | kTaken)) == kBroke;
+                        if (has_prev) d_prev = dlay[(ep & kPos) / kH];
+                    }
+                    if (s < last) {
+                        const uint16_t e = w.fe[s];
+                        has = (e & (kBroke | kTaken)) == kBroke;
+                        if (has) {
+                            pos = e & kPos;
+                            d = dlay[pos / kH];
+                            const double cn = w.capa[s + 1];
+                            o0 = cn > c;
+                            o1 = has_prev ? cn > (c - d_prev) : o0;
+                        }
+                    }
+                }
+                // pick_s = s+1 ?  constant stages (o0 == o1) decide themselves, the others copy the stage below
+                const unsigned kmask = x.ballot(o0 == o1), vmask = x.ballot(o0);
+                const unsigned below_me = x.lane() ? (0xFFFFFFFFu >> (32 - x.lane())) : 0u;     // lanes < mine
+                const unsigned kin = kmask & below_me;
+                const bool in = kin ? ((vmask >> (31 - clz32(kin))) & 1u) != 0u : carry != 0;
+                const bool up = (o0 == o1) ? o0 : in;          // this stage's sub-layer goes to s + 1
+                carry = x.bcast_last(up ? 1 : 0);
+                x.sync();                                     // every lane has read its neighbours' capacities
+                if (s <= last) {
+                    double cc = c;
+                    const bool got_prev = has_prev && in;     // (in is false when the stage below has no sub-layer to give)
+                    if (got_prev) cc -= d_prev;
+                    if (has && !up) cc -= d;
+                    if (got_prev || (has && !up)) w.capa[s] = cc;
+                    if (has) w.lstk[s] = (uint8_t)(up ? s + 1 : s);
+                }
+            }
+            x.sync();
+        }
+        // ---- middle block ----
+        if (m - st.k > Scratch<MAXS, MAXL>::kBlock) return METIS_FATAL_SCRATCH;
+        if (m > st.k) {
+            if (x.leader()) mail.flag = middle_lo<MAXS, MAXL>(S, w, st);
+            x.sync();
+            int lo = mail.flag;
+#pragma unroll 1
+            for (int j = st.k; j < m; ++j) {
+                int pick = 0x7FFFFFFF;
+                double best = -INFINITY;
+#pragma unroll 1
+                for (int t = lo + x.lane(); t <= last; t += x.width())
+                    if (w.capa[t] > best || (w.capa[t] == best && t < pick)) { best = w.capa[t]; pick = t; }
+                x.argmax_first(best, pick);
+                x.sync();                                     // every lane has read the capacities
+                if (x.leader()) {
+                    w.capa[pick] = best - dlay[j / kH];
+                    w.blk[j - st.k] = (uint8_t)pick;
+                }
+                x.sync();
+                if (pick != last) lo = pick;                  // the nearest block item below that is not on `last`
+            }
+        }
+        return METIS_FATAL_NONE;
+    }
+
     // LayerComputeBalancer.run (model/load_balancer.py:197-207): w.perf -> w.part, w.cnt
     MB_HD int balance_coop() {
         const int S = pd.S;
@@ -396,58 +623,83 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
         METIS_PAR(x, s, S) { w.capa[s] = w.perf[s]; w.got[s] = 0; }
         x.sync();
         x.mark(10);
-        if (x.leader()) {                                    // SEQ: the compare-and-subtract chain
-            int m = 0;
-            mail.err = seq_fill<MAXS, MAXL>(T, S, w, m);
-            mail.m = m;
-        }
-        x.sync();
-        if (mail.err) return mail.err;
+        const int rc_tail = fill_coop();
+        if (rc_tail) return rc_tail;
         const int m = mail.m;
         x.mark(13);
         // ---- majority vote back to real layers (:290-308), one layer per lane ----
-        const int nw = (L + 7) / 8;
-        METIS_PAR(x, r, nw * 8) {
-            int own = kDropped;                              // padding of the last owner word
-            if (r < L) {
-                const int nlow = m - kH * r;                 // sub-layers of r below the backward tail
-                if (nlow <= 0) {
-                    own = last;
-                } else {
-                    uint64_t v = w.subw[r];
-                    if (nlow < kH) {
-                        const uint64_t mask = (1ULL << (8 * nlow)) - 1ULL;
-                        v = (v & mask) | (((uint64_t)last * kOnes) & ~mask);
+        // Stage of sub-layer j, from the interval ends: j >= m -> last stage (backward tail); k <= j < m -> where
+        // the middle block put it (blk); below k the forward slot t = #{u : start of stage u+1 <= j}, and if j is
+        // that slot's skipped sub-layer: last stage when the backward pass took it, else where it was placed (lstk).
+        const int kfwd = mail.k;
+        METIS_PAR(x, r, L) {
+            const int j0 = kH * r;
+            int own = kDropped;
+            if (j0 >= m) {
+                own = last;
+            } else {
+                int t = 0;
+                if (j0 < kfwd) {                             // first slot whose successor starts above j0
+                    int lo = 0, hi = last - 1;               // (j0 < k: such a slot exists among 0 .. last-1)
+#pragma unroll 1
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const uint16_t e = w.fe[mid];
+                        if ((int)(e & kPos) + ((e & kBroke) ? 1 : 0) <= j0) lo = mid + 1; else hi = mid;
                     }
-                    v |= 0xFF00000000000000ULL;
-                    const int c3 = (int)((v >> 24) & 0xFF);
-                    if (swar_count(v, c3) * 2 > kH) own = c3;     // count > hallucination / 2 (:295)
+                    t = lo;
+                }
+                uint64_t v = 0xFF00000000000000ULL;
+                uint16_t e = w.fe[t];                        // slot t: its end, and where stage t + 1 starts
+                int nxt = (int)(e & kPos) + ((e & kBroke) ? 1 : 0);
+#pragma unroll 1
+                for (int q = 0; q < kH; ++q) {
+                    const int j = j0 + q;
+                    int st;
+                    if (j >= m) st = last;
+                    else if (j >= kfwd) st = w.blk[j - kfwd];
                     else {
-                        const int c0 = (int)(v & 0xFF), c1 = (int)((v >> 8) & 0xFF), c2 = (int)((v >> 16) & 0xFF);
-                        if (swar_count(v, c0) * 2 > kH) own = c0;
-                        else if (c1 != c0 && swar_count(v, c1) * 2 > kH) own = c1;
-                        else if (c2 != c1 && c2 != c0 && swar_count(v, c2) * 2 > kH) own = c2;
+#pragma unroll 1
+                        while (nxt <= j) { ++t; e = w.fe[t]; nxt = (int)(e & kPos) + ((e & kBroke) ? 1 : 0); }
+                        st = t;
+                        if (nxt - 1 == j && (e & kBroke)) st = (e & kTaken) ? last : (int)w.lstk[t];
                     }
+                    v |= (uint64_t)st << (8 * q);
+                }
+                const int c3 = (int)((v >> 24) & 0xFF);
+                if (swar_count(v, c3) * 2 > kH) own = c3;         // count > hallucination / 2 (:295)
+                else {
+                    const int c0 = (int)(v & 0xFF), c1 = (int)((v >> 8) & 0xFF), c2 = (int)((v >> 16) & 0xFF);
+                    if (swar_count(v, c0) * 2 > kH) own = c0;
+                    else if (c1 != c0 && swar_count(v, c1) * 2 > kH) own = c1;
+                    else if (c2 != c1 && c2 != c0 && swar_count(v, c2) * 2 > kH) own = c2;
                 }
             }
             reinterpret_cast<uint8_t *>(w.ownerw)[r] = (uint8_t)own;
         }
+        METIS_PAR(x, s, S) w.cnt[s] = 0;
         x.sync();
         x.mark(14);
-        // ---- first / last / count of the layers of each stage and the spare capacity (:300-306) ----
-        METIS_PAR(x, s, S) {
-            int n = 0, fi = 0, la = 0;
+        // ---- first / last / count of the layers of each stage: lanes holding layers of one stage form a group
+        //      (match), its lowest lane folds the group into the stage's entry; blocks of `width` layers in turn ----
 #pragma unroll 1
-            for (int k = 0; k < nw; ++k) {
-                const uint64_t z = swar_eq(w.ownerw[k], s) & 0x8080808080808080ULL;
-                if (z) {
-                    if (n == 0) fi = 8 * k + (ctz64(z) >> 3);
-                    la = 8 * k + ((63 - clz64(z)) >> 3);
-                    n += popc64(z);
-                }
+        for (int base = 0; base < L; base += x.width()) {
+            const int r = base + x.lane();
+            const int own = r < L ? (int)reinterpret_cast<const uint8_t *>(w.ownerw)[r] : (int)kDropped;
+            const unsigned peers = x.match_any(own);
+            if (own != (int)kDropped && x.lane() == ctz32(peers)) {
+                const int n = popc32(peers), lo_r = r, hi_r = base + 31 - clz32(peers);
+                const int have = w.cnt[own];
+                if (have == 0 || lo_r < (int)w.first[own]) w.first[own] = (uint16_t)lo_r;
+                if (have == 0 || hi_r > (int)w.lastl[own]) w.lastl[own] = (uint16_t)hi_r;
+                w.cnt[own] = (uint16_t)(have + n);
             }
-            w.cnt[s] = (uint16_t)n; w.first[s] = (uint16_t)fi; w.lastl[s] = (uint16_t)la;
-            w.capa[s] = n ? w.perf[s] - py_sum_range_compact(lc, fi, la + 1) : w.perf[s];
+            x.sync();
+        }
+        // ---- spare capacity (:300-306) ----
+        METIS_PAR(x, s, S) {
+            const int n = w.cnt[s];
+            w.capa[s] = n ? w.perf[s] - py_sum_range_compact(lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
         }
         x.sync();
         x.mark(15);
@@ -693,6 +945,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
         max_upd = x.max_all(max_upd);
         max_dp = x.max_all(max_dp);
         x.sync();
+        x.mark(23);
         if (x.leader()) {                                     // order-dependent sums, stage order
             double pp_cost = 0.;
 #pragma unroll 1
@@ -757,6 +1010,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
             if (get_cost_coop(cost) == 0) sink.emit(pd, step, nrep, cost, w.tpc, w.part);
             else sink.keyerror();
             x.sync();                                         // the leader's record is written before the state changes
+            x.mark(24);
             ++step;
         }
     }

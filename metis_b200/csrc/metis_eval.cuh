@@ -66,13 +66,16 @@ struct Tables {
     const double *dpk;         // [kDpk] 2*(dp-1) / (dp * (bw*2^20)), dp = 2^i, uniform bandwidth only (:40-41)
     const double *pp_hidden;   // [num_bs+1] mbs*seq*hidden / (bw*2^20), uniform bandwidth only (:45-47)
     const double *pp_vocab;    // [num_bs+1][num_tp] (mbs*seq*vocab / tp) / (bw*2^20)
+    // not a reference value: running sum of the sub-layer demands, psub[j] = dlay[0/7] + .. + dlay[(j-1)/7], used only
+    // to PREDICT where a stage's forward fill ends (metis_coop.cuh); every prediction is verified exactly
+    const double *psub;        // [7 * num_layers + 1] (empty when norm_len < num_layers)
 };
 
 constexpr int kDpk = 16;
 
 // Sizes (in doubles) of the derived tables, in the order derive_tables fills them.
 struct DerivedLayout {
-    int dlay, inv_exec, ratio, dpk, pp_hidden, pp_vocab, total;
+    int dlay, inv_exec, ratio, dpk, pp_hidden, pp_vocab, psub, total;
 };
 
 MB_HD DerivedLayout derived_layout(const MetisProblem &p) {
@@ -84,6 +87,7 @@ MB_HD DerivedLayout derived_layout(const MetisProblem &p) {
     d.dpk = o; o += kDpk;
     d.pp_hidden = o; o += p.num_bs + 1;
     d.pp_vocab = o; o += (p.num_bs + 1) * p.num_tp;
+    d.psub = o; o += (p.norm_len >= p.num_layers) ? kH * p.num_layers + 1 : 0;
     d.total = o;
     return d;
 }
@@ -100,6 +104,11 @@ MB_HD double derive_entry(const MetisProblem &p, const DerivedLayout &d, const d
         return (double)(2 * (dp - 1)) / ((double)dp * bw);
     }
     if (i < d.pp_vocab) return (double)((int64_t)(i - d.pp_hidden) * p.sequence_length * p.hidden_size) / bw;
+    if (i >= d.psub) {                                       // predictor table (see Tables::psub)
+        double acc = 0.0;
+        for (int j = 0; j < i - d.psub; ++j) acc += norm_lc[j / kH] / 7.0;
+        return acc;
+    }
     const int e = i - d.pp_vocab;
     const int mbs = e / p.num_tp, tpc = e - mbs * p.num_tp;
     return ((double)((int64_t)mbs * p.sequence_length * p.vocab_size) / (double)(1 << tpc)) / bw;
@@ -113,6 +122,7 @@ MB_HD void bind_derived(Tables &T, const double *base) {
     T.dpk = base + d.dpk;
     T.pp_hidden = base + d.pp_hidden;
     T.pp_vocab = base + d.pp_vocab;
+    T.psub = base + d.psub;
 }
 
 // One inter-stage plan (search_space/plan.py:21-29).
@@ -305,6 +315,27 @@ MB_HD int ctz64(uint64_t v) {            // v != 0
     return __ffsll((long long)v) - 1;
 #else
     return __builtin_ctzll(v);
+#endif
+}
+MB_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+MB_HD int ctz32(uint32_t v) {            // v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+MB_HD int clz32(uint32_t v) {            // v != 0
+#if defined(__CUDA_ARCH__)
+    return __clz((int)v);
+#else
+    return __builtin_clz(v);
 #endif
 }
 MB_HD int clz64(uint64_t v) {            // v != 0

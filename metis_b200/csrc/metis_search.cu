@@ -456,37 +456,72 @@ struct WarpCoop {
     __device__ bool leader() const { return (threadIdx.x & 31) == 0; }
     __device__ void sync() const { __syncwarp(); }
     __device__ bool any(bool p) const { return __any_sync(0xFFFFFFFFu, p); }
-    __device__ void argmax_first(double &v, int &i) const {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const double v2 = __shfl_xor_sync(0xFFFFFFFFu, v, d);
-            const int i2 = __shfl_xor_sync(0xFFFFFFFFu, i, d);
-            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+    __device__ unsigned ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
+    __device__ unsigned match_any(int v) const { return __match_any_sync(0xFFFFFFFFu, v); }
+    // first i in [0, n] with P[i] >= t (P ascending, shared memory), n + 1 if none: 32-ary search by the whole warp
+    __device__ int first_ge(const double *P, int n, double t) const {
+        const unsigned full = 0xFFFFFFFFu;
+        const int lane = threadIdx.x & 31;
+        const int G = (n + 32) >> 5;                          // entries per lane group: ceil((n + 1) / 32)
+        int ci = lane * G + G - 1;                            // last entry of this lane's group
+        if (ci > n) ci = n;
+        const unsigned m1 = __ballot_sync(full, P[ci] >= t);
+        if (m1 == 0u) return n + 1;
+        const int g0 = (__ffs(m1) - 1) * G;                   // the first group whose last entry reaches t holds the answer
+#pragma unroll 1
+        for (int off = 0; off < G; off += 32) {
+            const int idx = g0 + off + lane;
+            const unsigned m2 = __ballot_sync(full, off + lane < G && idx <= n && P[idx] >= t);
+            if (m2) return g0 + off + __ffs(m2) - 1;
         }
+        return n + 1;
     }
-    __device__ void argmin_first(double &v, int &i) const {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const double v2 = __shfl_xor_sync(0xFFFFFFFFu, v, d);
-            const int i2 = __shfl_xor_sync(0xFFFFFFFFu, i, d);
-            if (v2 < v || (v2 == v && i2 < i)) { v = v2; i = i2; }
-        }
+    __device__ int bcast_last(int v) const { return __shfl_sync(0xFFFFFFFFu, v, 31); }
+    // Reductions with REDUX (one instruction per 32-bit max / min over the warp) on an order-preserving integer
+    // image of the double (-0.0 and +0.0 share one key, like ==); no NaN reaches these.
+    static __device__ __forceinline__ unsigned long long dkey(double v) {
+        unsigned long long u = (unsigned long long)__double_as_longlong(v);
+        if ((u << 1) == 0ULL) u = 0ULL;                      // -0.0 -> +0.0
+        return u ^ ((u >> 63) ? ~0ULL : 0x8000000000000000ULL);
+    }
+    static __device__ __forceinline__ double dkey_inv(unsigned long long k) {
+        const unsigned long long u = k ^ ((k >> 63) ? 0x8000000000000000ULL : ~0ULL);
+        return __longlong_as_double((long long)u);
+    }
+    static __device__ __forceinline__ unsigned long long kmax(unsigned long long key, bool &mine) {
+        const unsigned full = 0xFFFFFFFFu;
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mh = __reduce_max_sync(full, hi);
+        const bool c1 = hi == mh;
+        const unsigned ml = __reduce_max_sync(full, c1 ? lo : 0u);
+        mine = c1 && lo == ml;
+        return ((unsigned long long)mh << 32) | ml;
+    }
+    __device__ void argmax_first(double &v, int &i) const {  // largest v, lowest index among equals
+        bool mine;
+        const unsigned long long k = kmax(dkey(v), mine);
+        i = (int)__reduce_min_sync(0xFFFFFFFFu, mine ? (unsigned)i : 0xFFFFFFFFu);
+        v = dkey_inv(k);
+    }
+    __device__ void argmin_first(double &v, int &i) const {  // smallest v, lowest index among equals
+        bool mine;
+        const unsigned long long k = ~kmax(~dkey(v), mine);
+        i = (int)__reduce_min_sync(0xFFFFFFFFu, mine ? (unsigned)i : 0xFFFFFFFFu);
+        v = dkey_inv(k);
     }
     __device__ void imax_first(int &v, int &i) const {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const int v2 = __shfl_xor_sync(0xFFFFFFFFu, v, d);
-            const int i2 = __shfl_xor_sync(0xFFFFFFFFu, i, d);
-            if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
-        }
+        const int m = __reduce_max_sync(0xFFFFFFFFu, v);
+        i = (int)__reduce_min_sync(0xFFFFFFFFu, v == m ? (unsigned)i : 0xFFFFFFFFu);
+        v = m;
+    }
+    __device__ void imin_first(int &v, int &i) const {
+        const int m = __reduce_min_sync(0xFFFFFFFFu, v);
+        i = (int)__reduce_min_sync(0xFFFFFFFFu, v == m ? (unsigned)i : 0xFFFFFFFFu);
+        v = m;
     }
     __device__ double max_all(double v) const {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const double v2 = __shfl_xor_sync(0xFFFFFFFFu, v, d);
-            if (v2 > v) v = v2;
-        }
-        return v;
+        bool mine;
+        return dkey_inv(kmax(dkey(v), mine));
     }
     __device__ int incl_scan(int v) const {
         const int lane = threadIdx.x & 31;
@@ -864,7 +899,7 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     if (problem->num_node_sequences < 1 || problem->num_node_sequences > 256)
         return arg_fail("more than 256 node sequences (geometry word)");
     if (space->rows_bytes < 0 || space->rows_bytes > 0xFFFFFFFFLL) return arg_fail("row tables must be smaller than 4 GiB (geometry word)");
-    if (detail && detail_stride < 3 * METIS_MAX_STAGES + 1) return arg_fail("detail_stride too small");
+    if (detail && detail_stride < 3 * space->max_stage + 1) return arg_fail("detail_stride too small (3 * max_stage + 1)");
     if (capacity < 0 || (capacity > 0 && !records)) return arg_fail("records/capacity mismatch");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const BlobLayout lay = make_layout(*problem);
@@ -904,7 +939,7 @@ int metis_het_detail(const MetisProblem *problem, const MetisPlanSpace *space, c
     int rc = check_problem(problem);
     if (rc) return rc;
     if (!space || !picks || !detail || !workspace) return arg_fail("NULL argument");
-    if (detail_stride < 3 * METIS_MAX_STAGES + 1) return arg_fail("detail_stride too small");
+    if (detail_stride < 3 * space->max_stage + 1) return arg_fail("detail_stride too small (3 * max_stage + 1)");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const BlobLayout lay = make_layout(*problem);
     if (workspace_bytes < 256 + kFixedWs + (int64_t)align16(lay.total)) return METIS_E_CAPACITY;

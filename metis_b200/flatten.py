@@ -242,6 +242,7 @@ def enumerate_device_group_tables(first_stage: int, last_stage: int, num_gpus: i
         size = int(counts[i]) * stages
         out[stages] = blob[off:off + size].reshape(int(counts[i]), stages)   # views into the one blob
         off += size
+    out[0] = blob                                                            # the blob itself (offset 0 = first table)
     return out
 
 
@@ -287,6 +288,8 @@ def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_la
     lib = lib or native.load_library()
     cache: Dict[int, np.ndarray] = enumerate_device_group_tables(1, cap + 1, num_devices, variance, max_permute_len, lib,
                                                                  rows_out)
+    blob_all = cache.pop(0)
+    in_blob = {id(v) for v in cache.values()}
 
     def rows_of(stages: int) -> np.ndarray:
         if stages not in cache:
@@ -325,8 +328,8 @@ def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_la
     tables: Dict[int, Tuple[int, np.ndarray]] = {}
     chunks, offset = [], 0
     # fast path: every table is a view into the blob of the one library call -> ship that blob as is
-    base = cache[1].base if (1 in cache and cache[1].base is not None) else None
-    shared = base is not None and all(r.base is base for _, _, r in plan_blocks)
+    base = blob_all
+    shared = all(id(r) in in_blob for _, _, r in plan_blocks)
     for _, _, rows in plan_blocks:
         stages = rows.shape[1]
         if stages not in tables:

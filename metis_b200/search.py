@@ -315,18 +315,20 @@ class Candidates:
         self.node_sequences = [tuple(s) for s in node_sequences]
         self._detail = detail
         self._detail_dev = detail_dev
-        n = len(records)
-        ordinal = records['ordinal'].astype(np.int64)
-        blocks = space.blocks
-        blk = (np.searchsorted(blocks['first_ordinal'], ordinal, side='right') - 1) if n else np.zeros(0, dtype=np.int64)
-        rel = ordinal - blocks['first_ordinal'][blk]
-        ndiv = len(space.batches)
-        self.row = rel // ndiv
-        self.batches = space.batches[rel % ndiv].astype(np.int64)
-        self.ns_idx = blocks['ns_idx'][blk].astype(np.int64)
-        self.num_stage = blocks['num_stage'][blk].astype(np.int64)
         self.cost = records['cost']
-        self.num_repartition = records['num_repartition'].astype(np.int64)
+
+    def columns(self, idx=None) -> Dict[str, np.ndarray]:
+        """ns_idx, num_stage, row (dg_idx), batches, num_repartition of the candidates ``idx`` (default: all)."""
+        rec = self.records if idx is None else self.records[idx]
+        blocks = self.space.blocks
+        ordinal = rec['ordinal'].astype(np.int64)
+        blk = (np.searchsorted(blocks['first_ordinal'], ordinal, side='right') - 1) if len(rec) \
+            else np.zeros(0, dtype=np.int64)
+        rel = ordinal - blocks['first_ordinal'][blk]
+        ndiv = len(self.space.batches)
+        return dict(row=rel // ndiv, batches=self.space.batches[rel % ndiv].astype(np.int64),
+                    ns_idx=blocks['ns_idx'][blk].astype(np.int64), num_stage=blocks['num_stage'][blk].astype(np.int64),
+                    num_repartition=rec['num_repartition'].astype(np.int64))
 
     def __len__(self) -> int:
         return len(self.records)
@@ -349,18 +351,20 @@ class Candidates:
         if not len(idx):
             return []
         det = self.detail_rows(idx)
+        col = self.columns(idx)
+        cost = self.cost[idx]
         out = []
         tables = self.space.tables
-        for k, i in enumerate(idx.tolist()):
-            S = int(self.num_stage[i])
+        for k in range(len(idx)):
+            S = int(col['num_stage'][k])
             d = det[k]
-            codes = tables[S][1][int(self.row[i])]
+            codes = tables[S][1][int(col['row'][k])]
             groups = (1 << codes.astype(np.int64)).tolist()
             dp = (1 << d[:S].astype(np.int64)).tolist()
             tp = (1 << d[S:2 * S].astype(np.int64)).tolist()
             part = d[2 * S:3 * S + 1].astype(np.int64).tolist()
-            out.append((self.node_sequences[int(self.ns_idx[i])], groups, list(zip(dp, tp)), int(self.batches[i]), part,
-                        int(self.num_repartition[i]), float(self.cost[i])))
+            out.append((self.node_sequences[int(col['ns_idx'][k])], groups, list(zip(dp, tp)), int(col['batches'][k]),
+                        part, int(col['num_repartition'][k]), float(cost[k])))
         return out
 
 

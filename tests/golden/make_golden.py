@@ -243,12 +243,37 @@ def save(name, meta, arrays):
     print(f'wrote {path} ({os.path.getsize(path)} bytes)', file=sys.stderr)
 
 
-def golden_het_workload(w: Workload, procs: int, sample_n: int = 0):
+def stratified_sample(w: Workload, fraction: float, seed: int = 4321):
+    """Ordinals covering EVERY (node sequence, stage count) block of the plan space - its first two and its last
+    device-group rows with every divisor of gbs, which includes every mislabelled Q1 block - plus a uniform
+    `fraction` of all ordinals.  The block structure comes from the library's host enumerator (it only defines
+    WHICH plans the reference is asked to evaluate; what the reference returns for them is its own)."""
+    import math
+    from metis_b200 import flatten
+    nseq = math.factorial(len(w.device_types()))
+    ndev = sum(n for _, n in w.nodes)
+    space = flatten.build_plan_space(nseq, ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len)
+    ndiv = len(space.batches)
+    picks = set()
+    for blk in space.blocks:
+        first, rows = int(blk['first_ordinal']), int(blk['num_rows'])
+        for row in sorted({0, 1, rows // 2, rows - 1}):
+            if 0 <= row < rows:
+                picks.update(range(first + row * ndiv, first + (row + 1) * ndiv))
+    rng = random.Random(seed)
+    total = space.num_plans
+    picks.update(rng.sample(range(total), int(total * fraction)))
+    return sorted(picks), total
+
+
+def golden_het_workload(w: Workload, procs: int, sample_n: int = 0, strat: float = 0.0):
     with tempfile.TemporaryDirectory() as root:
         digest = materialize(w, root)
         order = profile_file_order(w)
         argv = w.cli_args(root)
         sample = None
+        if strat:
+            sample, _total = stratified_sample(w, strat)
         if sample_n:
             # count plans with the reference generator, then sample ordinals with a fixed seed
             ref = import_reference()
@@ -408,6 +433,9 @@ def main():
             golden_homo_workload(WORKLOADS[name.split(':')[0]])
         elif name.endswith(':sample'):
             golden_het_workload(WORKLOADS[name.split(':')[0]], ns.procs, sample_n=20000)
+        elif ':strat' in name:            # name:strat=0.05 -> every block + 5 % of the ordinals
+            base, _, frac = name.partition(':strat')
+            golden_het_workload(WORKLOADS[base], ns.procs, strat=float(frac.lstrip('=') or 0.01))
         else:
             golden_het_workload(WORKLOADS[name], ns.procs)
 

@@ -70,13 +70,14 @@ def _assert_arrays_equal(out, space, arr):
     col = np.arange(smax)[None, :]
     live = col < S[:, None]
     rows = np.arange(n)[:, None]
-    dp = 1 << det[rows, np.minimum(col, 383)].astype(np.int64)
-    tp = 1 << det[rows, np.minimum(S[:, None] + col, 383)].astype(np.int64)
+    wmax = det.shape[1] - 1
+    dp = 1 << det[rows, np.minimum(col, wmax)].astype(np.int64)
+    tp = 1 << det[rows, np.minimum(S[:, None] + col, wmax)].astype(np.int64)
     assert (np.where(live, dp, 0) == np.where(live, arr['dp'], 0)).all()
     assert (np.where(live, tp, 0) == np.where(live, arr['tp'], 0)).all()
     colp = np.arange(smax + 1)[None, :]
     livep = colp <= S[:, None]
-    part = det[rows, np.minimum(2 * S[:, None] + colp, 383)].astype(np.int64)
+    part = det[rows, np.minimum(2 * S[:, None] + colp, wmax)].astype(np.int64)
     assert (np.where(livep, part, 0) == np.where(livep, arr['part'], 0)).all()
     assert (np.where(live, dp * tp, 0) == np.where(live, arr['groups'], 0)).all()
 
@@ -166,25 +167,44 @@ def test_launch_shapes_give_the_same_records(env, workload_dir, monkeypatch):
     _assert_arrays_equal(out, space, arr)
 
 
-def test_c4_sampled_vs_golden(workload_dir):
-    """BASELINE configs[3] (3 types, 128 GPUs, 4.5e6 plans): the reference was run on 20 000 sampled
-    ordinals; the full space is searched on the GPU and the sampled candidates compared."""
+@pytest.mark.parametrize('name', ['c4_het128', 'c4_het128_mpl6', 'sweep_n128_t1_v0', 'sweep_n256_t2_v0'])
+def test_sampled_vs_golden(name, workload_dir):
+    """Spaces too large for the reference to finish: BASELINE configs[3] (3 types, 128 GPUs: 4.5e6 plans, and 6.8e7
+    with max_permute_len 6) and two variance-0 points of configs[4] at 128 / 256 GPUs.  The reference was run on a
+    STRATIFIED sample of the ordinals - the first two, the middle and the last device-group row of EVERY
+    (node sequence, stage count) block with every divisor of gbs (this covers every mislabelled Q1 block) plus a
+    uniform share of all ordinals (make_golden.py name:strat).  The GPU searches the whole space; every sampled
+    candidate must match (counters per sample included), and the summary's best must be the argmin of all records."""
     _gpu()
-    meta, arr = load_golden('c4_het128')
-    w, root, digest = workload_dir('c4_het128')
+    from metis_b200 import flatten, search
+    meta, arr = load_golden(name)
+    w, root, digest = workload_dir(name)
     assert digest == meta['inputs_sha256']
-    problem, space, out = _device_search(meta, root, 'profile', _cfg(w))
+    cfg = _cfg(w)
+    cluster, profile, _, mc = _inputs(root, 'profile', meta['file_order'], cfg['L'], cfg['hidden'], cfg['seq'], cfg['vocab'])
+    seqs = [tuple(s) for s in meta['node_sequences']]
+    problem = flatten.build_problem(profile, cluster, mc, cfg['gbs'], cfg['max_tp'], cfg['max_bs'], seqs)
+    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), cfg['gbs'], cfg['L'], cfg['variance'], cfg['mpl'])
     assert space.num_plans == meta['counters']['A']
-    keep = np.isin(out.records['ordinal'].astype(np.int64), arr['sample'])
+    searcher = search.HetSearcher(search.DeviceProblem(problem, space, 'cuda:0'), want_records=True, want_detail=False)
+    out = searcher.run()
+    assert out.summary['fatal_ordinal'] == 2 ** 64 - 1
+    rec = out.records
+    keep = np.isin(rec['ordinal'].astype(np.int64), arr['sample'])
+    sub = rec[keep]
+    assert len(sub) == len(arr['cost']) == meta['counters']['C']
+    stride = 3 * int(space.blocks['num_stage'].max()) + 1
 
     class Sub:
-        records = out.records[keep]
-        detail = out.detail[keep]
+        records = sub
+        detail = searcher.detail_for(sub)[:, :max(stride, arr['dp'].shape[1] * 3 + 1)]
     _assert_arrays_equal(Sub, space, arr)
-    assert out.summary['fatal_ordinal'] == 2 ** 64 - 1
+    # every block of the space has sampled plans, and the blocks with costed candidates appear in the comparison
+    blk_of = np.searchsorted(space.blocks['first_ordinal'], arr['sample'], side='right') - 1
+    assert len(np.unique(blk_of)) == len(space.blocks)
     # checksum-style property at full size: the summary's best is the argmin of all records
-    i = int(np.lexsort((out.records['step'], out.records['ordinal'], out.records['cost']))[0])
-    assert out.best[:3] == (float(out.records['cost'][i]), int(out.records['ordinal'][i]), int(out.records['step'][i]))
+    i = int(np.lexsort((rec['step'], rec['ordinal'], rec['cost']))[0])
+    assert out.best[:3] == (float(rec['cost'][i]), int(rec['ordinal'][i]), int(rec['step'][i]))
 
 
 @pytest.mark.parametrize('name', ['c3_homo64_mpl4', 'sweep_n8_t1'])
@@ -416,3 +436,127 @@ def test_scheduler_modes_agree(name, factor, workload_dir):
     assert (out.summary['num_partition_calls'], out.summary['num_balancer_runs'], out.summary['num_records']) == \
         (c['B'], c['runs'], c['C'])
     _assert_arrays_equal(out, space, arr)
+
+
+def _api_inputs(name, workload_dir):
+    from metis_b200 import api
+    from metis_b200.arguments import parse_args
+    meta, arr = load_golden(name)
+    w, root, _ = workload_dir(name)
+    args = parse_args(w.cli_args(root))
+    cluster, profile, _types, cfg = _inputs(root, 'profile', meta['file_order'], w.num_layers, w.hidden_size,
+                                            w.sequence_length, w.vocab_size)
+    volume = api.GPTActivationAndParam(cfg, profile['model']['parameters'])
+    est = api.HeteroCostEstimator(profile, cfg, volume, cluster)
+    llb = api.LayerLoadBalancer(cluster, profile, cfg, args.gbs)
+    seqs = [tuple(s) for s in meta['node_sequences']]
+    return meta, arr, (args, cluster, profile, cfg, est, llb), seqs
+
+
+def test_api_lazy_result_equals_eager_tuples(workload_dir):
+    """api.cost_het_cluster (the function the reference's callers use, cost_het_cluster.py:71-74) on c3_homo64_mpl4:
+    the lazy sequence equals the eagerly materialised 7-tuples and the golden candidates; ranked() is Python's
+    stable sorted(); repeated calls reuse the cached engine and give the same answer."""
+    _gpu()
+    import time
+    from metis_b200 import api, search
+    meta, arr, call, seqs = _api_inputs('c3_homo64_mpl4', workload_dir)
+    res = api.cost_het_cluster(*call, node_sequences=seqs, device='cuda:0')
+    assert len(res) == meta['counters']['C'] == len(arr['cost'])
+    assert (res.costs.view(np.uint64) == arr['cost'].view(np.uint64)).all()
+    gold = golden_rows(arr)
+    eager = search.materialize(res.candidates.records, res.candidates.detail_rows(np.arange(len(res))),
+                               res.candidates.space, seqs)
+    assert len(eager) == len(gold)
+    for e, g in zip(eager, gold):
+        assert (e[1], e[2], e[3], e[4], e[5], e[6]) == (g[3], g[4], g[5], g[6], g[7], g[8])
+    assert res[0] == eager[0] and res[-1] == eager[-1] and res[1234] == eager[1234]
+    assert res[10:13] == eager[10:13]
+    lazy_all = list(res)
+    assert lazy_all == eager and res == eager
+    want_rank = sorted(eager, key=lambda kv: kv[6])
+    assert res.ranked(25) == want_rank[:25]
+    assert res.best() == want_rank[0]
+    t0 = time.perf_counter()
+    again = api.cost_het_cluster(*call, node_sequences=seqs, device='cuda:0')
+    wall = time.perf_counter() - t0
+    assert again.best() == want_rank[0] and len(again) == len(res)
+    assert (again.costs.view(np.uint64) == res.costs.view(np.uint64)).all()
+    assert wall < 2.0, f'second api.cost_het_cluster call took {wall:.3f} s'
+
+
+def test_api_small_and_mixed_vs_golden(workload_dir):
+    """The same through the cached engine for problems of different shapes back to back (buffers are re-used /
+    re-grown): mixed-type stages, tight memory, 4 types."""
+    _gpu()
+    from metis_b200 import api
+    for name in ('mix32', 'het32_tight', 'c2_het16', 'sweep_n32_t4', 'mix32'):
+        meta, arr, call, seqs = _api_inputs(name, workload_dir)
+        res = api.cost_het_cluster(*call, node_sequences=seqs, device='cuda:0')
+        gold = golden_rows(arr)
+        assert len(res) == len(gold), name
+        got = list(res)
+        for e, g in zip(got, gold):
+            assert e == (tuple(meta['node_sequences'][g[2]]), g[3], g[4], g[5], g[6], g[7], g[8]), name
+        assert res.ranked() == sorted(got, key=lambda kv: kv[6]), name
+
+
+def test_c4_whole_space_vs_oracle_on_host_cores(workload_dir):
+    """BASELINE configs[3] - the configuration north_star shards over 8 GPUs - compared in FULL: the pinned CPU oracle
+    evaluates every one of the 4.5e6 inter-stage plans on this box's host cores (tests/oracle_pool.py, block-parallel)
+    and every candidate it costs must equal the device's record - ordinal, chain step, strategies, layer partition,
+    num_repartition and all 64 bits of the cost - and the device must not have any record the oracle lacks.
+    METIS_ORACLE_BUDGET_S (default 900) bounds the oracle's wall time on a slow host: then at least a quarter of the
+    space must have been compared and the coverage is reported in the assertion message / stdout."""
+    _gpu()
+    import oracle_pool
+    from metis_b200 import flatten, search
+    name = 'c4_het128'
+    meta, _arr = load_golden(name)
+    w, root, _ = workload_dir(name)
+    cfg = _cfg(w)
+    cluster, profile, _, mc = _inputs(root, 'profile', meta['file_order'], cfg['L'], cfg['hidden'], cfg['seq'], cfg['vocab'])
+    seqs = [tuple(s) for s in meta['node_sequences']]
+    problem = flatten.build_problem(profile, cluster, mc, cfg['gbs'], cfg['max_tp'], cfg['max_bs'], seqs)
+    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), cfg['gbs'], cfg['L'], cfg['variance'], cfg['mpl'])
+    stride = 3 * int(space.blocks['num_stage'].max()) + 1
+    out = search.HetSearcher(search.DeviceProblem(problem, space, 'cuda:0'), want_records=True, want_detail=True,
+                             detail_stride=stride).run()
+    assert out.summary['fatal_ordinal'] == 2 ** 64 - 1
+    rec, det = out.records, out.detail
+    key = (rec['ordinal'].astype(np.int64) << 16) | rec['step'].astype(np.int64)      # sorted: estimate_costs order
+    seen = np.zeros(len(rec), dtype=bool)
+    items = oracle_pool.work_items(space)
+    budget = float(os.environ.get('METIS_ORACLE_BUDGET_S', '900'))
+    done = plans = cands = 0
+    totals = {'B': 0, 'runs': 0, 'keyerr': 0}
+    ndiv = len(space.batches)
+    for item, pk, counters in oracle_pool.run(root, name, meta['file_order'], seqs, items, budget):
+        first, _ns, _label, stages, row_lo, row_hi = item
+        lo_ord, hi_ord = first + row_lo * ndiv, first + row_hi * ndiv
+        a, b = np.searchsorted(key, [lo_ord << 16, hi_ord << 16])
+        n = len(pk['cost'])
+        assert b - a == n, f'plans {lo_ord}..{hi_ord}: device has {b - a} candidates, oracle {n}'
+        if n:
+            r, d = rec[a:b], det[a:b]
+            assert ((r['ordinal'].astype(np.int64) == pk['ordinal']) & (r['step'].astype(np.int64) == pk['step'])).all()
+            assert (r['num_repartition'].astype(np.int64) == pk['nrep']).all()
+            assert (r['cost'].view(np.uint64) == pk['cost'].view(np.uint64)).all(), f'cost bits differ in {lo_ord}..{hi_ord}'
+            assert (r['num_stage'] == stages).all()
+            assert ((1 << d[:, :stages].astype(np.int64)) == pk['dp']).all()
+            assert ((1 << d[:, stages:2 * stages].astype(np.int64)) == pk['tp']).all()
+            assert (d[:, 2 * stages:3 * stages + 1].astype(np.int64) == pk['part']).all()
+            seen[a:b] = True
+        done += 1
+        plans += (row_hi - row_lo) * ndiv
+        cands += n
+        for k in totals:
+            totals[k] += counters[k]
+    coverage = plans / space.num_plans
+    print(f'oracle covered {plans} of {space.num_plans} plans ({100 * coverage:.1f} %), {cands} candidates, '
+          f'{done}/{len(items)} work items on {oracle_pool.usable_cores()} cores')
+    assert coverage >= 0.25, f'oracle covered only {100 * coverage:.1f} % of the space within {budget} s'
+    if done == len(items):
+        assert seen.all() and cands == len(rec) == out.summary['num_records']
+        assert (totals['B'], totals['runs'], totals['keyerr']) == \
+            (out.summary['num_partition_calls'], out.summary['num_balancer_runs'], out.summary['num_keyerror'])

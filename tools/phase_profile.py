@@ -30,7 +30,7 @@ space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.g
 dp = search.DeviceProblem(problem, space, 'cuda:0')
 dp.lib = native._lib
 s = search.HetSearcher(dp, want_records=False)
-s.shard.reserved = int(os.environ.get('METIS_COOP', '0'))
+s.shard.reserved = int(os.environ.get('METIS_BULK_MIN', '0'))
 for _ in range(3):
     s.launch()
 torch.cuda.synchronize()
@@ -40,27 +40,13 @@ native._lib.metis_debug_marks(None, 1)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record(); s.launch(); b.record(); torch.cuda.synchronize()
 sm = s.summary()
-cyc = list(sm.reserved)[:5]
-tot = sum(cyc) or 1
 native._lib.metis_debug_marks(marks, 0)
-names = {0: 'between tasks', 1: 'restore', 2: 'P perf', 10: 'R fwd', 11: 'R bwd', 12: 'R leftovers', 13: 'R vote', 14: 'R cnt+capa', 15: 'R adjust', 16: 'R part', 20: 'M demand', 21: 'M reweight', 22: 'C cost', 23: 'chain', 24: 'save'}
+names = {0: 'fetch+decode', 1: 'begin', 2: 'P perf', 10: 'R forward', 11: 'R backward', 12: 'R leftovers', 13: 'R vote',
+         14: 'R cnt+capa', 15: 'R adjust', 16: 'R part', 20: 'M demand', 21: 'M reweight', 22: 'C stage terms',
+         23: 'C sums+emit', 24: 'chain advance'}
 mt = sum(marks[:32]) or 1
-print('  cooperative-mode marks (leader-lane cycles): ' + ', '.join(f'{names.get(i, i)} {100.0 * marks[i] / mt:.1f}%' for i in range(32) if marks[i]))
-print(f'{name}: {a.elapsed_time(b):.2f} ms, plans {space.num_plans}, B {sm.num_partition_calls}, runs {sm.num_balancer_runs}, C {sm.num_records}')
-import numpy as np  # noqa: E402
-base = (s.workspace.data_ptr() + 127) & ~127
-off = base - s.workspace.data_ptr()
-trace = s.workspace[off + 4096: off + 4096 + 512 * 16].cpu().numpy().view(np.uint64).reshape(-1, 2)
-rows = [(int(n), int(t)) for n, t in trace if t]
-if rows:
-    t0 = rows[0][1]
-    print('  round: tasks  start_us  (duration_us)')
-    for i, (n, t) in enumerate(rows):
-        dur = (rows[i + 1][1] - t) / 1e3 if i + 1 < len(rows) else 0.0
-        print(f'  {i + 1:3d}: {n:7d} {(t - t0) / 1e3:9.1f}  ({dur:8.1f})')
-for k, n in zip(cyc, ['F fetch/advance', 'P performance', 'R balance_run', 'M memory/adjust', 'C cost/emit']):
-    print(f'  {n:18s} {100.0 * k / tot:6.2f} %   {k / 1e6:10.1f} Mcycles (summed over warps)')
-if any(marks[32:]):
-    print('  largest lane skew (cycles) at marks: ' + ', '.join(f'{names.get(i, i)} {marks[32 + i]}' for i in range(32) if marks[32 + i]))
-elif os.environ.get('METIS_LIB', '').find('skew') >= 0:
-    print('  lane skew: 0 cycles at every mark (all lanes read the same clock value)')
+print(f'{name}: {a.elapsed_time(b):.2f} ms (profiling build), plans {space.num_plans}, admitted {sm.reserved[0]}, chained '
+      f'{sm.reserved[1]}, B {sm.num_partition_calls}, runs {sm.num_balancer_runs}, C {sm.num_records}')
+print('  chain kernel, leader-lane cycles per phase: ' + ', '.join(
+    f'{names.get(i, i)} {100.0 * marks[i] / mt:.1f}%' for i in range(32) if marks[i]))
+print(f'  total {mt / 1e6:.1f} Mcycles over all chain warps')

@@ -46,6 +46,12 @@ extern "C" {
 #define METIS_FATAL_SCRATCH     5   /* internal scratch exceeded (more stages / leftovers than compiled limits)     */
 #define METIS_FATAL_ZERODIV     6   /* ZeroDivisionError in the reference (zero profiled time / zero total)         */
 
+/* MetisProblem.corrected bits (never set by default) */
+#define METIS_FIX_Q5  1   /* a layer goes to the stage holding MOST of its 7 sub-layers (lowest stage on ties):
+                             no layer is dropped (the reference keeps only count > 3.5, load_balancer.py:293-296) */
+#define METIS_FIX_Q6  2   /* memory demand from the profile of the stage's OWN device type; mixed-type stage:
+                             largest replica instead of the sum over a whole-cluster split (load_balancer.py:41-52) */
+
 /* limits compiled into the kernels */
 #define METIS_MAX_TYPES   8
 #define METIS_MAX_STAGES  128
@@ -76,7 +82,11 @@ typedef struct MetisProblem {
     int32_t total_devices;
     int32_t num_node_sequences;
     int32_t uniform_bw;           /* 1 when every type has the same first/min bandwidth             */
-    int32_t reserved0;
+    int32_t q10_devices;          /* num_nodes x devices of node 0: length of the rank lists the reference builds
+                                     with node 0's GPU count (load_balancer.py:109-119, cluster_bandwidth.py:34-47;
+                                     quirk Q10); == total_devices when every node has the same count   */
+    int32_t corrected;            /* opt-in deviations from the reference (0 = strict parity): METIS_FIX_* bits  */
+    int32_t reserved1;
     int64_t sequence_length, hidden_size, vocab_size;
     double optimizer_time;        /* profile_data['model']['optimizer_time'] (= 2 x optimizer_time_ms) */
     double batch_generator;       /* profile_data['model']['batch_generator']                       */
@@ -94,6 +104,8 @@ typedef struct MetisProblem {
     const double *type_bw_min;    /* [device] [num_types] _get_inter_bandwidth([type]) (quirk Q2)   */
     const uint8_t *ns_run_type;   /* [device] [num_node_sequences][num_types] type id of k-th run   */
     const int32_t *ns_run_end;    /* [device] [num_node_sequences][num_types] cumulative rank count */
+    const int32_t *ns_q10_end;    /* [device] [num_node_sequences][num_types] cumulative (nodes of the type x devices of
+                                     node 0): the type runs of the Q10 rank list                        */
 } MetisProblem;
 
 /* One block of inter-stage plans sharing (ns_idx, num_stage): plan.py:153-175 incl. quirk Q1. */

@@ -278,13 +278,16 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
     same order (see HetSearchResult).  With torch.distributed initialised the plans are sharded over the ranks and
     every rank returns the full list.
 
-    ``corrected`` (opt-in, default = strict parity with the reference): a subset of ('Q1', 'Q2') - 'Q1' drops the
-    mislabelled one-stage block of every node sequence after the first (plan.py:144-148), 'Q2' uses the
-    clusterfile's inter_bandwidth between nodes (gpu_cluster.py:56-58 returns the intra value).  Results of a
-    corrected search are NOT the reference's; ``result.summary['corrected']`` records what was applied."""
-    unknown = set(corrected) - {'Q1', 'Q2'}
+    ``corrected`` (opt-in, default = strict parity with the reference): a subset of ('Q1', 'Q2', 'Q5', 'Q6') - 'Q1'
+    drops the mislabelled one-stage block of every node sequence after the first (plan.py:144-148), 'Q2' uses the
+    clusterfile's inter_bandwidth between nodes (gpu_cluster.py:56-58 returns the intra value), 'Q5' gives every
+    layer to the stage holding most of its seven sub-layers so that none is dropped (load_balancer.py:293-296), 'Q6'
+    takes a stage's memory demand from the profile of its own device type (load_balancer.py:41-52 uses the first
+    type of the node sequence and, for mixed stages, sums a whole-cluster split).  Results of a corrected search are
+    NOT the reference's; ``result.summary['corrected']`` records what was applied."""
+    unknown = set(corrected) - {'Q1', 'Q2', 'Q5', 'Q6'}
     if unknown:
-        raise ValueError(f'unknown corrections {sorted(unknown)}: only Q1 and Q2 can be corrected on the host')
+        raise ValueError(f'unknown corrections {sorted(unknown)}: choose from Q1, Q2, Q5, Q6')
     import torch
     from . import search
     t0 = time.perf_counter()

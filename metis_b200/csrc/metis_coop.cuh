@@ -666,14 +666,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
                     }
                     v |= (uint64_t)st << (8 * q);
                 }
-                const int c3 = (int)((v >> 24) & 0xFF);
-                if (swar_count(v, c3) * 2 > kH) own = c3;         // count > hallucination / 2 (:295)
-                else {
-                    const int c0 = (int)(v & 0xFF), c1 = (int)((v >> 8) & 0xFF), c2 = (int)((v >> 16) & 0xFF);
-                    if (swar_count(v, c0) * 2 > kH) own = c0;
-                    else if (c1 != c0 && swar_count(v, c1) * 2 > kH) own = c1;
-                    else if (c2 != c1 && c2 != c0 && swar_count(v, c2) * 2 > kH) own = c2;
-                }
+                own = layer_owner(v, (T.p.corrected & METIS_FIX_Q5) != 0);
             }
             reinterpret_cast<uint8_t *>(w.ownerw)[r] = (uint8_t)own;
         }
@@ -840,13 +833,20 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
         const int S = pd.S;
         const bool one_type = T.p.num_types == 1;
         const int type0 = T.run_type[pd.ns * T.p.num_types];
+        const bool q10_short = T.p.q10_devices < T.p.total_devices;   // node 0 has fewer GPUs than the average (Q10)
+        const bool own_type = (T.p.corrected & METIS_FIX_Q6) != 0;
         bool failed = false, oom = false;
         x.sync();                                            // the balancer's last readers of capa / extra / mstate are done
         METIS_PAR(x, s, S) {
             const int g = w.gcode[s], tpc = w.tpc[s];
-            const int a = one_type ? 0 : this->rank_start(s), b = a + (1 << g);
+            const int a = this->rank_start(s), b = a + (1 << g);
             double md = 0.001, err = 0.0;
-            if (one_type || type_of_rank(T, pd.ns, a) == type_of_rank(T, pd.ns, b - 1)) {
+            if (own_type) {                                  // opt-in METIS_FIX_Q6 (not the reference)
+                const int rc = this->memory_demand_own_type(s, md);
+                if (rc) err = (double)rc + (double)aux * 256.0;
+            } else if (q10_short && b > T.p.q10_devices) {
+                err = (double)METIS_FATAL_INDEX;             // device_types[rank]: IndexError (load_balancer.py:36, Q10)
+            } else if (one_type || type_of_q10(T, pd.ns, a) == type_of_q10(T, pd.ns, b - 1)) {
                 const int bs = bs_total >> (g - tpc);
                 const int key = key_of(T, type0, tpc, bs);
                 if (key < 0) err = (double)METIS_FATAL_KEY_MEMORY + (double)(((uint32_t)tpc << 16) | (uint32_t)bs) * 256.0;
@@ -886,6 +886,8 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
         const bool one_type = T.p.num_types == 1;
         const bool ubw = T.p.uniform_bw != 0;
         const int nstage = pd.label < pd.S ? pd.label : pd.S;  // zip(range(plan.num_stage), strategies)
+        // rank_node_map holds num_nodes * devices(node 0) ranks (cluster_bandwidth.py:34-47, Q10): beyond -> KeyError
+        if (T.p.q10_devices < T.p.total_devices && this->rank_start(nstage) > T.p.q10_devices) return 1;
         double *ppterm = reinterpret_cast<double *>(w.subw);  // free after the vote (MAXL >= MAXS)
         bool bad = false;
         double max_len = -INFINITY, max_upd = -INFINITY, max_dp = -INFINITY;

@@ -57,7 +57,9 @@ struct Tables {
     const double *norm_lc;     // [norm_len]
     const double *type_memory, *bw_first, *bw_min;
     const uint8_t *run_type;   // [ns][num_types]
-    const int32_t *run_end;    // [ns][num_types]
+    const int32_t *run_end;    // [ns][num_types]  type runs of the true rank -> device map (model/device_group.py:22-32)
+    const int32_t *q10_end;    // [ns][num_types]  type runs of the rank list built with node 0's GPU count (quirk Q10):
+                               //                  load_balancer.py:109-119 (ranks) and cluster_bandwidth.py:158-167 (nodes)
     // derived once per launch (derive_tables): every entry is the result of the same single IEEE
     // operation the reference performs, so looking it up is bit-identical to recomputing it
     const double *dlay;        // [norm_len] norm_lc[r] / 7              (load_balancer.py:190-193)
@@ -104,10 +106,11 @@ MB_HD double derive_entry(const MetisProblem &p, const DerivedLayout &d, const d
         return (double)(2 * (dp - 1)) / ((double)dp * bw);
     }
     if (i < d.pp_vocab) return (double)((int64_t)(i - d.pp_hidden) * p.sequence_length * p.hidden_size) / bw;
-    if (i >= d.psub) {                                       // predictor table (see Tables::psub)
+    if (i >= d.psub) {                                       // predictor table (see Tables::psub): whole layers + a share
+        const int j = i - d.psub, r = j / kH;
         double acc = 0.0;
-        for (int j = 0; j < i - d.psub; ++j) acc += norm_lc[j / kH] / 7.0;
-        return acc;
+        for (int t = 0; t < r; ++t) acc += norm_lc[t];
+        return r < p.norm_len ? acc + norm_lc[r] * ((double)(j - r * kH) / 7.0) : acc;
     }
     const int e = i - d.pp_vocab;
     const int mbs = e / p.num_tp, tpc = e - mbs * p.num_tp;
@@ -272,6 +275,17 @@ MB_HD int type_of_rank(const Tables &T, int ns, int rank) {
     return typ[nt - 1];
 }
 
+// device type at position `idx` of the Q10 rank list (callers check idx < T.p.q10_devices)
+MB_HD int type_of_q10(const Tables &T, int ns, int idx) {
+    const int nt = T.p.num_types;
+    const int32_t *end = T.q10_end + ns * nt;
+    const uint8_t *typ = T.run_type + ns * nt;
+#pragma unroll 1
+    for (int k = 0; k < nt; ++k)
+        if (idx < end[k]) return typ[k];
+    return typ[nt - 1];
+}
+
 MB_HD int key_of(const Tables &T, int type, int tpc, int bs) {
     if (tpc >= T.p.num_tp || bs < 1 || bs > T.p.num_bs) return -1;
     return T.key_index[(type * T.p.num_tp + tpc) * T.p.num_bs + (bs - 1)];
@@ -355,6 +369,30 @@ MB_HD uint64_t swar_eq(uint64_t x, int c) {
 
 // number of bytes of x (bytes 0..6) equal to c
 MB_HD int swar_count(uint64_t x, int c) { return popc64(swar_eq(x, c) & 0x0080808080808080ULL); }
+
+// Owner of a real layer from the packed stages of its 7 sub-layers (bytes 0..6 of v, byte 7 = 0xFF).
+// Reference (model/load_balancer.py:293-296): the stage holding more than half of them, else nobody (kDropped,
+// quirk Q5).  A stage holding >= 4 of 7 holds the middle one or one of the first three, so four candidates do.
+// `plurality` (opt-in METIS_FIX_Q5, not the reference): the stage holding most, lowest stage among equals.
+MB_HD int layer_owner(uint64_t v, bool plurality) {
+    if (plurality) {
+        int best = 0, own = (int)kDropped;
+#pragma unroll 1
+        for (int q = 0; q < kH; ++q) {
+            const int cq = (int)((v >> (8 * q)) & 0xFF);
+            const int n = swar_count(v, cq);
+            if (n > best || (n == best && cq < own)) { best = n; own = cq; }
+        }
+        return own;
+    }
+    const int c3 = (int)((v >> 24) & 0xFF);
+    if (swar_count(v, c3) * 2 > kH) return c3;                // count > hallucination / 2 (:295)
+    const int c0 = (int)(v & 0xFF), c1 = (int)((v >> 8) & 0xFF), c2 = (int)((v >> 16) & 0xFF);
+    if (swar_count(v, c0) * 2 > kH) return c0;
+    if (c1 != c0 && swar_count(v, c1) * 2 > kH) return c1;
+    if (c2 != c1 && c2 != c0 && swar_count(v, c2) * 2 > kH) return c2;
+    return (int)kDropped;
+}
 
 template <int MAXS, int MAXL, class X>
 MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x) {
@@ -570,15 +608,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
                 v = (v & mask) | (((uint64_t)last * kOnes) & ~mask);
             }
             v |= 0xFF00000000000000ULL;
-            const int c3 = (int)((v >> 24) & 0xFF);
-            own = kDropped;
-            if (swar_count(v, c3) * 2 > kH) own = c3;         // count > hallucination / 2 (:295)
-            else {
-                const int c0 = (int)(v & 0xFF), c1 = (int)((v >> 8) & 0xFF), c2 = (int)((v >> 16) & 0xFF);
-                if (swar_count(v, c0) * 2 > kH) own = c0;
-                else if (c1 != c0 && swar_count(v, c1) * 2 > kH) own = c1;
-                else if (c2 != c1 && c2 != c0 && swar_count(v, c2) * 2 > kH) own = c2;
-            }
+            own = layer_owner(v, (T.p.corrected & METIS_FIX_Q5) != 0);
         }
         reinterpret_cast<uint8_t *>(w.ownerw)[r] = (uint8_t)own;
     }
@@ -686,14 +716,14 @@ struct HSplit {
 };
 
 MB_HD_NOINLINE int partition_data(const Tables &T, int ns, int rank_lo, int count, int dp, int tpc, int bs,
-                                  HSplit &out, uint32_t &aux) {
+                                  HSplit &out, uint32_t &aux, bool q10 = false) {
     const int gsz = count / dp;
     double perf[METIS_MAX_TYPES];
     PySum total;
     out.nruns = 0;
 #pragma unroll 1
     for (int i = 0; i < dp; ++i) {
-        const int t = type_of_rank(T, ns, rank_lo + i * gsz);
+        const int t = q10 ? type_of_q10(T, ns, rank_lo + i * gsz) : type_of_rank(T, ns, rank_lo + i * gsz);
         if (out.nruns == 0 || out.type[out.nruns - 1] != t) {
             const int key = key_of(T, t, tpc, 1);
             if (key < 0) { aux = ((uint32_t)tpc << 16) | 1u; return METIS_FATAL_KEY_EXEC; }
@@ -752,9 +782,10 @@ struct PlanEvaluator {
     int bs_total;         // gbs // batches
     int nbad;             // stages of the current strategy that violate _is_valid_strategies
     uint32_t aux;
+    int chain_hint;       // scheduling hint only: how many halvings the out-of-memory stages are away from fitting
 
     MB_HD PlanEvaluator(const Tables &t, Scratch<MAXS, MAXL> &s, const X &lanes = X())
-        : T(t), w(s), x(lanes), bs_total(0), nbad(0), aux(0) {}
+        : T(t), w(s), x(lanes), bs_total(0), nbad(0), aux(0), chain_hint(0) {}
 
     MB_HD int group(int s) const { return 1 << w.gcode[s]; }
     MB_HD int dp_of(int s) const { return (1 << w.gcode[s]) >> w.tpc[s]; }
@@ -945,7 +976,7 @@ struct PlanEvaluator {
     MB_HD_NOINLINE int hetero_memory_demand(int s, int type0, double &demand) {
         const int la = w.part[s], lb = w.part[s + 1], tpc = w.tpc[s];
         HSplit hs;                                           // whole-cluster device list (quirk Q6)
-        const int rc = partition_data(T, pd.ns, 0, T.p.total_devices, dp_of(s), tpc, bs_total, hs, aux);
+        const int rc = partition_data(T, pd.ns, 0, T.p.q10_devices, dp_of(s), tpc, bs_total, hs, aux, true);
         if (rc) return rc;
 #pragma unroll (X::kUniform ? 1 : 0)
         for (int r = 0; r < hs.nruns; ++r)
@@ -961,6 +992,45 @@ struct PlanEvaluator {
                     demand += sum_range<X>(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
                 }
             }
+        return 0;
+    }
+
+    // Opt-in METIS_FIX_Q6 (NOT the reference; mirrored by oracle.stage_memory_demand_own_type): the stage's own
+    // devices decide the memory profile; a mixed-type stage needs the memory of its largest replica.
+    MB_HD_NOINLINE int memory_demand_own_type(int s, double &demand) {
+        const int la = w.part[s], lb = w.part[s + 1], tpc = w.tpc[s], g = w.gcode[s];
+        const int a = rank_start(s), b = a + (1 << g);
+        const int ta = type_of_rank(T, pd.ns, a), tb = type_of_rank(T, pd.ns, b - 1);
+        if (ta == tb) {
+            const int bs = bs_total >> (g - tpc);
+            const int key = key_of(T, ta, tpc, bs);
+            if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; return METIS_FATAL_KEY_MEMORY; }
+            demand += py_sum_range_compact(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
+            return 0;
+        }
+        HSplit hs;
+        const int rc = partition_data(T, pd.ns, a, b - a, 1 << (g - tpc), tpc, bs_total, hs, aux);
+        if (rc) return rc;
+        double worst = 0.0;
+#pragma unroll 1
+        for (int r = 0; r < hs.nruns; ++r)
+#pragma unroll 1
+            for (int v = 0; v < 2; ++v) {
+                const int cntv = v ? hs.plus[r] : hs.n[r] - hs.plus[r];
+                const int h = hs.base[r] + v;
+                if (cntv <= 0 || h == 0) continue;
+                double need = 0.0;
+#pragma unroll 1
+                for (int bit = 30; bit >= 0; --bit) {
+                    const int piece = 1 << bit;
+                    if (!(h & piece)) continue;
+                    const int key = key_of(T, hs.type[r], tpc, piece);
+                    if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)piece; return METIS_FATAL_KEY_MEMORY; }
+                    need += py_sum_range_compact(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
+                }
+                if (need > worst) worst = need;
+            }
+        demand += worst;
         return 0;
     }
 
@@ -1043,13 +1113,20 @@ struct PlanEvaluator {
         const int S = pd.S;
         const bool one_type = T.p.num_types == 1;
         const int type0 = T.run_type[pd.ns * T.p.num_types];
+        const bool q10_short = T.p.q10_devices < T.p.total_devices;   // node 0 has fewer GPUs than the average (Q10)
+        const bool own_type = (T.p.corrected & METIS_FIX_Q6) != 0;
         x.sync();                                            // balance_run's last readers of capa/extra/mstate are done
 #pragma unroll (X::kUniform ? 1 : 0)
         for (int s = x.lane(); s < S; s += x.width()) {
             const int g = w.gcode[s], tpc = w.tpc[s];
-            const int a = one_type ? 0 : rank_start(s), b = a + (1 << g);
+            const int a = (one_type && !q10_short) ? 0 : rank_start(s), b = a + (1 << g);
             double md = 0.001, err = 0.0;
-            if (one_type || type_of_rank(T, pd.ns, a) == type_of_rank(T, pd.ns, b - 1)) {
+            if (own_type) {                                  // opt-in METIS_FIX_Q6 (not the reference)
+                const int rc = memory_demand_own_type(s, md);
+                if (rc) err = (double)rc + (double)aux * 256.0;
+            } else if (q10_short && b > T.p.q10_devices) {
+                err = (double)METIS_FATAL_INDEX;             // device_types[rank]: IndexError (load_balancer.py:36, Q10)
+            } else if (one_type || type_of_q10(T, pd.ns, a) == type_of_q10(T, pd.ns, b - 1)) {
                 const int bs = bs_total >> (g - tpc);
                 const int key = key_of(T, type0, tpc, bs);
                 if (key < 0) err = (double)METIS_FATAL_KEY_MEMORY + (double)(((uint32_t)tpc << 16) | (uint32_t)bs) * 256.0;
@@ -1059,8 +1136,14 @@ struct PlanEvaluator {
                 if (rc) err = (double)rc + (double)aux * 256.0;
             }
             w.extra[s] = md;
-            w.capa[s] = one_type ? T.type_memory[0] * (double)(1 << g) - md : memory_capacity(a, b) - md;
+            const double mc = one_type ? T.type_memory[0] * (double)(1 << g) : memory_capacity(rank_start(s), rank_start(s) + (1 << g));
+            w.capa[s] = mc - md;
             w.mstate[s] = err;
+            if (defer && md > mc && mc > 0.0) {              // log2(demand / capacity), rounded up, from the exponents
+                uint64_t bd, bc;
+                memcpy(&bd, &md, 8); memcpy(&bc, &mc, 8);
+                chain_hint += (int)((bd >> 52) & 0x7FF) - (int)((bc >> 52) & 0x7FF) + 1;
+            }
         }
         x.sync();
         bool oom = false;
@@ -1107,10 +1190,10 @@ struct PlanEvaluator {
     // bandwidth of a set of ranks given as node range / strided group (model/cluster_bandwidth.py:169-195)
     MB_HD double bw_of_node_range(int n0, int n1) const {
         const int per = T.p.devices_per_node;
-        if (n0 == n1) return T.bw_first[type_of_rank(T, pd.ns, n0 * per)];
+        if (n0 == n1) return T.bw_first[type_of_q10(T, pd.ns, n0 * per)];
         double slow = INFINITY;
         const int nt = T.p.num_types;
-        const int32_t *end = T.run_end + pd.ns * nt;
+        const int32_t *end = T.q10_end + pd.ns * nt;
         const uint8_t *typ = T.run_type + pd.ns * nt;
         int lo = 0;
 #pragma unroll (X::kUniform ? 1 : 0)
@@ -1139,10 +1222,10 @@ struct PlanEvaluator {
             for (int i = 0; i < tp; ++i) {
                 const int node = (a + d + i * dp) / per;
                 if (node != nlast) { multi = true; nlast = node; }
-                const int t = type_of_rank(T, pd.ns, node * per);
+                const int t = type_of_q10(T, pd.ns, node * per);
                 if (t != tprev) { const double v = T.bw_min[t]; if (v < gmin) gmin = v; tprev = t; }
             }
-            const double bw = multi ? gmin : T.bw_first[type_of_rank(T, pd.ns, n0 * per)];
+            const double bw = multi ? gmin : T.bw_first[type_of_q10(T, pd.ns, n0 * per)];
             if (bw < slow) slow = bw;
         }
         return slow;
@@ -1208,6 +1291,9 @@ struct PlanEvaluator {
         const bool one_type = T.p.num_types == 1;
         const bool ubw = T.p.uniform_bw != 0;
         const int nstage = pd.label < pd.S ? pd.label : pd.S;  // zip(range(plan.num_stage), strategies)
+        // rank_node_map holds num_nodes * devices(node 0) ranks (cluster_bandwidth.py:34-47, Q10): a costed stage
+        // (or its pipeline successor) beyond that raises KeyError -> the candidate is skipped
+        if (T.p.q10_devices < T.p.total_devices && rank_start(nstage) > T.p.q10_devices) return 1;
         // execution time of every stage first (independent range sums; w.capa[s] = time, w.extra[s] = error flag)
         x.sync();
 #pragma unroll (X::kUniform ? 1 : 0)
@@ -1345,10 +1431,11 @@ struct PlanEvaluator {
 // strategy of every admitted plan is therefore evaluated with 32 plans per warp in lockstep; a
 // plan whose first attempt runs out of memory is handed, unchanged, to the chain kernel (one warp
 // per plan, metis_coop.cuh), which replays that attempt and walks the rest of the chain.
-// returns true when the plan continues in the chain kernel.
+// returns true when the plan continues in the chain kernel; `chain_hint` then estimates how long its chain is
+// (used only to start long chains first).
 // ---------------------------------------------------------------------------
 template <int MAXS, int MAXL, class Sink>
-MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool has, const PlanDesc &plan) {
+MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool has, const PlanDesc &plan, int &chain_hint) {
     PlanEvaluator<MAXS, MAXL, Serial> ev(T, w);
     bool cont = false;
     sink.phase(1);
@@ -1373,7 +1460,7 @@ MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool 
     if (has) {                                               // ---- M ----
         const int r = ev.memory_phase(1, true);
         if (r < 0) sink.fatal(plan.ordinal, -r, ev.aux);
-        else if (r == 2) cont = true;                        // out of memory: re-weighting and the rest in the chain kernel
+        else if (r == 2) { cont = true; chain_hint = ev.chain_hint; }   // out of memory: the rest in the chain kernel
         else costing = true;                                 // r == 1: partition accepted at the first attempt
     }
     sink.phase(4);

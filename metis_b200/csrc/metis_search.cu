@@ -58,7 +58,7 @@ int fail_arg(const char *what) { return arg_fail(what); }
 
 struct BlobLayout {
     uint32_t total;
-    uint32_t key, lc, mem, exec_full, fb, norm, derived, tmem, bwf, bwm, runt, rune;
+    uint32_t key, lc, mem, exec_full, fb, norm, derived, tmem, bwf, bwm, runt, rune, q10e;
 };
 
 static uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -79,6 +79,7 @@ static BlobLayout make_layout(const MetisProblem &p) {
     l.bwm = o;       o = align16(o + (uint32_t)p.num_types * 8);
     l.runt = o;      o = align16(o + (uint32_t)p.num_node_sequences * p.num_types);
     l.rune = o;      o = align16(o + (uint32_t)p.num_node_sequences * p.num_types * 4);
+    l.q10e = o;      o = align16(o + (uint32_t)p.num_node_sequences * p.num_types * 4);
     l.total = o;
     return l;
 }
@@ -98,6 +99,7 @@ __device__ __forceinline__ Tables make_tables(const MetisProblem &p, const BlobL
     T.bw_min = reinterpret_cast<const double *>(base + l.bwm);
     T.run_type = base + l.runt;
     T.run_end = reinterpret_cast<const int32_t *>(base + l.rune);
+    T.q10_end = reinterpret_cast<const int32_t *>(base + l.q10e);
     return T;
 }
 
@@ -120,6 +122,7 @@ __global__ void pack_tables_kernel(MetisProblem p, BlobLayout l, uint8_t *blob) 
     copy_bytes(blob + l.bwm, p.type_bw_min, (uint32_t)p.num_types * 8, tid, nthr);
     copy_bytes(blob + l.runt, p.ns_run_type, (uint32_t)p.num_node_sequences * p.num_types, tid, nthr);
     copy_bytes(blob + l.rune, p.ns_run_end, (uint32_t)p.num_node_sequences * p.num_types * 4, tid, nthr);
+    copy_bytes(blob + l.q10e, p.ns_q10_end, (uint32_t)p.num_node_sequences * p.num_types * 4, tid, nthr);
     // derived tables: each entry is one IEEE operation of the reference, evaluated once per launch
     double *derived = reinterpret_cast<double *>(blob + l.derived);
     const DerivedLayout d = derived_layout(p);
@@ -318,6 +321,7 @@ struct SearchLists {
     long long bulk_min;           // lists shorter than this skip the bulk round
 };
 constexpr int kCtlHist = 16, kCtlCursor = 16 + 160;
+constexpr int kCtlHist2 = 512, kCtlCursor2 = 512 + 160;   // ordering of the continuations by chain hint
 
 __device__ __forceinline__ uint4 make_entry(uint32_t ordinal, uint32_t flags, uint64_t geo) {
     return make_uint4(ordinal, flags, (uint32_t)geo, (uint32_t)(geo >> 32));
@@ -420,18 +424,44 @@ het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
             const bool has = pos < (long long)n;
             uint4 e = make_uint4(0, 0, 0, 0);
             if (has) { e = ls.b[pos]; decode_entry(sp, e, pd); }
-            const bool cont = first_task<MAXS, MAXL>(T, w, sink, has, pd);
+            int hint = 0;
+            const bool cont = first_task<MAXS, MAXL>(T, w, sink, has, pd, hint);
             const unsigned m = __ballot_sync(0xFFFFFFFFu, cont);
             if (m) {
                 const int leader = __ffs(m) - 1;
                 unsigned int at = 0;
                 if (lane == leader) at = atomicAdd(&ls.ctl[2], (unsigned int)__popc(m));
                 at = __shfl_sync(0xFFFFFFFFu, at, leader);
-                if (cont) { e.y = 1u; ls.a[at + __popc(m & ((1u << lane) - 1u))] = e; }
+                if (cont) {
+                    const unsigned key = hint < 0 ? 0u : (hint > 127 ? 127u : (unsigned)hint);
+                    e.y = 1u | (key << 8);
+                    ls.a[at + __popc(m & ((1u << lane) - 1u))] = e;
+                    atomicAdd(&ls.ctl[kCtlHist2 + key], 1u);
+                }
             }
         }
     }
     finish_block(sink, out, best_slot + blockIdx.x);
+}
+
+// Continuations of the bulk round (list C, in the storage of list A) -> list B, longest expected chain first: the
+// chain kernel walks a plan's whole chain on one warp, so the long ones must start early (LPT order).
+__global__ void __launch_bounds__(256)
+het_order_kernel(const SearchLists ls) {
+    __shared__ unsigned int s_base[128];
+    if ((long long)ls.ctl[0] < ls.bulk_min) return;          // no bulk round: list B already holds the work
+    const unsigned int n = ls.ctl[2];
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int k = 127; k >= 0; --k) { s_base[k] = acc; acc += ls.ctl[kCtlHist2 + k]; }
+    }
+    __syncthreads();
+    const long long span = (long long)gridDim.x * blockDim.x;
+    for (long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x; pos < (long long)n; pos += span) {
+        const uint4 e = ls.a[pos];
+        const unsigned key = (e.y >> 8) & 0x7Fu;
+        ls.b[s_base[key] + atomicAdd(&ls.ctl[kCtlCursor2 + key], 1u)] = e;
+    }
 }
 
 // Lane policy of the chain kernel (metis_coop.cuh): 32 lanes, leader = lane 0, __syncwarp between sections.
@@ -541,11 +571,9 @@ struct alignas(16) ChainScratch {
     CoopMail mail;
 };
 
-#ifndef METIS_CHAIN_MIN_BLOCKS
-#define METIS_CHAIN_MIN_BLOCKS 4
-#endif
+// 64 registers per thread: 32 resident warps per SM in blocks of 16 warps (tables staged once per block)
 template <int MAXS, int MAXL>
-__global__ void __launch_bounds__(256, METIS_CHAIN_MIN_BLOCKS)
+__global__ void __launch_bounds__(512, 2)
 het_chain_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                  const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob, const int use_smem,
                  const unsigned int scratch_off, const __grid_constant__ DeviceOut out, const SearchLists ls,
@@ -564,7 +592,7 @@ het_chain_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
     ChainScratch<MAXS, MAXL> *cs = reinterpret_cast<ChainScratch<MAXS, MAXL> *>(smem + scratch_off) + (threadIdx.x >> 5);
     const unsigned int n_adm = ls.ctl[0];
     const bool bulk = (long long)n_adm >= ls.bulk_min;
-    const uint4 *list = bulk ? ls.a : ls.b;
+    const uint4 *list = ls.b;                                // sorted: by chain hint after a bulk round, else by stage count
     const unsigned int n = bulk ? ls.ctl[2] : n_adm;
     WarpCoop lanes;
     CoopEvaluator<MAXS, MAXL, WarpCoop> ev(T, cs->w, cs->mail, lanes);
@@ -709,7 +737,7 @@ static int check_problem(const MetisProblem *p) {
     if (p->num_layers < 1 || p->num_layers > METIS_MAX_LAYERS) return arg_fail("num_layers out of range (METIS_MAX_LAYERS)");
     if (p->lpad < p->num_layers) return arg_fail("lpad < num_layers");
     if (p->num_keys < 1 || p->num_tp < 1 || p->num_bs < 1 || p->norm_len < 1) return arg_fail("empty profile tables");
-    if (p->devices_per_node < 1 || p->total_devices < 1) return arg_fail("empty cluster");
+    if (p->devices_per_node < 1 || p->total_devices < 1 || p->q10_devices < 1) return arg_fail("empty cluster");
     return METIS_OK;
 }
 
@@ -814,10 +842,10 @@ static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg,
     int chain_threads = 0, chain_per_sm = 0;
     size_t chain_dyn = 0;
     unsigned int chain_off = 0;
-    const int forced = env_int("METIS_CHAIN_THREADS", 32, 256, 0);
+    const int forced = env_int("METIS_CHAIN_THREADS", 32, 512, 0);
     for (int pass = 0; pass < 2 && chain_threads == 0; ++pass) {       // second pass: tables in global memory
         int best_warps = 0;
-        for (int threads = 64; threads <= 256; threads *= 2) {
+        for (int threads = 64; threads <= 512; threads *= 2) {
             if (forced && threads != ((forced + 31) & ~31)) continue;
             const unsigned int off = chain_smem_tables ? blob_pad : 0u;
             const size_t dyn = off + (size_t)(threads / 32) * per_warp;
@@ -868,6 +896,7 @@ static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg,
         if (scatter_blocks > 8LL * sms) scatter_blocks = 8LL * sms;
         het_scatter_kernel<<<(unsigned)scatter_blocks, 256, 0, stream>>>(ls);
         first<<<(unsigned)first_grid, kThreads, first_dyn, stream>>>(p_arg, s_arg, lay, ws.blob, first_smem_tables, out, ls, 0);
+        het_order_kernel<<<(unsigned)(2 * sms), 256, 0, stream>>>(ls);
         chain<<<(unsigned)chain_grid, chain_threads, chain_dyn, stream>>>(p_arg, s_arg, lay, ws.blob, chain_smem_tables,
                                                                          chain_off, out, ls, (int)first_grid);
         e = cudaGetLastError();

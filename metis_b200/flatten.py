@@ -72,7 +72,7 @@ class FlatProblem:
         for k, v in self.scalars.items():
             setattr(p, k, v)
         for name in ('key_index', 'layer_compute', 'layer_memory', 'exec_full', 'fb_sync', 'norm_lc',
-                     'type_memory', 'type_bw_first', 'type_bw_min', 'ns_run_type', 'ns_run_end'):
+                     'type_memory', 'type_bw_first', 'type_bw_min', 'ns_run_type', 'ns_run_end', 'ns_q10_end'):
             setattr(p, name, ptr_of(name))
         return p
 
@@ -89,12 +89,11 @@ def build_problem(profile_data: Dict, gpu_cluster, model_config, gbs: int, max_t
                   node_sequences: Sequence[Sequence], norm_lc: Optional[Sequence[float]] = None,
                   corrected: Sequence[str] = ()) -> FlatProblem:
     """``corrected`` (opt-in): 'Q2' fills the between-node bandwidth table from the
-    clusterfile's ``inter_bandwidth`` instead of reproducing gpu_cluster.py:56-58, which returns the intra value."""
+    clusterfile's ``inter_bandwidth`` instead of reproducing gpu_cluster.py:56-58, which returns the intra value;
+    'Q5' / 'Q6' set the METIS_FIX_* bits evaluated on the device (vote without dropped layers, memory demand from
+    the stage's own device type)."""
     nodes = [gpu_cluster.nodes[i] for i in gpu_cluster.nodes.keys()]
-    per_node = nodes[0].num_devices
-    if any(n.num_devices != per_node for n in nodes):
-        raise NotImplementedError('clusters whose nodes have different GPU counts are not supported '
-                                  '(the reference maps ranks with node 0\'s count, quirk Q10)')
+    per_node = nodes[0].num_devices                         # gpu_cluster.py:25-26: node 0's count stands for all (Q10)
     type_names: List[str] = []
     for n in nodes:
         if _type_name(n.device_type) not in type_names:
@@ -160,21 +159,26 @@ def build_problem(profile_data: Dict, gpu_cluster, model_config, gbs: int, max_t
     seqs = [tuple(_type_name(t) for t in seq) for seq in node_sequences]
     run_type = np.zeros((len(seqs), len(type_names)), dtype=np.uint8)
     run_end = np.zeros((len(seqs), len(type_names)), dtype=np.int32)
+    q10_end = np.zeros((len(seqs), len(type_names)), dtype=np.int32)
+    nodes_of = {name: sum(1 for n in nodes if _type_name(n.device_type) == name) for name in type_names}
     for si, seq in enumerate(seqs):
         if sorted(seq) != sorted(type_names):
             raise ValueError('node sequence is not a permutation of the cluster device types')
-        total = 0
-        for k, name in enumerate(seq):                       # model/device_group.py:22-32
-            total += gpu_cluster.get_num_nodes_by_device_type(name)
+        total = total_q10 = 0
+        for k, name in enumerate(seq):
+            total += gpu_cluster.get_num_nodes_by_device_type(name)      # devices of the type: model/device_group.py:22-32
+            total_q10 += nodes_of[name] * per_node                       # load_balancer.py:109-119 (Q10)
             run_type[si, k] = type_names.index(name)
             run_end[si, k] = total
+            q10_end[si, k] = total_q10
 
     params = profile_data['model']['parameters']
     scalars = dict(
         num_types=len(type_names), num_tp=num_tp, num_bs=num_bs, num_keys=len(key_names), lpad=lpad,
         num_layers=num_layers, norm_len=len(norm_lc), gbs=gbs, max_tp=max_tp, max_bs=max_bs,
-        num_nodes=len(nodes), devices_per_node=per_node, total_devices=per_node * len(nodes),
-        num_node_sequences=len(seqs), uniform_bw=uniform_bw, reserved0=0,
+        num_nodes=len(nodes), devices_per_node=per_node, total_devices=int(sum(n.num_devices for n in nodes)),
+        num_node_sequences=len(seqs), uniform_bw=uniform_bw, q10_devices=per_node * len(nodes),
+        corrected=(1 if 'Q5' in corrected else 0) | (2 if 'Q6' in corrected else 0), reserved1=0,
         sequence_length=int(model_config.sequence_length), hidden_size=int(model_config.hidden_size),
         vocab_size=int(model_config.vocab_size),
         optimizer_time=float(profile_data['model']['optimizer_time']),
@@ -189,7 +193,7 @@ def build_problem(profile_data: Dict, gpu_cluster, model_config, gbs: int, max_t
         norm_lc=np.asarray(norm_lc, dtype=np.float64),
         type_memory=np.asarray(type_memory, dtype=np.float64),
         type_bw_first=np.asarray(bw_first, dtype=np.float64), type_bw_min=np.asarray(bw_min, dtype=np.float64),
-        ns_run_type=run_type, ns_run_end=run_end,
+        ns_run_type=run_type, ns_run_end=run_end, ns_q10_end=q10_end,
     )
     return FlatProblem(scalars, arrays, type_names, key_names, seqs)
 

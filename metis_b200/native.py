@@ -26,7 +26,7 @@ class MetisProblem(C.Structure):
         ('lpad', C.c_int32), ('num_layers', C.c_int32), ('norm_len', C.c_int32), ('gbs', C.c_int32),
         ('max_tp', C.c_int32), ('max_bs', C.c_int32), ('num_nodes', C.c_int32),
         ('devices_per_node', C.c_int32), ('total_devices', C.c_int32), ('num_node_sequences', C.c_int32),
-        ('uniform_bw', C.c_int32), ('reserved0', C.c_int32),
+        ('uniform_bw', C.c_int32), ('q10_devices', C.c_int32), ('corrected', C.c_int32), ('reserved1', C.c_int32),
         ('sequence_length', C.c_int64), ('hidden_size', C.c_int64), ('vocab_size', C.c_int64),
         ('optimizer_time', C.c_double), ('batch_generator', C.c_double),
         ('input_params', C.c_double), ('transformer_params', C.c_double), ('output_params', C.c_double),
@@ -34,7 +34,7 @@ class MetisProblem(C.Structure):
         ('key_index', C.c_void_p), ('layer_compute', C.c_void_p), ('layer_memory', C.c_void_p),
         ('exec_full', C.c_void_p), ('fb_sync', C.c_void_p), ('norm_lc', C.c_void_p),
         ('type_memory', C.c_void_p), ('type_bw_first', C.c_void_p), ('type_bw_min', C.c_void_p),
-        ('ns_run_type', C.c_void_p), ('ns_run_end', C.c_void_p),
+        ('ns_run_type', C.c_void_p), ('ns_run_end', C.c_void_p), ('ns_q10_end', C.c_void_p),
     ]
 
 

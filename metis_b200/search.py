@@ -28,7 +28,7 @@ def _align(n: int, a: int = 256) -> int:
 
 
 _PROBLEM_ARRAYS = ('key_index', 'layer_compute', 'layer_memory', 'exec_full', 'fb_sync', 'norm_lc', 'type_memory',
-                   'type_bw_first', 'type_bw_min', 'ns_run_type', 'ns_run_end')
+                   'type_bw_first', 'type_bw_min', 'ns_run_type', 'ns_run_end', 'ns_q10_end')
 _ARENA_ORDER = _PROBLEM_ARRAYS + ('blocks', 'batches', 'rows')
 
 

@@ -504,8 +504,10 @@ def stage_compute_performance(profile: Dict, rank_types: Sequence[str], groups: 
 
 
 def layer_compute_balance(num_stage: int, num_layer: int, capa_in: Sequence[float],
-                          lc: Sequence[float]) -> List[int]:
-    """model/load_balancer.py:182-372 (LayerComputeBalancer.run) -> layer partition."""
+                          lc: Sequence[float], plurality: bool = False) -> List[int]:
+    """model/load_balancer.py:182-372 (LayerComputeBalancer.run) -> layer partition.
+    ``plurality`` (opt-in correction Q5, not the reference): a layer goes to the stage that holds most of its
+    sub-layers (lowest stage on ties) instead of only to a stage holding more than half."""
     H = HALLUCINATION
     N = num_layer * H
     bak = list(capa_in)
@@ -573,10 +575,19 @@ def layer_compute_balance(num_stage: int, num_layer: int, capa_in: Sequence[floa
 
     # majority vote :290-308
     real: Dict[int, List[int]] = {}
-    for s in range(num_stage):
-        grp = [int(j / H) for j in alloc[s]]
-        keep = [r for r in grp if grp.count(r) > (H / 2)]
-        real[s] = sorted(list(set(keep)))
+    if plurality:
+        count = [[0] * num_stage for _ in range(num_layer)]
+        for s in range(num_stage):
+            for j in alloc[s]:
+                count[int(j / H)][s] += 1
+        real = {s: [] for s in range(num_stage)}
+        for r in range(num_layer):
+            real[max(range(num_stage), key=lambda s: (count[r][s], -s))].append(r)
+    else:
+        for s in range(num_stage):
+            grp = [int(j / H) for j in alloc[s]]
+            keep = [r for r in grp if grp.count(r) > (H / 2)]
+            real[s] = sorted(list(set(keep)))
     alloc = real
     capa = []
     for s in range(num_stage):
@@ -623,6 +634,35 @@ def layer_compute_balance(num_stage: int, num_layer: int, capa_in: Sequence[floa
     for s in alloc.keys():
         part.append(part[s] + len(alloc[s]))
     return part
+
+
+def stage_memory_demand_own_type(profile: Dict, part: Sequence[int], strategies: Sequence[Tuple[int, int]],
+                                 groups: Sequence[int], rank_types: Sequence[str], gbs: int, batches: int) -> List[float]:
+    """Opt-in correction Q6 (NOT the reference): the stage's own devices (true rank -> type map) decide the memory
+    profile; a mixed-type stage is split like its compute (partition_data over its own devices) and needs the
+    memory of its largest replica."""
+    out = []
+    for s, (dp, tp) in enumerate(strategies):
+        a, b = sum(groups[:s]), sum(groups[:s + 1])
+        cur = [rank_types[r] for r in range(a, b)]
+        la, lb = part[s], part[s + 1]
+        demand = 0.001
+        if len(set(cur)) == 1:
+            bs = gbs // batches // dp
+            demand += fsum(profile[f'DeviceType.{cur[0]}'][f'tp{tp}_bs{bs}']['memory'][la:lb]) * MEM_COEF
+        else:
+            hetero_bs = partition_data(profile, cur, (dp, tp), gbs // batches)
+            worst = 0.0
+            for r, h in enumerate(hetero_bs):
+                dev = cur[(len(cur) // dp) * r]
+                need = 0.0
+                for piece in _pow2_slices(h) if h else []:
+                    need += fsum(profile[f'DeviceType.{dev}'][f'tp{tp}_bs{piece}']['memory'][la:lb]) * MEM_COEF
+                if need > worst:
+                    worst = need
+            demand += worst
+        out.append(demand)
+    return out
 
 
 def stage_memory_demand(profile: Dict, part: Sequence[int], strategies: Sequence[Tuple[int, int]],
@@ -681,16 +721,23 @@ def adjust_compute_performance(c_capa: Sequence[float], m_capa: Sequence, m_dema
 
 
 def partition_layer(profile: Dict, cluster: OracleCluster, norm_lc: Sequence[float], num_layers: int,
-                    plan: dict, strategies, perf, m_capa, counters: Optional[dict] = None):
-    """model/load_balancer.py:121-144."""
+                    plan: dict, strategies, perf, m_capa, counters: Optional[dict] = None,
+                    corrected: Sequence[str] = ()):
+    """model/load_balancer.py:121-144.  ``corrected``: opt-in 'Q5' / 'Q6' (see layer_compute_balance,
+    stage_memory_demand_own_type); default = the reference."""
     device_types = rank_types_by_nodes(cluster, plan['node_sequence'])
     attempt = 1
     while attempt <= 3:
         if counters is not None:
             counters['runs'] = counters.get('runs', 0) + 1
-        part = layer_compute_balance(len(perf), num_layers, list(perf), norm_lc)
-        demand = stage_memory_demand(profile, part, strategies, plan['device_groups'], device_types,
-                                     plan['gbs'], plan['batches'])
+        part = layer_compute_balance(len(perf), num_layers, list(perf), norm_lc, plurality='Q5' in corrected)
+        if 'Q6' in corrected:
+            demand = stage_memory_demand_own_type(profile, part, strategies, plan['device_groups'],
+                                                  rank_types_by_devices(cluster, plan['node_sequence']),
+                                                  plan['gbs'], plan['batches'])
+        else:
+            demand = stage_memory_demand(profile, part, strategies, plan['device_groups'], device_types,
+                                         plan['gbs'], plan['batches'])
         state = [mc - md for mc, md in zip(m_capa, demand)]   # :57-63
         if not (min(state) < 0):
             return part, attempt, state
@@ -820,7 +867,8 @@ def het_cost(profile: Dict, cluster: OracleCluster, model: OracleModel, plan: di
 
 
 def het_evaluate_plan(profile: Dict, cluster: OracleCluster, model: OracleModel, norm_lc, plan: dict,
-                      ordinal: int, num_layers: int, max_tp: int, max_bs: int, counters: dict, out: list) -> None:
+                      ordinal: int, num_layers: int, max_tp: int, max_bs: int, counters: dict, out: list,
+                      corrected: Sequence[str] = ()) -> None:
     """Loop body of cost_het_cluster.py:31-48 for one inter-stage plan, with the
     IntraStagePlanGenerator chain (search_space/plan.py:178-268) inlined."""
     gbs = plan['gbs']
@@ -863,7 +911,7 @@ def het_evaluate_plan(profile: Dict, cluster: OracleCluster, model: OracleModel,
             perf = stage_compute_performance(profile, rank_types, groups, strategies, gbs, plan['batches'])
             counters['B'] += 1
             part, n_rep, state = partition_layer(profile, cluster, norm_lc, num_layers, plan,
-                                                 strategies, perf, m_capa, counters)
+                                                 strategies, perf, m_capa, counters, corrected)
             mem_state = state
             if part:                                     # :219-226
                 nrep = n_rep
@@ -899,7 +947,7 @@ def het_search(profile: Dict, cluster: OracleCluster, model: OracleModel, node_s
         if plan_filter is not None and not plan_filter(ordinal):
             continue
         het_evaluate_plan(profile, cluster, model, norm_lc, plan, ordinal, num_layers, max_tp, max_bs,
-                          counters, out)
+                          counters, out, corrected)
     return out, counters
 
 

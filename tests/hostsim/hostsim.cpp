@@ -35,6 +35,7 @@ Tables host_tables(const MetisProblem &p, std::vector<double> &dlay) {
     T.bw_min = p.type_bw_min;
     T.run_type = p.ns_run_type;
     T.run_end = p.ns_run_end;
+    T.q10_end = p.ns_q10_end;
     bind_derived(T, dlay.data());
     return T;
 }
@@ -140,7 +141,8 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
             }
             bool skip_first = false;
             if (mode == 1) {
-                if (!first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, true, pd)) continue;
+                int hint = 0;
+                if (!first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, true, pd, hint)) continue;
                 skip_first = true;
             }
             CoopEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS, OneLane> ev(T, w, mail, lanes);

@@ -52,7 +52,7 @@ def test_c1_het():
 @pytest.mark.parametrize('mode', [0, 1, 2, 3], ids=['sequential_run', 'first_task_then_chain', 'chain_only',
                                                 'chain_only_reversed_par_sections'])
 @pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight', 'sweep_n8_t1', 'sweep_n16_t2_v0',
-                                  'long_profile'])
+                                  'long_profile', 'q10_big_first'])
 def test_synthetic(name, mode, workload_dir):
     meta, arr = load_golden(name)
     w, root, _ = workload_dir(name)
@@ -89,6 +89,18 @@ def test_fatal_keyerror(workload_dir):
                                           w.vocab_size, w.gbs, w.variance, w.max_permute_len, w.max_tp, w.max_bs)
     assert summary.fatal_ordinal == meta['fatal'][0]
     assert summary.fatal_code == 1 and summary.fatal_aux == (0 << 16 | 3)     # 'tp1_bs3'
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('name', ['q10_small_first', 'q10_small_first_t1'])
+def test_fatal_indexerror_unequal_nodes(name, mode, workload_dir):
+    """Node 0 smaller than the others (quirk Q10): the reference aborts with IndexError at the first plan whose stage
+    reaches past the too-short rank list; the device reports that plan and the INDEX code."""
+    meta, _ = load_golden(name)
+    w, root, _ = workload_dir(name)
+    _, _, (_rec, _det, summary) = _search(meta, root, 'profile', w.num_layers, w.hidden_size, w.sequence_length,
+                                          w.vocab_size, w.gbs, w.variance, w.max_permute_len, w.max_tp, w.max_bs, mode=mode)
+    assert summary.fatal_ordinal == meta['fatal'][0] and summary.fatal_code == 3
 
 
 @pytest.fixture(scope='module')
@@ -299,6 +311,43 @@ def test_opt_in_corrected_mode(name, workload_dir):
         assert (g[0], g[1], g[3], g[4], g[5], g[6], g[7], g[8]) == (x[0], x[1], x[3], x[4], x[5], x[6], x[7], x[8])
     gold_costs = set(arr['cost'].tolist())
     assert any(x[8] not in gold_costs for x in want)                      # Q2 changes costs of multi-node stages
+
+
+@pytest.mark.parametrize('name,fix,mode', [('mix32', ('Q5',), 0), ('mix32', ('Q5',), 2), ('c2_v100', ('Q6',), 1),
+                                           ('c2_v100', ('Q5',), 2), ('mix32', ('Q6',), 2),
+                                           ('mix32', ('Q1', 'Q2', 'Q5', 'Q6'), 1), ('c2_v100', ('Q1', 'Q2', 'Q5', 'Q6'), 0)])
+def test_opt_in_corrected_mode_on_device(name, fix, mode, workload_dir):
+    """SURVEY.md 8(f)-4, the device half: 'Q5' (no layer dropped by the vote) and 'Q6' (memory demand from the stage's
+    own device type) change the evaluation itself (METIS_FIX_* bits of MetisProblem.corrected).  The device code, in
+    every schedule, equals the oracle run with the same corrections bit for bit; with 'Q5' every partition ends at
+    num_layers; the result differs from the strict search.  Never the default."""
+    from oracle import metis_oracle as orc
+    meta, arr = load_golden(name)
+    w, root, _ = workload_dir(name)
+    cluster, profile, _types, cfg = hs.load_inputs(root, 'profile', meta['file_order'], w.num_layers, w.hidden_size,
+                                                   w.sequence_length, w.vocab_size)
+    seqs = [tuple(s) for s in meta['node_sequences']]
+    problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs, corrected=fix)
+    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance,
+                                     w.max_permute_len, corrected=fix)
+    rec, det, summary = hs.host_het_search(problem, space, mode=mode)
+    ocl = orc.OracleCluster(os.path.join(root, 'hostfile'), os.path.join(root, 'clusterfile.json'), corrected=fix)
+    oprof, _ = orc.load_profile_dir(os.path.join(root, 'profile'), meta['file_order'])
+    omodel = orc.OracleModel(w.num_layers, w.hidden_size, w.sequence_length, w.vocab_size, oprof['model']['parameters'])
+    want, counters = orc.het_search(oprof, ocl, omodel, seqs, w.gbs, w.num_layers, w.variance, w.max_permute_len,
+                                    w.max_tp, w.max_bs, corrected=fix)
+    assert (space.num_plans, summary.num_partition_calls, summary.num_balancer_runs, summary.num_records) == \
+        (counters['A'], counters['B'], counters['runs'], counters['C'])
+    got = hs.unpack_candidates(rec, det, space)
+    assert len(got) == len(want)
+    for g, x in zip(got, want):
+        assert (g[0], g[1], g[3], g[4], g[5], g[6], g[7]) == (x[0], x[1], x[3], x[4], x[5], x[6], x[7])
+        assert g[8] == x[8]
+    if 'Q5' in fix:
+        assert all(x[6][-1] == w.num_layers for x in want)                 # nothing dropped
+    gold = {(int(o), int(st)): c for o, st, c in zip(arr['ordinal'], arr['step'], arr['cost'])}
+    if set(fix) <= {'Q5', 'Q6'}:
+        assert len(want) != len(gold) or any(gold.get((x[0], x[1])) != x[8] for x in want)   # not the strict result
 
 
 def test_layer_balancer_random_vs_oracle_on_host():

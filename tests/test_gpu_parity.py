@@ -113,7 +113,7 @@ def test_c1_het_and_homo_vs_golden_and_oracle():
 
 
 @pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight', 'sweep_n8_t1', 'sweep_n16_t2_v0',
-                                  'sweep_n32_t4', 'long_profile'])
+                                  'sweep_n32_t4', 'long_profile', 'q10_big_first'])
 def test_synthetic_vs_golden(name, workload_dir):
     _gpu()
     meta, arr = load_golden(name)
@@ -232,6 +232,21 @@ def test_fatal_keyerror_like_reference(workload_dir):
     problem, space, out = _device_search(meta, root, 'profile', _cfg(w))
     assert out.summary['fatal_ordinal'] == meta['fatal'][0]
     with pytest.raises(KeyError) as err:
+        search.raise_fatal(out.summary, problem)
+    assert str(err.value) == meta['fatal'][2]
+
+
+@pytest.mark.parametrize('name', ['q10_small_first', 'q10_small_first_t1'])
+def test_fatal_indexerror_unequal_nodes(name, workload_dir):
+    """Nodes with different GPU counts, node 0 the smallest (quirk Q10, gpu_cluster.py:25-26 + load_balancer.py:109-119):
+    the reference dies with IndexError; so does the drop-in, at the same plan."""
+    _gpu()
+    from metis_b200 import search
+    meta, _ = load_golden(name)
+    w, root, _ = workload_dir(name)
+    problem, space, out = _device_search(meta, root, 'profile', _cfg(w))
+    assert out.summary['fatal_ordinal'] == meta['fatal'][0]
+    with pytest.raises(IndexError) as err:
         search.raise_fatal(out.summary, problem)
     assert str(err.value) == meta['fatal'][2]
 

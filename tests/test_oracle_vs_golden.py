@@ -72,7 +72,7 @@ def test_c1_homo_kat2():
 
 
 @pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight', 'sweep_n8_t1', 'sweep_n16_t2_v0',
-                                  'long_profile'])
+                                  'long_profile', 'q10_big_first'])
 def test_synthetic_het(name, workload_dir):
     meta, arr = load_golden(name)
     w, root, digest = workload_dir(name)
@@ -94,6 +94,20 @@ def test_fatal_keyerror(workload_dir):
         orc.het_search(profile, cluster, model, [tuple(s) for s in meta['node_sequences']], w.gbs,
                        w.num_layers, w.variance, w.max_permute_len, w.max_tp, w.max_bs)
     assert meta['fatal'][1] == 'KeyError' and str(err.value) == meta['fatal'][2]
+
+
+@pytest.mark.parametrize('name', ['q10_small_first', 'q10_small_first_t1'])
+def test_fatal_indexerror_unequal_nodes(name, workload_dir):
+    """Quirk Q10 with node 0 SMALLER than the others: the rank list of the memory model is too short and the
+    reference dies with IndexError at the first stage that reaches past it (load_balancer.py:36)."""
+    meta, arr = load_golden(name)
+    w, root, _ = workload_dir(name)
+    cluster, profile, _, model = _oracle_inputs(root, 'profile', meta['file_order'], w.num_layers,
+                                                w.hidden_size, w.sequence_length, w.vocab_size)
+    with pytest.raises(IndexError) as err:
+        orc.het_search(profile, cluster, model, [tuple(s) for s in meta['node_sequences']], w.gbs,
+                       w.num_layers, w.variance, w.max_permute_len, w.max_tp, w.max_bs)
+    assert meta['fatal'][1] == 'IndexError' and str(err.value) == meta['fatal'][2]
 
 
 @pytest.fixture(scope='module')

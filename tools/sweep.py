@@ -12,6 +12,7 @@ import itertools
 import json
 import os
 import random
+import re
 import sys
 import tempfile
 import time
@@ -27,7 +28,9 @@ from metis_b200.workloads import materialize, profile_file_order, sweep_workload
 
 DEFAULT_POINTS = [(8, 1, 1, 4), (16, 2, 1, 4), (32, 2, 1, 4), (32, 4, 1, 4), (64, 1, 1, 4), (64, 1, 1, 6), (64, 2, 1, 4),
                   (64, 1, 0, 4), (128, 1, 1, 4), (128, 3, 1, 4), (128, 1, 1, 6), (256, 1, 1, 4), (256, 2, 1, 4),
-                  (512, 1, 1, 4), (512, 4, 1, 6)]
+                  (512, 1, 1, 4), (512, 4, 1, 6),
+                  # variance 0 (the variance-1 filter collapses the space at >= 256 GPUs)
+                  (128, 1, 0, 4), (128, 2, 0, 4), (256, 1, 0, 4)]
 
 
 def run_point(ndev, ntypes, variance, mpl, check):
@@ -47,7 +50,7 @@ def run_point(ndev, ntypes, variance, mpl, check):
                                      w.max_permute_len)
     enum_ms = 1e3 * (time.perf_counter() - t0)
     dp = search.DeviceProblem(problem, space, 'cuda:0')
-    searcher = search.HetSearcher(dp, want_records=True, want_detail=check > 0)
+    searcher = search.HetSearcher(dp, want_records=True, want_detail=False)
     out = searcher.run()
     best_only = search.HetSearcher(dp, want_records=False)
     for _ in range(2):
@@ -72,9 +75,10 @@ def run_point(ndev, ntypes, variance, mpl, check):
         rng = random.Random(ndev * 131 + ntypes)
         limit = out.summary['fatal_ordinal'] if out.summary['fatal_ordinal'] != 2 ** 64 - 1 else space.num_plans
         picks = sorted(rng.sample(range(limit), min(check, limit))) if limit else []
-        got = search.materialize(out.records, out.detail, space, seqs)
+        sub = out.records[np.isin(out.records['ordinal'].astype(np.int64), np.asarray(picks, dtype=np.int64))]
+        got = search.materialize(sub, searcher.detail_for(sub), space, seqs) if len(sub) else []
         by_ord = {}
-        for rec, tup in zip(out.records, got):
+        for rec, tup in zip(sub, got):
             by_ord.setdefault(int(rec['ordinal']), []).append(tup)
         bad = 0
         for o in picks:
@@ -101,9 +105,9 @@ def main():
     points = DEFAULT_POINTS
     if ns.points:
         points = []
-        for tok in ns.points.split(','):
-            n, rest = tok[1:].split('t')
-            points.append((int(n), int(rest), 1, 4))
+        for tok in ns.points.split(','):                      # n128t1 or n128t1v0m4
+            m = re.fullmatch(r'n(\d+)t(\d+)(?:v(\d+))?(?:m(\d+))?', tok)
+            points.append((int(m.group(1)), int(m.group(2)), int(m.group(3) or 1), int(m.group(4) or 4)))
     os.makedirs(os.path.dirname(ns.out) or '.', exist_ok=True)
     with open(ns.out, 'w') as fh:
         for p in points:

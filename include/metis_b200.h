@@ -55,7 +55,7 @@ extern "C" {
 /* limits compiled into the kernels */
 #define METIS_MAX_TYPES   8
 #define METIS_MAX_STAGES  128
-#define METIS_MAX_LAYERS  256
+#define METIS_MAX_LAYERS  256   /* scratch size; --num_layers itself is limited to 255 (one-byte partition entries) */
 
 /*
  * Flattened search problem: the dict-of-dicts `profile_data` (data_loader.py:39-61),

@@ -58,6 +58,13 @@ struct OneLane {
     MB_HD bool any(bool p) const { return p; }
     MB_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
     MB_HD unsigned match_any(int) const { return 1u; }
+    // the same, looking only at P[i0 .. i0 + 31] (clipped to n): the index if the crossing lies inside the window
+    // (P[i0] < t <= P[i] or i0 == lo), -1 if the window cannot tell
+    MB_HD int first_ge_window(const double *P, int n, int i0, int lo, double t) const {
+        for (int k = 0; k < 32 && i0 + k <= n; ++k)
+            if (P[i0 + k] >= t) return (k > 0 || i0 <= lo) ? i0 + k : -1;
+        return -1;
+    }
     // first i in [0, n] with P[i] >= t (P ascending), n + 1 if none
     MB_HD int first_ge(const double *P, int n, double t) const {
         int lo = 0, hi = n + 1;
@@ -100,7 +107,7 @@ struct FillState {
 // Only the interval ends fe[] and the residual capacities are written; which stage owns a sub-layer follows from
 // fe[] (CoopEvaluator::vote_coop), so the loop body is a compare and a subtract.
 template <int MAXS, int MAXL>
-MB_HD FillState seq_forward(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
+MB_HD_NOINLINE FillState seq_forward(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
     const int L = T.p.num_layers;
     const double *dlay = T.dlay;
     const int N = kH * L;
@@ -156,7 +163,7 @@ MB_HD FillState seq_forward(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
 
 // backward pass (:233-249): the last stage takes a contiguous tail [m, N); returns m
 template <int MAXS, int MAXL>
-MB_HD int seq_backward(const Tables &T, int S, Scratch<MAXS, MAXL> &w, int k) {
+MB_HD_NOINLINE int seq_backward(const Tables &T, int S, Scratch<MAXS, MAXL> &w, int k) {
     const int L = T.p.num_layers;
     const double *dlay = T.dlay;
     const int N = kH * L;
@@ -205,7 +212,7 @@ MB_HD int seq_backward(const Tables &T, int S, Scratch<MAXS, MAXL> &w, int k) {
 // below j whose stage holds nothing above j, hi = stage of the smallest assigned id above j whose stage holds
 // nothing below j.
 template <int MAXS, int MAXL>
-MB_HD int seq_skipped(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
+MB_HD_NOINLINE int seq_skipped(const Tables &T, int S, Scratch<MAXS, MAXL> &w) {
     const double *dlay = T.dlay;
     const int last = S - 1;
     int start = 0;                                        // first sub-layer of stage s's forward interval
@@ -273,10 +280,10 @@ MB_HD int middle_lo(int S, const Scratch<MAXS, MAXL> &w, const FillState &st) {
 }
 
 // CPython sum() of w-resident values v[0..n) in index order, for the leader lane (rolled: code size)
-MB_HD double seq_py_sum(const double *v, int n) {
+MB_HD_NOINLINE double seq_py_sum(const double *v, int n) {
     if (n <= 0) return 0.0;
     double f = 0.0 + v[0], c = 0.0;
-#pragma unroll 2
+#pragma unroll 1
     for (int i = 1; i < n; ++i) {
         const double x = v[i];
         const double t = f + x;
@@ -291,9 +298,11 @@ MB_HD double seq_py_sum(const double *v, int n) {
 // ---------------------------------------------------------------------------------------------------------
 // The chain evaluator.  One instance per lane (registers); `w` and `mail` are the warp's shared scratch.
 // ---------------------------------------------------------------------------------------------------------
-template <int MAXS, int MAXL, class X>
-struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
-    using Base = PlanEvaluator<MAXS, MAXL, SerialUniform>;
+// ONE = the cluster has a single device type (compile-time: the mixed-type paths are not even instantiated,
+// which halves the code the warps of an SM compete for in the instruction cache)
+template <int MAXS, int MAXL, class X, bool ONE = false>
+struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform, ONE> {
+    using Base = PlanEvaluator<MAXS, MAXL, SerialUniform, ONE>;
     using Base::T; using Base::w; using Base::pd; using Base::bs_total; using Base::nbad; using Base::aux;
     X x;
     CoopMail &mail;
@@ -361,7 +370,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
     }
 
     // first stage (in stage order) whose error mailbox is set: leader scan, rare path
-    MB_HD int first_error(const double *box, int n) {
+    MB_HD_NOINLINE int first_error(const double *box, int n) {
         x.sync();
         if (x.leader()) {
             mail.err = 0;
@@ -381,7 +390,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
 
     // StagePerformance.get_intra_stage_compute_performance (model/device_group.py:54-85) -> w.perf
     MB_HD int compute_performance_coop() {
-        const bool one_type = T.p.num_types == 1;
+        const bool one_type = ONE || T.p.num_types == 1;
         bool failed = false;
         x.sync();
         METIS_PAR(x, s, pd.S) {
@@ -437,18 +446,24 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
         if (S < 4 || T.p.norm_len < L) return false;          // nothing to overlap: sequential pass
         const int N = kH * L;
         const int lim = (N - 1 - kH) > 0 ? (N - 1 - kH) : 0;  // :218
-        const double *dlay = T.dlay;
+        const double *dsub = T.dsub;
         const double *P = T.psub;
         // ---- prediction: uniform walk over the stages ----
         int a = 0, first_open = -1;
+        int span = lim / last;                                // sub-layers the previous stage took: where to look first
 #pragma unroll 1
         for (int s = 0; s < last; ++s) {
             int b = lim;
             bool closed = false;
             if (a < lim) {
-                const int i = x.first_ge(P, N, w.perf[s] + P[a]);
+                const double t = w.perf[s] + P[a];
+                int i0 = a + span - 14;                       // a 32-entry window around the expected end
+                if (i0 < a + 1) i0 = a + 1;
+                int i = x.first_ge_window(P, N, i0, a + 1, t);
+                if (i < 0) i = x.first_ge(P, N, t);
                 b = i - 1 > a ? i - 1 : a;
                 if (b >= lim) b = lim; else closed = true;
+                span = b - a;
             }
             if (x.leader()) { w.first[s] = (uint16_t)a; w.fe[s] = (uint16_t)(b | (closed ? kBroke : 0)); }
             if (!closed && first_open < 0) first_open = s;
@@ -462,21 +477,13 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
             const uint16_t e = w.fe[s];
             const int b = e & kPos;
             double c = w.perf[s];
-            int j = st, r = st / kH, q = st - r * kH;
-#pragma unroll 1
-            while (j < b) {
-                const double d = dlay[r];
-                if (q == 0 && j + kH <= b && c > 9.0 * d) {   // whole layer fits with room to spare (see seq_forward)
-                    c -= d; c -= d; c -= d; c -= d; c -= d; c -= d; c -= d;
-                    j += kH; ++r;
-                    continue;
-                }
+#pragma unroll 4
+            for (int j = st; j < b; ++j) {
+                const double d = dsub[j];
                 if (!(c > d)) { bad = true; break; }          // the reference would have closed the stage here
                 c -= d;
-                ++j;
-                if (++q == kH) { q = 0; ++r; }
             }
-            if ((e & kBroke) && !bad && c > dlay[b / kH]) bad = true;   // the reference would have gone on
+            if ((e & kBroke) && !bad && c > dsub[b]) bad = true;      // the reference would have gone on
             w.capa[s] = c;
         }
 #ifdef METIS_HOST_STATS
@@ -759,7 +766,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
     // in: w.perf (c_capa), w.extra (m_demand); out: w.perf; returns 1 = None, 0 ok, <0 fatal (negated code)
     MB_HD int adjust_performance_coop() {
         const int S = pd.S;
-        const bool one_type = T.p.num_types == 1;
+        const bool one_type = ONE || T.p.num_types == 1;
         double *ratio = reinterpret_cast<double *>(w.subw);      // free after the vote (MAXL >= MAXS)
         double *mcap = ratio + MAXS / 2;                          // stage memory capacity; subw has MAXL >= 2*(MAXS/2).. see static_assert
         static_assert(MAXL >= MAXS, "subw doubles as two S-sized fp64 arrays only when MAXL >= 2 * MAXS / 2");
@@ -831,7 +838,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
     // memory demand (:29-55), OOM test (:57-63), capacity re-weighting.  Returns like PlanEvaluator::memory_phase.
     MB_HD int memory_phase_coop(int attempt) {
         const int S = pd.S;
-        const bool one_type = T.p.num_types == 1;
+        const bool one_type = ONE || T.p.num_types == 1;
         const int type0 = T.run_type[pd.ns * T.p.num_types];
         const bool q10_short = T.p.q10_devices < T.p.total_devices;   // node 0 has fewer GPUs than the average (Q10)
         const bool own_type = (T.p.corrected & METIS_FIX_Q6) != 0;
@@ -841,10 +848,10 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
             const int g = w.gcode[s], tpc = w.tpc[s];
             const int a = this->rank_start(s), b = a + (1 << g);
             double md = 0.001, err = 0.0;
-            if (own_type) {                                  // opt-in METIS_FIX_Q6 (not the reference)
+            if (!ONE && own_type) {                          // opt-in METIS_FIX_Q6 (not the reference; single type: no change)
                 const int rc = this->memory_demand_own_type(s, md);
                 if (rc) err = (double)rc + (double)aux * 256.0;
-            } else if (q10_short && b > T.p.q10_devices) {
+            } else if (q10_short && !own_type && b > T.p.q10_devices) {
                 err = (double)METIS_FATAL_INDEX;             // device_types[rank]: IndexError (load_balancer.py:36, Q10)
             } else if (one_type || type_of_q10(T, pd.ns, a) == type_of_q10(T, pd.ns, b - 1)) {
                 const int bs = bs_total >> (g - tpc);
@@ -883,7 +890,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform> {
     MB_HD int get_cost_coop(double &cost_out) {
         const int per = T.p.devices_per_node;
         const int Lm = T.p.num_layers;
-        const bool one_type = T.p.num_types == 1;
+        const bool one_type = ONE || T.p.num_types == 1;
         const bool ubw = T.p.uniform_bw != 0;
         const int nstage = pd.label < pd.S ? pd.label : pd.S;  // zip(range(plan.num_stage), strategies)
         // rank_node_map holds num_nodes * devices(node 0) ranks (cluster_bandwidth.py:34-47, Q10): beyond -> KeyError

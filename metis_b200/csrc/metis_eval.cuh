@@ -25,7 +25,7 @@
 #define MB_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define MB_HD inline
-#define MB_HD_NOINLINE
+#define MB_HD_NOINLINE inline
 #endif
 
 namespace metis {
@@ -71,13 +71,14 @@ struct Tables {
     // not a reference value: running sum of the sub-layer demands, psub[j] = dlay[0/7] + .. + dlay[(j-1)/7], used only
     // to PREDICT where a stage's forward fill ends (metis_coop.cuh); every prediction is verified exactly
     const double *psub;        // [7 * num_layers + 1] (empty when norm_len < num_layers)
+    const double *dsub;        // [7 * num_layers] demand of every sub-layer, dsub[j] = dlay[j / 7] (the same bits)
 };
 
 constexpr int kDpk = 16;
 
 // Sizes (in doubles) of the derived tables, in the order derive_tables fills them.
 struct DerivedLayout {
-    int dlay, inv_exec, ratio, dpk, pp_hidden, pp_vocab, psub, total;
+    int dlay, inv_exec, ratio, dpk, pp_hidden, pp_vocab, psub, dsub, total;
 };
 
 MB_HD DerivedLayout derived_layout(const MetisProblem &p) {
@@ -90,6 +91,7 @@ MB_HD DerivedLayout derived_layout(const MetisProblem &p) {
     d.pp_hidden = o; o += p.num_bs + 1;
     d.pp_vocab = o; o += (p.num_bs + 1) * p.num_tp;
     d.psub = o; o += (p.norm_len >= p.num_layers) ? kH * p.num_layers + 1 : 0;
+    d.dsub = o; o += (p.norm_len >= p.num_layers) ? kH * p.num_layers : 0;
     d.total = o;
     return d;
 }
@@ -106,6 +108,7 @@ MB_HD double derive_entry(const MetisProblem &p, const DerivedLayout &d, const d
         return (double)(2 * (dp - 1)) / ((double)dp * bw);
     }
     if (i < d.pp_vocab) return (double)((int64_t)(i - d.pp_hidden) * p.sequence_length * p.hidden_size) / bw;
+    if (i >= d.dsub) return norm_lc[(i - d.dsub) / kH] / 7.0;      // expand_lc_demand (load_balancer.py:189-193)
     if (i >= d.psub) {                                       // predictor table (see Tables::psub): whole layers + a share
         const int j = i - d.psub, r = j / kH;
         double acc = 0.0;
@@ -126,6 +129,7 @@ MB_HD void bind_derived(Tables &T, const double *base) {
     T.pp_hidden = base + d.pp_hidden;
     T.pp_vocab = base + d.pp_vocab;
     T.psub = base + d.psub;
+    T.dsub = base + d.dsub;
 }
 
 // One inter-stage plan (search_space/plan.py:21-29).
@@ -773,7 +777,7 @@ MB_HD_NOINLINE int partition_data(const Tables &T, int ns, int rank_lo, int coun
 //   void fatal(uint32_t ordinal, int code, uint32_t aux);
 //   void emit(const PlanDesc&, int step, int nrep, double cost, const uint8_t *tpc, const uint16_t *part);
 
-template <int MAXS, int MAXL, class X = Serial>
+template <int MAXS, int MAXL, class X = Serial, bool ONE = false>
 struct PlanEvaluator {
     const Tables &T;
     Scratch<MAXS, MAXL> &w;
@@ -856,7 +860,7 @@ struct PlanEvaluator {
     // StagePerformance.get_device_group_memory_capacity, one stage (model/device_group.py:87-101)
     MB_HD double memory_capacity(int a, int b) const {
         const int nt = T.p.num_types;
-        if (nt == 1) return T.type_memory[0] * (double)(b - a);
+        if (ONE || nt == 1) return T.type_memory[0] * (double)(b - a);
         const int32_t *end = T.run_end + pd.ns * nt;
         const uint8_t *typ = T.run_type + pd.ns * nt;
         PySum acc;
@@ -922,7 +926,7 @@ struct PlanEvaluator {
 
     // StagePerformance.get_intra_stage_compute_performance (model/device_group.py:54-85) -> w.perf
     MB_HD int compute_performance() {
-        const bool one_type = T.p.num_types == 1;
+        const bool one_type = ONE || T.p.num_types == 1;
         int fail = 0;
         x.sync();
 #pragma unroll (X::kUniform ? 1 : 0)
@@ -1038,7 +1042,7 @@ struct PlanEvaluator {
     // in: w.perf (c_capa), w.extra (m_demand); out: w.perf; returns 1 = None, 0 ok, <0 fatal (negated code)
     MB_HD_NOINLINE int adjust_performance() {
         const int S = pd.S;
-        const bool one_type = T.p.num_types == 1;
+        const bool one_type = ONE || T.p.num_types == 1;
         double *ratio = reinterpret_cast<double *>(w.subw);      // free after the vote (MAXL >= MAXS)
         x.sync();
 #pragma unroll (X::kUniform ? 1 : 0)
@@ -1111,7 +1115,7 @@ struct PlanEvaluator {
     // first-task round hands such plans to the chain kernel, which replays the attempt).
     MB_HD int memory_phase(int attempt, bool defer = false) {
         const int S = pd.S;
-        const bool one_type = T.p.num_types == 1;
+        const bool one_type = ONE || T.p.num_types == 1;
         const int type0 = T.run_type[pd.ns * T.p.num_types];
         const bool q10_short = T.p.q10_devices < T.p.total_devices;   // node 0 has fewer GPUs than the average (Q10)
         const bool own_type = (T.p.corrected & METIS_FIX_Q6) != 0;
@@ -1288,7 +1292,7 @@ struct PlanEvaluator {
     MB_HD int get_cost(double &cost_out) {
         const int per = T.p.devices_per_node;
         const int Lm = T.p.num_layers;
-        const bool one_type = T.p.num_types == 1;
+        const bool one_type = ONE || T.p.num_types == 1;
         const bool ubw = T.p.uniform_bw != 0;
         const int nstage = pd.label < pd.S ? pd.label : pd.S;  // zip(range(plan.num_stage), strategies)
         // rank_node_map holds num_nodes * devices(node 0) ranks (cluster_bandwidth.py:34-47, Q10): a costed stage
@@ -1434,9 +1438,9 @@ struct PlanEvaluator {
 // returns true when the plan continues in the chain kernel; `chain_hint` then estimates how long its chain is
 // (used only to start long chains first).
 // ---------------------------------------------------------------------------
-template <int MAXS, int MAXL, class Sink>
+template <int MAXS, int MAXL, bool ONE, class Sink>
 MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool has, const PlanDesc &plan, int &chain_hint) {
-    PlanEvaluator<MAXS, MAXL, Serial> ev(T, w);
+    PlanEvaluator<MAXS, MAXL, Serial, ONE> ev(T, w);
     bool cont = false;
     sink.phase(1);
     if (has) {                                               // ---- P ----

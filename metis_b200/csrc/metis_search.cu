@@ -376,8 +376,13 @@ het_scatter_kernel(const SearchLists ls) {
     __shared__ unsigned int s_base[METIS_MAX_STAGES];
     const unsigned int n = ls.ctl[0];
     if (threadIdx.x == 0) {
+        // bulk round: longest stage counts first (equal trip counts inside a warp, long batches early).  Chain kernel
+        // alone: shortest first - measured on BASELINE configs[2], where the plans with long chains have middle stage
+        // counts, descending order starts them late (makespan 136 vs 114 time units; 113.5 is perfect balance)
+        const bool bulk = (long long)n >= ls.bulk_min;
         unsigned int acc = 0;
-        for (int k = METIS_MAX_STAGES - 1; k >= 0; --k) { s_base[k] = acc; acc += ls.ctl[kCtlHist + k]; }   // longest first
+        if (bulk) for (int k = METIS_MAX_STAGES - 1; k >= 0; --k) { s_base[k] = acc; acc += ls.ctl[kCtlHist + k]; }
+        else      for (int k = 0; k < METIS_MAX_STAGES; ++k)      { s_base[k] = acc; acc += ls.ctl[kCtlHist + k]; }
     }
     __syncthreads();
     const long long span = (long long)gridDim.x * blockDim.x;
@@ -396,7 +401,7 @@ het_scatter_kernel(const SearchLists ls) {
     }
 }
 
-template <int MAXS, int MAXL>
+template <int MAXS, int MAXL, bool ONE>
 __global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? METIS_MIN_BLOCKS : (METIS_MIN_BLOCKS * 2 + 2) / 3))
 het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                  const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob, const int use_smem,
@@ -425,7 +430,7 @@ het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
             uint4 e = make_uint4(0, 0, 0, 0);
             if (has) { e = ls.b[pos]; decode_entry(sp, e, pd); }
             int hint = 0;
-            const bool cont = first_task<MAXS, MAXL>(T, w, sink, has, pd, hint);
+            const bool cont = first_task<MAXS, MAXL, ONE>(T, w, sink, has, pd, hint);
             const unsigned m = __ballot_sync(0xFFFFFFFFu, cont);
             if (m) {
                 const int leader = __ffs(m) - 1;
@@ -488,8 +493,15 @@ struct WarpCoop {
     __device__ bool any(bool p) const { return __any_sync(0xFFFFFFFFu, p); }
     __device__ unsigned ballot(bool p) const { return __ballot_sync(0xFFFFFFFFu, p); }
     __device__ unsigned match_any(int v) const { return __match_any_sync(0xFFFFFFFFu, v); }
+    // the crossing inside the 32-entry window P[i0 .. i0 + 31]?  (one load and one ballot; see OneLane::first_ge_window)
+    __device__ int first_ge_window(const double *P, int n, int i0, int lo, double t) const {
+        const int idx = i0 + (threadIdx.x & 31);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, idx <= n && P[idx] >= t);
+        if (m == 0u || ((m & 1u) && i0 > lo)) return -1;
+        return i0 + __ffs(m) - 1;
+    }
     // first i in [0, n] with P[i] >= t (P ascending, shared memory), n + 1 if none: 32-ary search by the whole warp
-    __device__ int first_ge(const double *P, int n, double t) const {
+    __device__ __noinline__ int first_ge(const double *P, int n, double t) const {
         const unsigned full = 0xFFFFFFFFu;
         const int lane = threadIdx.x & 31;
         const int G = (n + 32) >> 5;                          // entries per lane group: ceil((n + 1) / 32)
@@ -553,7 +565,7 @@ struct WarpCoop {
         bool mine;
         return dkey_inv(kmax(dkey(v), mine));
     }
-    __device__ int incl_scan(int v) const {
+    __device__ __noinline__ int incl_scan(int v) const {
         const int lane = threadIdx.x & 31;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -572,7 +584,7 @@ struct alignas(16) ChainScratch {
 };
 
 // 64 registers per thread: 32 resident warps per SM in blocks of 16 warps (tables staged once per block)
-template <int MAXS, int MAXL>
+template <int MAXS, int MAXL, bool ONE>
 __global__ void __launch_bounds__(512, 2)
 het_chain_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                  const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob, const int use_smem,
@@ -595,7 +607,7 @@ het_chain_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
     const uint4 *list = ls.b;                                // sorted: by chain hint after a bulk round, else by stage count
     const unsigned int n = bulk ? ls.ctl[2] : n_adm;
     WarpCoop lanes;
-    CoopEvaluator<MAXS, MAXL, WarpCoop> ev(T, cs->w, cs->mail, lanes);
+    CoopEvaluator<MAXS, MAXL, WarpCoop, ONE> ev(T, cs->w, cs->mail, lanes);
     for (;;) {
         unsigned int i = 0;
         if (lane == 0) i = atomicAdd(&ls.ctl[3], 1u);
@@ -734,7 +746,9 @@ __global__ void divide_by_seven_kernel(const double *lc, int n, double *out) {
 static int check_problem(const MetisProblem *p) {
     if (!p) return arg_fail("problem is NULL");
     if (p->num_types < 1 || p->num_types > METIS_MAX_TYPES) return arg_fail("num_types out of range");
-    if (p->num_layers < 1 || p->num_layers > METIS_MAX_LAYERS) return arg_fail("num_layers out of range (METIS_MAX_LAYERS)");
+    // detail rows keep layer_partition entries in one byte: the last boundary (num_layers) must fit
+    if (p->num_layers < 1 || p->num_layers > METIS_MAX_LAYERS || p->num_layers > 255)
+        return arg_fail("num_layers out of range (1 .. 255)");
     if (p->lpad < p->num_layers) return arg_fail("lpad < num_layers");
     if (p->num_keys < 1 || p->num_tp < 1 || p->num_bs < 1 || p->norm_len < 1) return arg_fail("empty profile tables");
     if (p->devices_per_node < 1 || p->total_devices < 1 || p->q10_devices < 1) return arg_fail("empty cluster");
@@ -816,7 +830,7 @@ static int env_int(const char *name, int lo, int hi, int dflt) {
 }  // extern "C"
 
 // Launch configuration of one search: which instantiation, how the tables are staged, block shapes.
-template <int MAXS, int MAXL>
+template <int MAXS, int MAXL, bool ONE>
 static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg, const MetisShard &sh,
                          const BlobLayout &lay, const Workspace &ws, const DeviceOut &out, int64_t slots,
                          cudaStream_t stream) {
@@ -836,7 +850,7 @@ static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg,
     ls.ctl = ws.ctl;
 
     // ---- chain kernel: warps per block chosen so that tables + per-warp scratch fill the SM with warps ----
-    auto chain = het_chain_kernel<MAXS, MAXL>;
+    auto chain = het_chain_kernel<MAXS, MAXL, ONE>;
     const size_t per_warp = sizeof(ChainScratch<MAXS, MAXL>);
     int chain_smem_tables = (int)lay.total <= blob_max;
     int chain_threads = 0, chain_per_sm = 0;
@@ -870,7 +884,7 @@ static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg,
     int64_t chain_grid = (int64_t)sms * chain_per_sm;
 
     // ---- bulk round ----
-    auto first = het_first_kernel<MAXS, MAXL>;
+    auto first = het_first_kernel<MAXS, MAXL, ONE>;
     int first_smem_tables = (int)lay.total <= blob_max && blob_pad <= (unsigned int)smem_optin;
     size_t first_dyn = first_smem_tables ? blob_pad : 0;
     if (first_dyn > 48 * 1024) {
@@ -951,12 +965,17 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     out.counters = ws.counters; out.block_best = ws.block_best;
     // three instantiations: per-warp scratch of the chain kernel (and per-thread scratch of the bulk round)
     // sized for S <= 64 / L <= 128, S <= 96 / L <= 128, and the compiled limits
+    // ... each once for single-type clusters (no mixed-type code at all) and once for the general case
+    const bool one = problem->num_types == 1;
     if (space->max_stage <= 64 && problem->num_layers <= 128)
-        rc = launch_search<64, 128>(*problem, *space, *shard, lay, ws, out, slots, stream);
+        rc = one ? launch_search<64, 128, true>(*problem, *space, *shard, lay, ws, out, slots, stream)
+                 : launch_search<64, 128, false>(*problem, *space, *shard, lay, ws, out, slots, stream);
     else if (space->max_stage <= 96 && problem->num_layers <= 128)
-        rc = launch_search<96, 128>(*problem, *space, *shard, lay, ws, out, slots, stream);
+        rc = one ? launch_search<96, 128, true>(*problem, *space, *shard, lay, ws, out, slots, stream)
+                 : launch_search<96, 128, false>(*problem, *space, *shard, lay, ws, out, slots, stream);
     else
-        rc = launch_search<kMaxS, kMaxL>(*problem, *space, *shard, lay, ws, out, slots, stream);
+        rc = one ? launch_search<kMaxS, kMaxL, true>(*problem, *space, *shard, lay, ws, out, slots, stream)
+                 : launch_search<kMaxS, kMaxL, false>(*problem, *space, *shard, lay, ws, out, slots, stream);
     if (rc) return rc;
     e = cudaMemcpyAsync(summary, ws.summary, sizeof(MetisSearchSummary), cudaMemcpyDeviceToHost, stream);
     if (e != cudaSuccess) return cuda_fail(e, "copy summary");

@@ -100,9 +100,11 @@ def build_problem(profile_data: Dict, gpu_cluster, model_config, gbs: int, max_t
             type_names.append(_type_name(n.device_type))
     if len(type_names) > native.METIS_MAX_TYPES:
         raise NotImplementedError(f'more than {native.METIS_MAX_TYPES} device types')
+    if len(node_sequences) > 256:                            # ns_idx travels in 8 bits of the list entries
+        raise NotImplementedError('more than 256 node sequences')
     num_layers = model_config.num_layers
-    if num_layers > native.METIS_MAX_LAYERS:
-        raise NotImplementedError(f'--num_layers > {native.METIS_MAX_LAYERS}')
+    if num_layers > min(native.METIS_MAX_LAYERS, 255):       # layer_partition entries travel as one byte
+        raise NotImplementedError('--num_layers > 255')
 
     num_tp = max(1, int(math.floor(math.log2(max_tp))) + 1) if max_tp >= 1 else 1
     profiled_bs = [1]
@@ -359,4 +361,8 @@ def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_la
         blob = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)
         if blob.size % 16:
             blob = np.concatenate([blob, np.zeros(16 - blob.size % 16, dtype=np.uint8)])
+    if blob.size > 0xFFFFFFFF:                               # list entries address a row with 32 bits
+        raise NotImplementedError('device-group tables of 4 GiB or more are not supported')
+    if ordinal > 0xFFFFFFF0:
+        raise NotImplementedError('more than 2^32 inter-stage plans')
     return FlatPlanSpace(ordinal, blocks, np.asarray(batches, dtype=np.int32), blob, tables)

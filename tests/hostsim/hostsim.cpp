@@ -142,12 +142,38 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
             bool skip_first = false;
             if (mode == 1) {
                 int hint = 0;
-                if (!first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS>(T, w, sink, true, pd, hint)) continue;
+                if (!first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS, false>(T, w, sink, true, pd, hint)) continue;
                 skip_first = true;
             }
             CoopEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS, OneLane> ev(T, w, mail, lanes);
             ev.run_chain(pd, sink, skip_first);
         }
+    }
+    return 0;
+}
+
+// developer statistics: LayerComputeBalancer runs per inter-stage plan (0 = plan without a valid strategy)
+int hostsim_runs_per_plan(const MetisProblem *p, const MetisPlanSpace *sp, int32_t *runs_out) {
+    std::vector<double> dlay;
+    const Tables T = host_tables(*p, dlay);
+    MetisSearchSummary sum;
+    memset(&sum, 0, sizeof(sum));
+    sum.fatal_ordinal = ~0ULL;
+    sum.best.cost = INFINITY;
+    HostSink sink{nullptr, 0, nullptr, 0, &sum};
+    static thread_local Scratch<METIS_MAX_STAGES, METIS_MAX_LAYERS> w;
+    static thread_local CoopMail mail;
+    OneLane lanes;
+    for (int64_t ordinal = 0; ordinal < sp->num_plans; ++ordinal) {
+        PlanDesc pd;
+        runs_out[ordinal] = 0;
+        if (!decode(*sp, ordinal, pd)) continue;
+        PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> probe(T, w);
+        if (probe.begin(pd) != 1) continue;
+        const uint64_t before = sum.num_balancer_runs;
+        CoopEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS, OneLane> ev(T, w, mail, lanes);
+        ev.run_chain(pd, sink, false);
+        runs_out[ordinal] = (int32_t)(sum.num_balancer_runs - before);
     }
     return 0;
 }

@@ -46,7 +46,21 @@ for ln in dis.splitlines():
         line_of[int(m.group(1), 16)] = cur
 csvtxt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
                         capture_output=True, text=True).stdout
-rows = list(csv.reader(csvtxt.splitlines()))
+allrows = list(csv.reader(csvtxt.splitlines()))
+# the report may hold several kernels: sections start with a "Kernel Name" row followed by the column header
+want = kern.replace('ILi', '<(int)').split('<')[0] if False else kern
+sections, cur_rows = [], None
+for r in allrows:
+    if r and r[0] == 'Kernel Name':
+        cur_rows = [r]
+        sections.append(cur_rows)
+    elif cur_rows is not None:
+        cur_rows.append(r)
+def _matches(name):
+    plain = re.sub(r'[^A-Za-z0-9_]', '', name)
+    return re.sub(r'[^A-Za-z0-9_]', '', kern.split('ILi')[0]) in plain and \
+        (('ILi' not in kern) or re.sub(r'\D', '', kern.split('ILi', 1)[1])[:2] in re.sub(r'\D', '', name)[:4])
+rows = next((sec for sec in sections if _matches(sec[0][1])), sections[0] if sections else allrows)
 hdr = rows[1]
 ia, iex, ith, ism = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('Thread Instructions Executed'), hdr.index('# Samples')
 base = int(rows[2][ia], 16)
@@ -82,3 +96,24 @@ if sectors:
 print(f'total warp-inst {tot[0]/1e9:.3f}e9, thread/inst {tot[1]/max(tot[0],1):.2f}, samples {tot[2]}')
 for key, (ex, th, sm) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f'{100*ex/tot[0]:5.1f}% inst {100*sm/max(tot[2],1):5.1f}% smp  {key[0]}:{key[1]:<5d} {text(key)}')
+
+# ---- the same, summed per enclosing function (crude: the nearest preceding function header in the source file) ----
+if '--functions' in os.environ.get('NCU_BY_LINE', ''):
+    heads = {}
+    for f, lines in src.items():
+        hs = []
+        for i, l in enumerate(lines, 1):
+            m = re.match(r'\s*(?:template.*)?\s*(?:MB_HD(?:_NOINLINE)?|static __device__ \w+|__device__(?: __\w+__)?|__global__)\s+.*?(\w+)\(', l)
+            if m and not l.strip().startswith('//'):
+                hs.append((i, m.group(1)))
+        heads[f] = hs
+    fagg = collections.defaultdict(lambda: [0, 0])
+    for (f, n), (ex, th, sm) in agg.items():
+        name = '?'
+        for i, nm in heads.get(f, []):
+            if i <= n:
+                name = nm
+        fagg[(f, name)][0] += ex; fagg[(f, name)][1] += sm
+    print('--- by function ---')
+    for key, (ex, sm) in sorted(fagg.items(), key=lambda kv: -kv[1][0])[:30]:
+        print(f'{100*ex/tot[0]:5.1f}% inst {100*sm/max(tot[2],1):5.1f}% smp  {key[0]}:{key[1]}')

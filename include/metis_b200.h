@@ -208,6 +208,16 @@ int metis_het_detail(const MetisProblem *problem, const MetisPlanSpace *space, c
                      int64_t workspace_bytes, void *stream);
 
 /*
+ * Verbose transcript (debug): replays the listed inter-stage plans, one thread each, and records the values the
+ * reference prints while it evaluates them (search_space/plan.py:207-218, model/load_balancer.py:92,132-133,143,
+ * model/cost_estimator.py:193,201-203,239-240, cost_het_cluster.py:43,48) as a stream of 64-bit words per plan; the
+ * layout is documented in metis_b200/csrc/metis_trace.cuh and decoded by metis_b200/verbose.py.
+ *   ordinals [device] n uint32 plan ordinals;  trace [device] n * words_per_plan uint64 (words_per_plan >= 64)
+ */
+int metis_het_trace(const MetisProblem *problem, const MetisPlanSpace *space, const uint32_t *ordinals, int64_t n,
+                    uint64_t *trace, int32_t words_per_plan, void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
  * Replaces HomoCostEstimator.get_cost (model/cost_estimator.py:98-138) for n UniformPlans
  * (search_space/plan.py:12-18), as called from cost_homo_cluster.py:29.
  *   plans  [device] n x 5 int32 (dp, pp, tp, mbs, gbs)

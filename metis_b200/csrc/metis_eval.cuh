@@ -777,6 +777,13 @@ MB_HD_NOINLINE int partition_data(const Tables &T, int ns, int rank_lo, int coun
 //   void fatal(uint32_t ordinal, int code, uint32_t aux);
 //   void emit(const PlanDesc&, int step, int nrep, double cost, const uint8_t *tpc, const uint16_t *part);
 
+// Optional tap of intermediate values for the verbose transcript (metis_trace.cuh); null in the search kernels.
+struct TraceTap {
+    double *demand;     // [S] stage_memory_demand of the last partition attempt (load_balancer.py:133)
+    double *state;      // [S] memory_state of that attempt
+    double cost[5];     // execution_cost, fb_sync_cost, max parameter update, max dp, pp_cost (cost_estimator.py:239-240)
+};
+
 template <int MAXS, int MAXL, class X = Serial, bool ONE = false>
 struct PlanEvaluator {
     const Tables &T;
@@ -787,9 +794,10 @@ struct PlanEvaluator {
     int nbad;             // stages of the current strategy that violate _is_valid_strategies
     uint32_t aux;
     int chain_hint;       // scheduling hint only: how many halvings the out-of-memory stages are away from fitting
+    TraceTap *tap;        // verbose transcript only
 
     MB_HD PlanEvaluator(const Tables &t, Scratch<MAXS, MAXL> &s, const X &lanes = X())
-        : T(t), w(s), x(lanes), bs_total(0), nbad(0), aux(0), chain_hint(0) {}
+        : T(t), w(s), x(lanes), bs_total(0), nbad(0), aux(0), chain_hint(0), tap(nullptr) {}
 
     MB_HD int group(int s) const { return 1 << w.gcode[s]; }
     MB_HD int dp_of(int s) const { return (1 << w.gcode[s]) >> w.tpc[s]; }
@@ -1143,6 +1151,7 @@ struct PlanEvaluator {
             const double mc = one_type ? T.type_memory[0] * (double)(1 << g) : memory_capacity(rank_start(s), rank_start(s) + (1 << g));
             w.capa[s] = mc - md;
             w.mstate[s] = err;
+            if (tap) { tap->demand[s] = md; tap->state[s] = mc - md; }
             if (defer && md > mc && mc > 0.0) {              // log2(demand / capacity), rounded up, from the exponents
                 uint64_t bd, bc;
                 memcpy(&bd, &md, 8); memcpy(&bc, &mc, 8);
@@ -1386,6 +1395,7 @@ struct PlanEvaluator {
         const double exec = ((double)(pd.batches - 1) * max_len) + lens_sum.result();   // :235-236
         const double bg = T.p.batch_generator * (double)pd.batches;
         cost_out = exec + fb_sync + max_upd + max_dp + pp_cost + bg;                   // :241-242
+        if (tap) { tap->cost[0] = exec; tap->cost[1] = fb_sync; tap->cost[2] = max_upd; tap->cost[3] = max_dp; tap->cost[4] = pp_cost; }
         return 0;
     }
 

@@ -25,6 +25,7 @@
 
 #include "metis_eval.cuh"
 #include "metis_coop.cuh"
+#include "metis_trace.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -700,6 +701,24 @@ het_detail_kernel(const __grid_constant__ MetisProblem p, const __grid_constant_
     ev.run(pd, sink, (int)picks[i].step);
 }
 
+// verbose transcript: one thread replays one plan and records what the reference prints (metis_trace.cuh)
+__global__ void __launch_bounds__(64)
+het_trace_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
+                 const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob,
+                 const uint32_t *__restrict__ ordinals, long long n, uint64_t *trace, int words) {
+    const Tables T = make_tables(p, lay, blob);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TraceOut out(trace + (size_t)i * words, words);
+    PlanDesc pd;
+    if (decode_plan(sp, ordinals[i], pd)) {
+        Scratch<kMaxS, kMaxL> w;
+        TraceEvaluator<kMaxS, kMaxL> ev(T, w, out);
+        ev.run_traced(pd);
+    }
+    out.finish();
+}
+
 __global__ void __launch_bounds__(kThreads)
 homo_cost_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ BlobLayout lay,
                  const uint8_t *__restrict__ blob, int type_id, const int32_t *__restrict__ plans, long long n,
@@ -1000,6 +1019,26 @@ int metis_het_detail(const MetisProblem *problem, const MetisPlanSpace *space, c
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "het_detail_kernel");
+    return METIS_OK;
+}
+
+int metis_het_trace(const MetisProblem *problem, const MetisPlanSpace *space, const uint32_t *ordinals, int64_t n,
+                    uint64_t *trace, int32_t words_per_plan, void *workspace, int64_t workspace_bytes, void *stream_) {
+    int rc = check_problem(problem);
+    if (rc) return rc;
+    if (!space || !ordinals || !trace || !workspace) return arg_fail("NULL argument");
+    if (words_per_plan < 64) return arg_fail("words_per_plan too small");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const BlobLayout lay = make_layout(*problem);
+    if (workspace_bytes < 256 + kFixedWs + (int64_t)align16(lay.total)) return METIS_E_CAPACITY;
+    const Workspace ws = carve(workspace, lay);
+    pack_tables_kernel<<<8, 256, 0, stream>>>(*problem, lay, ws.blob);
+    if (n > 0) {
+        const unsigned nb = (unsigned)((n + 63) / 64);
+        het_trace_kernel<<<nb, 64, 0, stream>>>(*problem, *space, lay, ws.blob, ordinals, n, trace, words_per_plan);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "het_trace_kernel");
     return METIS_OK;
 }
 

@@ -74,7 +74,7 @@ BLOCK_DTYPE = [('first_ordinal', '<i8'), ('rows_offset', '<i8'), ('num_rows', '<
                ('label_stage', '<i2'), ('num_stage', '<i2'), ('reserved', '<i2', (3,))]
 
 SYMBOLS = ['metis_last_error', 'metis_abi_version', 'metis_set_profile_events', 'metis_het_workspace_bytes', 'metis_het_search',
-           'metis_het_detail', 'metis_homo_cost', 'metis_layer_balance', 'metis_enum_device_groups',
+           'metis_het_detail', 'metis_het_trace', 'metis_homo_cost', 'metis_layer_balance', 'metis_enum_device_groups',
            'metis_enum_device_group_tables', 'metis_sort_workspace_bytes', 'metis_sort_records']
 SORT_POSITION, SORT_RANKED, SORT_BY_COST_STABLE = 0, 1, 2
 
@@ -108,6 +108,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.metis_het_detail.restype = C.c_int
     lib.metis_het_detail.argtypes = [C.POINTER(MetisProblem), C.POINTER(MetisPlanSpace), C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.metis_het_trace.restype = C.c_int
+    lib.metis_het_trace.argtypes = [C.POINTER(MetisProblem), C.POINTER(MetisPlanSpace), C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
     lib.metis_homo_cost.restype = C.c_int
     lib.metis_homo_cost.argtypes = [C.POINTER(MetisProblem), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]

@@ -356,6 +356,58 @@ def golden_homo_workload(w: Workload):
         print(f'{w.name}_homo: yielded={yielded} costed={len(costs)}', file=sys.stderr)
 
 
+def golden_transcript(name: str):
+    """The reference's WHOLE stdout for one configuration (cost_het_cluster.py:53-80, with the per-candidate lines of
+    plan.py / load_balancer.py / cost_estimator.py): the unmodified cost_het_cluster() function driven exactly like the
+    reference's __main__ block, with the profile listing order pinned (Q3) and PYTHONHASHSEED=0 (Q4).  The
+    `search_time:` line is masked.  -> tests/golden/transcript_<name>.txt.gz + .json (flags, node sequences)"""
+    import gzip
+    ref = import_reference()
+    sys.path.insert(0, REF)
+    import cost_het_cluster as ref_main                         # /root/reference/cost_het_cluster.py
+    with tempfile.TemporaryDirectory() as root:
+        if name == 'c1':
+            fix = os.path.join(HERE, 'fixtures', 'c1')
+            order = sorted(os.listdir(os.path.join(fix, 'profile_data_samples')))
+            order = ['DeviceType.A100_tp2_bs2.json'] + [f for f in order if f != 'DeviceType.A100_tp2_bs2.json']
+            argv = C1_FLAGS + ['--hostfile_path', os.path.join(fix, 'hostfile'),
+                               '--clusterfile_path', os.path.join(fix, 'clusterfile.json'),
+                               '--profile_data_path', os.path.join(fix, 'profile_data_samples')]
+            digest = None
+        else:
+            w = WORKLOADS[name]
+            digest = materialize(w, root)
+            order = profile_file_order(w)
+            argv = w.cli_args(root)
+        args, cluster, profile_data, _types, model_config, volume = build_objects(ref, argv, order)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            print(profile_data)
+            estimator = ref['cost_estimator'].HeteroCostEstimator(profile_data, model_config, volume, cluster)
+            balancer = ref['load_balancer'].LayerLoadBalancer(cluster, profile_data, model_config, args.gbs)
+            t0 = time.time()
+            costs = ref_main.cost_het_cluster(args, cluster, profile_data, model_config, estimator, balancer)
+            print(f'search_time: {time.time() - t0}s')
+            print(f'len(costs): {len(costs)}')
+            ranked = sorted(costs, key=lambda kv: kv[6])
+            print('rank, cost, node_sequence, device_groups, strategies(dp_deg, tp_deg), batches(number of batch), layer_partition')
+            for idx, result in enumerate(ranked):
+                print(f'{idx + 1}, {result[6]}, {result[0]}, {result[1]}, {result[2]}, {result[3]}, {result[4]}')
+        text = buf.getvalue()
+        text = '\n'.join('search_time: <masked>' if ln.startswith('search_time: ') else ln for ln in text.split('\n'))
+        gen = ref['plan'].InterStagePlanGenerator(device_types=set(cluster.get_device_types()),
+                                                  num_devices=cluster.get_total_num_devices(), gbs=args.gbs,
+                                                  num_layers=args.num_layers, variance=args.min_group_scale_variance,
+                                                  max_permute_len=args.max_permute_len)
+        names = [[d.name for d in seq] for seq in gen.node_sequences]
+    with gzip.open(os.path.join(HERE, f'transcript_{name}.txt.gz'), 'wt') as fh:
+        fh.write(text)
+    json.dump({'workload': name, 'inputs_sha256': digest, 'file_order': order, 'node_sequences': names,
+               'costs': len(costs), 'lines': text.count('\n')},
+              open(os.path.join(HERE, f'transcript_{name}.json'), 'w'))
+    print(f'transcript_{name}: {len(costs)} costs, {text.count(chr(10))} lines, {len(text)} bytes', file=sys.stderr)
+
+
 def golden_units():
     """Unit-level vectors from reference functions on seeded random inputs."""
     ref = import_reference()
@@ -429,6 +481,8 @@ def main():
             golden_units()
         elif name == 'c1':
             golden_c1(ns.procs)
+        elif name.startswith('transcript:'):
+            golden_transcript(name.split(':', 1)[1])
         elif name.endswith(':homo'):
             golden_homo_workload(WORKLOADS[name.split(':')[0]])
         elif name.endswith(':sample'):

@@ -13,6 +13,7 @@
 
 #include "../../metis_b200/csrc/metis_eval.cuh"
 #include "../../metis_b200/csrc/metis_coop.cuh"
+#include "../../metis_b200/csrc/metis_trace.cuh"
 
 using namespace metis;
 
@@ -148,6 +149,24 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
             CoopEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS, OneLane> ev(T, w, mail, lanes);
             ev.run_chain(pd, sink, skip_first);
         }
+    }
+    return 0;
+}
+
+// the device's trace replay (metis_trace.cuh) on the host: lets the CPU suite check the verbose transcript
+int hostsim_het_trace(const MetisProblem *p, const MetisPlanSpace *sp, const uint32_t *ordinals, int64_t n,
+                      uint64_t *trace, int32_t words) {
+    std::vector<double> dlay;
+    const Tables T = host_tables(*p, dlay);
+    static thread_local Scratch<METIS_MAX_STAGES, METIS_MAX_LAYERS> w;
+    for (int64_t i = 0; i < n; ++i) {
+        TraceOut out(trace + (size_t)i * words, words);
+        PlanDesc pd;
+        if (decode(*sp, ordinals[i], pd)) {
+            TraceEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> ev(T, w, out);
+            ev.run_traced(pd);
+        }
+        out.finish();
     }
     return 0;
 }

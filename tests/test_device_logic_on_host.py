@@ -413,3 +413,51 @@ def test_random_homo_clusters_vs_oracle(tmp_path):
         costed += len(want)
         skipped += counters['keyerr']
     assert costed > 500 and skipped > 0, (costed, skipped)
+
+
+@pytest.mark.parametrize('name', ['c1', 'mix32', 'c2_het16'])
+def test_verbose_transcript_equals_the_reference(name, workload_dir):
+    """every line the reference prints while it searches (inter_stage_plan, invalid / valid
+    strategies, stage performance, each partition attempt with its memory demand and state, re-weighted performance,
+    'data loadbalancer', cost terms, cost / KeyError) - 499 / 10 201 / 32 796 lines captured from the unmodified
+    reference (make_golden.py transcript:<name>) - against metis_b200.verbose.format_plan fed with the device's trace
+    replay (metis_trace.cuh, here in its host build).  Byte for byte."""
+    import ctypes as C
+    import gzip
+    from metis_b200 import api, verbose
+    from metis_b200.arguments import parse_args
+    from metis_b200.utils import DeviceType
+    meta = json.load(open(os.path.join(GOLDEN, f'transcript_{name}.json')))
+    gold = gzip.open(os.path.join(GOLDEN, f'transcript_{name}.txt.gz'), 'rt').read().split('\n')
+    if name == 'c1':
+        root, sub = C1_DIR, 'profile_data_samples'
+        argv = ['--num_layers', '10', '--gbs', '128', '--max_profiled_tp_degree', '4', '--max_profiled_batch_size', '4',
+                '--min_group_scale_variance', '1', '--max_permute_len', '4', '--hidden_size', '4096',
+                '--sequence_length', '1024', '--vocab_size', '51200', '--attention_head_size', '32']
+    else:
+        w, root, digest = workload_dir(name)
+        assert digest == meta['inputs_sha256']
+        sub, argv = 'profile', w.cli_args(root)
+    args = parse_args(argv)
+    cluster, profile, _types, cfg = hs.load_inputs(root, sub, meta['file_order'], args.num_layers, args.hidden_size,
+                                                   args.sequence_length, args.vocab_size)
+    seqs = [tuple(DeviceType[t] for t in seq) for seq in meta['node_sequences']]
+    problem, space, _ = api.het_problem(args, cluster, profile, cfg, None, seqs)
+    keep = dict(problem.arrays)
+    keep.update(blocks=space.blocks, batches=space.batches, rows=space.rows)
+    p = problem.as_struct(lambda n: keep[n].ctypes.data)
+    sp = space.as_struct(lambda n: keep[n].ctypes.data)
+    n, words = space.num_plans, max(256, 64 * (4 * sp.max_stage + 24))
+    ords = np.arange(n, dtype=np.uint32)
+    trace = np.zeros((n, words), dtype=np.uint64)
+    hs.hostsim().hostsim_het_trace(C.byref(p), C.byref(sp), C.c_void_p(ords.ctypes.data), C.c_int64(n),
+                                   C.c_void_p(trace.ctypes.data), C.c_int32(words))
+    lines = []
+    for o in range(n):
+        ns, label, row, batches, codes = space.locate(o)
+        plan = api.InterStagePlan(ns_idx=ns, node_sequence=seqs[ns], dg_idx=row, device_groups=[1 << int(c) for c in codes],
+                                  num_stage=label, batches=batches, gbs=args.gbs)
+        lines += list(verbose.format_plan(trace[o], plan, cluster, args.max_profiled_tp_degree, args.max_profiled_batch_size))
+    end = next(i for i, l in enumerate(gold) if l.startswith('search_time:'))
+    assert len(lines) == end - 1
+    assert lines == gold[1:end]

@@ -575,3 +575,60 @@ def test_c4_whole_space_vs_oracle_on_host_cores(workload_dir):
         assert seen.all() and cands == len(rec) == out.summary['num_records']
         assert (totals['B'], totals['runs'], totals['keyerr']) == \
             (out.summary['num_partition_calls'], out.summary['num_balancer_runs'], out.summary['num_keyerror'])
+
+
+@pytest.mark.parametrize('name', ['c1', 'c2_het16'])
+def test_cli_whole_stdout_equals_the_reference_transcript(name, workload_dir, capsys, monkeypatch):
+    """The drop-in CLI with METIS_VERBOSE=1 against the stdout captured from the unmodified reference
+    (make_golden.py transcript:<name>: print(profile_data), the per-candidate lines of every inter-stage plan,
+    len(costs), the ranked table): every line equal, only `search_time:` masked (cost_het_cluster.py:53-80)."""
+    _gpu()
+    import gzip
+    import cost_het_cluster as cli
+    from metis_b200.utils import DeviceType
+    meta = json.load(open(os.path.join(GOLDEN, f'transcript_{name}.json')))
+    gold = gzip.open(os.path.join(GOLDEN, f'transcript_{name}.txt.gz'), 'rt').read().split('\n')
+    if name == 'c1':
+        argv = ['--model_name', 'GPT', '--model_size', '1.5B', '--num_layers', '10', '--gbs', '128',
+                '--max_profiled_tp_degree', '4', '--max_profiled_batch_size', '4', '--min_group_scale_variance', '1',
+                '--max_permute_len', '4', '--hidden_size', '4096', '--sequence_length', '1024', '--vocab_size', '51200',
+                '--attention_head_size', '32', '--hostfile_path', os.path.join(C1_DIR, 'hostfile'),
+                '--clusterfile_path', os.path.join(C1_DIR, 'clusterfile.json'),
+                '--profile_data_path', os.path.join(C1_DIR, 'profile_data_samples')]
+    else:
+        w, root, digest = workload_dir(name)
+        assert digest == meta['inputs_sha256']
+        argv = w.cli_args(root)
+    monkeypatch.setenv('METIS_VERBOSE', '1')
+    seqs = [tuple(DeviceType[t] for t in seq) for seq in meta['node_sequences']]
+    capsys.readouterr()
+    cli.main(argv, node_sequences=seqs, file_order=meta['file_order'])
+    ours = capsys.readouterr().out.split('\n')
+    ours = ['search_time: <masked>' if ln.startswith('search_time: ') else ln for ln in ours]
+    assert len(ours) == len(gold)
+    for i, (a, b) in enumerate(zip(ours, gold)):
+        assert a == b, f'line {i + 1} differs'
+
+
+@pytest.mark.parametrize('name,fix', [('mix32', ('Q5',)), ('c2_v100', ('Q6',)), ('mix32', ('Q1', 'Q2', 'Q5', 'Q6'))])
+def test_opt_in_corrections_on_gpu_vs_corrected_oracle(name, fix, workload_dir):
+    """SURVEY.md 8(f)-4 through the drop-in API: api.cost_het_cluster(..., corrected=fix) equals the oracle run with
+    the same corrections (never the default; the strict result is the goldens' business) - every tuple, every cost bit;
+    with 'Q5' no partition loses a layer."""
+    _gpu()
+    from metis_b200 import api
+    from oracle import metis_oracle as orc
+    meta, arr, call, seqs = _api_inputs(name, workload_dir)
+    w, root, _ = workload_dir(name)
+    res = api.cost_het_cluster(*call, node_sequences=seqs, device='cuda:0', corrected=fix)
+    ocl = orc.OracleCluster(os.path.join(root, 'hostfile'), os.path.join(root, 'clusterfile.json'), corrected=fix)
+    oprof, _ = orc.load_profile_dir(os.path.join(root, 'profile'), meta['file_order'])
+    omodel = orc.OracleModel(w.num_layers, w.hidden_size, w.sequence_length, w.vocab_size, oprof['model']['parameters'])
+    want, counters = orc.het_search(oprof, ocl, omodel, seqs, w.gbs, w.num_layers, w.variance, w.max_permute_len,
+                                    w.max_tp, w.max_bs, corrected=fix)
+    assert len(res) == len(want) == counters['C']
+    assert res.summary['corrected'] == tuple(sorted(fix))
+    for g, x in zip(res, want):
+        assert g == (x[2], x[3], x[4], x[5], x[6], x[7], x[8])
+    if 'Q5' in fix:
+        assert all(g[4][-1] == w.num_layers for g in res)

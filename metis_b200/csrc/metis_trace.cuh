@@ -160,7 +160,6 @@ struct TraceEvaluator : PlanEvaluator<MAXS, MAXL, Serial, false> {
     // walk itself (including the invalid strategies the reference prints) is replayed by the host from the recorded
     // memory states; the device records only the valid strategies it evaluates.
     MB_HD void run_traced(const PlanDesc &plan) {
-        NullSink sink;
         const int ok = this->begin(plan);
         if (ok < 0) { fatal(METIS_FATAL_SCRATCH); return; }
         if (ok == 0) return;

@@ -276,6 +276,29 @@ int64_t metis_enum_device_group_tables(int32_t first_stage, int32_t last_stage, 
                                        double variance, int32_t max_permute_len, int64_t *rows_per_stage,
                                        uint8_t *out, int64_t capacity_bytes);
 
+/*
+ * Device-side generation of the device-group rows.  The host lists the compositions of every
+ * stage count and merges their groups (search_space/device_group.py:7-81) - thousands of compositions - and the GPU
+ * writes their multiset permutations in the reference's order (search_space/utils.py:72-88), one thread per
+ * composition: millions of rows that never exist on the host or on PCIe.
+ */
+typedef struct MetisCompRec {
+    int64_t row_offset;           /* byte offset of the composition's first row in the row blob               */
+    uint32_t pool_offset;         /* its entry in the pool: num_groups lengths, then `stages` log2 codes of the
+                                     groups in sorted order (utils.py:57)                                     */
+    uint16_t stages;
+    uint16_t num_groups;          /* merged groups (<= METIS_MAX_PERMUTE_GROUPS on the device)                 */
+} MetisCompRec;
+#define METIS_MAX_PERMUTE_GROUPS 32
+/* host: fills recs / pool (call with recs == NULL to size: returns the number of compositions, *pool_bytes the
+ * pool size, *max_groups the largest num_groups); rows_per_stage like metis_enum_device_group_tables */
+int64_t metis_enum_compositions(int32_t first_stage, int32_t last_stage, int32_t num_gpus, double variance,
+                                int32_t max_permute_len, int64_t *rows_per_stage, MetisCompRec *recs,
+                                int64_t recs_capacity, uint8_t *pool, int64_t pool_capacity, int64_t *pool_bytes,
+                                int32_t *max_groups);
+/* device: recs / pool [device], rows [device] receives every row (same layout as metis_enum_device_group_tables) */
+int metis_generate_rows(const MetisCompRec *recs, int64_t num_comps, const uint8_t *pool, uint8_t *rows, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,8 +224,9 @@ class HetSearchResult(Sequence):
 
 def het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer=None,
                 node_sequences: Optional[Sequence[Sequence]] = None, corrected: Sequence[str] = (),
-                rows_out: Optional[np.ndarray] = None):
-    """Flatten the inputs of cost_het_cluster() (order of ``set(device_types)`` = quirk Q4)."""
+                rows_out: Optional[np.ndarray] = None, device_rows: bool = False):
+    """Flatten the inputs of cost_het_cluster() (order of ``set(device_types)`` = quirk Q4).  ``device_rows``: the
+    host lists only the compositions, the GPU writes the device-group rows."""
     if node_sequences is None:
         node_sequences = list(permutations(set(gpu_cluster.get_device_types())))
     norm = layer_load_balancer.norm_layer_duration if layer_load_balancer is not None else None
@@ -234,7 +235,7 @@ def het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balanc
                                     norm, corrected=corrected)
     space = flatten.build_plan_space(len(node_sequences), gpu_cluster.get_total_num_devices(), args.gbs,
                                      args.num_layers, args.min_group_scale_variance, args.max_permute_len,
-                                     corrected=corrected, rows_out=rows_out)
+                                     corrected=corrected, rows_out=rows_out, device_rows=device_rows)
     return problem, space, [tuple(s) for s in node_sequences]
 
 
@@ -294,10 +295,9 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
     dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     dev = search._require_cuda(device)
-    cached = _ENGINES.get((dev.index if dev.index is not None else -1, rank, world))
-    rows_out = cached[0].staging('rows') if cached is not None else None       # enumerate straight into pinned staging
+    # the host lists the compositions (a few thousand records); the rows themselves are written by the GPU
     problem, space, seqs = het_problem(args, gpu_cluster, profile_data, model_config, layer_load_balancer,
-                                       node_sequences, corrected=tuple(corrected), rows_out=rows_out)
+                                       node_sequences, corrected=tuple(corrected), device_rows=True)
     t1 = time.perf_counter()
     stride = 3 * int(space.blocks['num_stage'].max()) + 1
     dp, searcher = _engine(problem, space, dev, rank, world, stride)
@@ -327,7 +327,9 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
         # the reference dies at that plan: nothing is returned (quirk Q8)
         search.raise_fatal(summary, problem)
     t2 = time.perf_counter()
-    cand = search.Candidates(out.records, out.detail, space, seqs, detail_dev=out.detail_dev)
+    # the row blob of the engine is rewritten by the next call: a lazy result keeps its own copy (a few MB, on the GPU)
+    cand = search.Candidates(out.records, out.detail, space, seqs, detail_dev=out.detail_dev,
+                             rows_dev=dp.rows_device().clone())
     result = HetSearchResult(cand, out.rank_order,
                              dict(summary, num_plans=space.num_plans, corrected=tuple(sorted(corrected))))
     result.timings = {'flatten_enumerate_s': t1 - t0, 'gpu_search_s': t2 - t1,

@@ -371,3 +371,67 @@ extern "C" int64_t metis_enum_device_group_tables(int32_t first_stage, int32_t l
     cache.set = TableSet();
     return total_bytes;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Compact form of the same enumeration for DEVICE-side generation of the rows: the host lists
+// the compositions and merges their groups (cheap: thousands of compositions for millions of rows); the
+// permutations - the bulk of the bytes - are written by het_rows_kernel (metis_search.cu), one thread per
+// composition running the same prefix-shift walk as williams_rows above.
+//   recs  [ncomp] MetisCompRec: byte offset of the composition's first row in the row blob, stage count, number of
+//         merged groups, offset of its entry in `pool`
+//   pool  bytes: per composition n group lengths followed by the log2 codes of the groups in SORTED order
+//         (search_space/utils.py:57), `stages` bytes in total
+// Call with recs == NULL to size (returns the number of compositions, *pool_bytes receives the pool size).
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int64_t metis_enum_compositions(int32_t first_stage, int32_t last_stage, int32_t num_gpus, double variance,
+                                           int32_t max_permute_len, int64_t *rows_per_stage, MetisCompRec *recs,
+                                           int64_t recs_capacity, uint8_t *pool, int64_t pool_capacity,
+                                           int64_t *pool_bytes, int32_t *max_groups) {
+    if (first_stage < 1 || last_stage < first_stage || num_gpus < 1 || max_permute_len < 1 || !rows_per_stage || !pool_bytes)
+        return METIS_E_ARG;
+    const int n = last_stage - first_stage + 1;
+    struct Prepared { int first, last, gpus, mpl; double variance; TableSet set; };
+    static thread_local Prepared cache{0, 0, 0, 0, 0.0, {}};
+    const bool hit = cache.first == first_stage && cache.last == last_stage && cache.gpus == num_gpus &&
+                     cache.mpl == max_permute_len && cache.variance == variance && (int)cache.set.tables.size() == n;
+    if (!hit) {
+        cache.first = first_stage; cache.last = last_stage; cache.gpus = num_gpus; cache.mpl = max_permute_len;
+        cache.variance = variance;
+        cache.set.prepare(first_stage, last_stage, num_gpus, variance, max_permute_len);
+    }
+    const TableSet &set = cache.set;
+    int64_t ncomp = 0, pbytes = 0, byte_off = 0;
+    int most = 0;
+    for (int i = 0; i < n; ++i) {
+        const StageTable &t = set.tables[i];
+        rows_per_stage[i] = t.rows();
+        for (size_t c = 0; c < t.merged.size(); ++c) {
+            pbytes += (int64_t)t.merged[c].size() + t.stages;
+            most = std::max(most, (int)t.merged[c].size());
+        }
+        ncomp += (int64_t)t.merged.size();
+    }
+    *pool_bytes = pbytes;
+    if (max_groups) *max_groups = most;
+    if (!recs) return ncomp;
+    if (ncomp > recs_capacity || pbytes > pool_capacity || !pool) return METIS_E_CAPACITY;
+    int64_t k = 0, po = 0;
+    for (int i = 0; i < n; ++i) {
+        const StageTable &t = set.tables[i];
+        for (size_t c = 0; c < t.merged.size(); ++c) {
+            MetisCompRec &r = recs[k++];
+            r.row_offset = byte_off + t.offset[c] * t.stages;
+            r.pool_offset = (uint32_t)po;
+            r.stages = (uint16_t)t.stages;
+            r.num_groups = (uint16_t)t.merged[c].size();
+            for (const Group &g : t.merged[c]) pool[po++] = (uint8_t)g.size();
+            for (const Group &g : t.merged[c])
+                for (int v : g) pool[po++] = ilog2(v);
+        }
+        byte_off += t.rows() * t.stages;
+    }
+    cache.first = cache.last = 0;
+    cache.set = TableSet();
+    return ncomp;
+}

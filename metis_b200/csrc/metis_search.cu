@@ -26,6 +26,7 @@
 #include "metis_eval.cuh"
 #include "metis_coop.cuh"
 #include "metis_trace.cuh"
+#include "metis_rows.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -757,6 +758,14 @@ layer_balance_kernel(const double *__restrict__ capa, const int32_t *__restrict_
     for (int s = 0; s <= S; ++s) out[s] = w.part[s];
 }
 
+// one thread per composition writes its rows straight into the row blob in HBM (metis_rows.cuh)
+__global__ void __launch_bounds__(128)
+het_rows_kernel(const MetisCompRec *__restrict__ recs, long long ncomp, const uint8_t *__restrict__ pool,
+                uint8_t *__restrict__ rows) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncomp) write_composition_rows(recs[c], pool, rows);
+}
+
 __global__ void divide_by_seven_kernel(const double *lc, int n, double *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = lc[i] / 7.0;
@@ -906,6 +915,11 @@ static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg,
     auto first = het_first_kernel<MAXS, MAXL, ONE>;
     int first_smem_tables = (int)lay.total <= blob_max && blob_pad <= (unsigned int)smem_optin;
     size_t first_dyn = first_smem_tables ? blob_pad : 0;
+    first_dyn += (size_t)env_int("METIS_FIRST_SMEM_PAD", 0, 128 * 1024, 0);       // developer knob (L1 / shared split)
+    {
+        const int carve = env_int("METIS_FIRST_CARVEOUT", 0, 100, -1);
+        if (carve >= 0) cudaFuncSetAttribute(first, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
     if (first_dyn > 48 * 1024) {
         e = cudaFuncSetAttribute(first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_dyn);
         if (e != cudaSuccess) { cudaGetLastError(); first_smem_tables = 0; first_dyn = 0; }
@@ -1039,6 +1053,17 @@ int metis_het_trace(const MetisProblem *problem, const MetisPlanSpace *space, co
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "het_trace_kernel");
+    return METIS_OK;
+}
+
+int metis_generate_rows(const MetisCompRec *recs, int64_t num_comps, const uint8_t *pool, uint8_t *rows, void *stream_) {
+    if (num_comps < 0 || (num_comps > 0 && (!recs || !pool || !rows))) return arg_fail("NULL argument");
+    if (num_comps > 0) {
+        const unsigned nb = (unsigned)((num_comps + 127) / 128);
+        het_rows_kernel<<<nb, 128, 0, static_cast<cudaStream_t>(stream_)>>>(recs, (long long)num_comps, pool, rows);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "het_rows_kernel");
     return METIS_OK;
 }
 

@@ -260,11 +260,14 @@ class FlatPlanSpace:
     batches: np.ndarray           # int32, divisors of gbs descending
     rows: np.ndarray              # uint8 blob of all row tables
     tables: Dict[int, Tuple[int, np.ndarray]] = field(default_factory=dict)   # S -> (byte offset, rows)
+    rows_total_bytes: int = -1    # device_rows spaces: size of the row blob the GPU writes (rows stays empty)
+    comp_recs: Optional[np.ndarray] = None     # native.COMP_DTYPE, device_rows spaces
+    comp_pool: Optional[np.ndarray] = None
 
     def as_struct(self, ptr_of: Callable[[str], int]) -> native.MetisPlanSpace:
         s = native.MetisPlanSpace()
         s.num_plans = self.num_plans
-        s.rows_bytes = int(self.rows.size)
+        s.rows_bytes = int(self.rows_total_bytes if self.rows_total_bytes >= 0 else self.rows.size)
         s.num_blocks = len(self.blocks)
         s.num_div = len(self.batches)
         s.max_stage = int(self.blocks['num_stage'].max()) if len(self.blocks) else 1
@@ -284,85 +287,139 @@ class FlatPlanSpace:
         return int(blk['ns_idx']), int(blk['label_stage']), row, int(self.batches[div]), table[row]
 
 
-def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_layers: int, variance,
-                     max_permute_len: int, lib=None, rows_out: Optional[np.ndarray] = None,
-                     corrected: Sequence[str] = ()) -> FlatPlanSpace:
-    """Block structure of InterStagePlanGenerator.__next__ (search_space/plan.py:153-175),
-    including the mislabelled num_stage=1 block of every later node sequence (quirk Q1).  With 'Q1' in
-    ``corrected`` (opt-in) every node sequence starts with the real one-stage rows, like the first one."""
-    cap = min(num_devices, num_layers)
-    lib = lib or native.load_library()
-    cache: Dict[int, np.ndarray] = enumerate_device_group_tables(1, cap + 1, num_devices, variance, max_permute_len, lib,
-                                                                 rows_out)
-    blob_all = cache.pop(0)
-    in_blob = {id(v) for v in cache.values()}
-
-    def rows_of(stages: int) -> np.ndarray:
-        if stages not in cache:
-            cache[stages] = enumerate_device_groups(stages, num_devices, variance, max_permute_len, lib)
-        return cache[stages]
-
-    def next_stage(start: int) -> Tuple[int, np.ndarray]:      # plan.py:130-142
+def _walk_blocks(num_node_sequences: int, cap: int, nrows_of: Callable[[int], int],
+                 corrected: Sequence[str]) -> List[Tuple[int, int, int]]:
+    """The (ns_idx, label, stage count) blocks in the order of InterStagePlanGenerator.__next__
+    (search_space/plan.py:153-175), including the mislabelled num_stage=1 block of every later node sequence
+    (quirk Q1; with 'Q1' in ``corrected`` every node sequence starts with the real one-stage rows)."""
+    def next_stage(start: int) -> int:                         # plan.py:130-142
         s = start
-        while True:
-            r = rows_of(s)
-            if len(r) or s > cap:
-                return s, r
+        while nrows_of(s) == 0 and s <= cap:
             s += 1
+        return s
 
-    batches = [b for b in range(gbs, 0, -1) if gbs % b == 0]   # plan.py:120-124
-    plan_blocks: List[Tuple[int, int, np.ndarray]] = []
-    ns, label, rows = 0, 1, rows_of(1)
-    if not len(rows):
+    if nrows_of(1) == 0:
         raise IndexError('list index out of range')            # plan.py:117-118
+    out: List[Tuple[int, int, int]] = []
+    ns, label, stages = 0, 1, 1
     while True:
-        plan_blocks.append((ns, label, rows))
-        s, r = next_stage(label + 1)
+        out.append((ns, label, stages))
+        s = next_stage(label + 1)
         if s > cap:
             ns += 1
             if ns >= num_node_sequences:
                 break
             if 'Q1' in corrected:
-                label, rows = 1, rows_of(1)
+                label, stages = 1, 1
             else:
-                label, (_, rows) = 1, next_stage(2)            # plan.py:144-148 (Q1)
-            if not len(rows):
+                label, stages = 1, next_stage(2)               # plan.py:144-148 (Q1)
+            if nrows_of(stages) == 0:
                 raise IndexError('list index out of range')    # plan.py:173
         else:
-            label, rows = s, r
+            label, stages = s, s
+    return out
 
-    tables: Dict[int, Tuple[int, np.ndarray]] = {}
-    chunks, offset = [], 0
-    # fast path: every table is a view into the blob of the one library call -> ship that blob as is
-    base = blob_all
-    shared = all(id(r) in in_blob for _, _, r in plan_blocks)
-    for _, _, rows in plan_blocks:
-        stages = rows.shape[1]
-        if stages not in tables:
-            if shared:
-                tables[stages] = (rows.__array_interface__['data'][0] - base.__array_interface__['data'][0], rows)
-                continue
-            tables[stages] = (offset, rows)
-            chunks.append(rows.reshape(-1))
-            offset += rows.size
+
+def _blocks_array(plan_blocks, nrows_of, offset_of, ndiv: int) -> Tuple[np.ndarray, int]:
     blocks = np.zeros(len(plan_blocks), dtype=native.BLOCK_DTYPE)
     ordinal = 0
-    for i, (ns_idx, label, rows) in enumerate(plan_blocks):
+    for i, (ns_idx, label, stages) in enumerate(plan_blocks):
         blocks[i]['first_ordinal'] = ordinal
-        blocks[i]['rows_offset'] = tables[rows.shape[1]][0]
-        blocks[i]['num_rows'] = len(rows)
+        blocks[i]['rows_offset'] = offset_of(stages)
+        blocks[i]['num_rows'] = nrows_of(stages)
         blocks[i]['ns_idx'] = ns_idx
         blocks[i]['label_stage'] = label
-        blocks[i]['num_stage'] = rows.shape[1]
-        ordinal += len(rows) * len(batches)
-    if shared:
-        blob = base
-    else:
-        blob = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)
-        if blob.size % 16:
-            blob = np.concatenate([blob, np.zeros(16 - blob.size % 16, dtype=np.uint8)])
+        blocks[i]['num_stage'] = stages
+        ordinal += nrows_of(stages) * ndiv
+    return blocks, ordinal
+
+
+def build_plan_space(num_node_sequences: int, num_devices: int, gbs: int, num_layers: int, variance,
+                     max_permute_len: int, lib=None, rows_out: Optional[np.ndarray] = None,
+                     corrected: Sequence[str] = (), device_rows: bool = False) -> FlatPlanSpace:
+    """The candidate space of one search.  ``device_rows``: the host only lists the compositions
+    (``comp_recs`` / ``comp_pool``) and the GPU writes the rows (metis_generate_rows); ``rows`` stays empty and
+    ``tables`` is filled by the host enumerator only if somebody asks for it."""
+    cap = min(num_devices, num_layers)
+    lib = lib or native.load_library()
+    batches = [b for b in range(gbs, 0, -1) if gbs % b == 0]   # plan.py:120-124
+    if device_rows:
+        counts, recs, pool, most = enumerate_compositions(1, cap + 1, num_devices, variance, max_permute_len, lib)
+        if most <= native.METIS_MAX_PERMUTE_GROUPS:
+            offsets, off = {}, 0
+            for stages in range(1, cap + 2):
+                offsets[stages] = off
+                off += int(counts[stages - 1]) * stages
+            nrows_of = lambda st: int(counts[st - 1]) if 1 <= st <= cap + 1 else 0     # noqa: E731
+            plan_blocks = _walk_blocks(num_node_sequences, cap, nrows_of, corrected)
+            blocks, total = _blocks_array(plan_blocks, nrows_of, lambda st: offsets[st], len(batches))
+            if off > 0xFFFFFFFF or total > 0xFFFFFFF0:
+                raise NotImplementedError('device-group tables of 4 GiB or more / more than 2^32 plans are not supported')
+            space = FlatPlanSpace(total, blocks, np.asarray(batches, dtype=np.int32), np.zeros(0, dtype=np.uint8))
+            space.rows_total_bytes = off
+            space.comp_recs, space.comp_pool = recs, pool
+            space.tables = _LazyTables(cap, num_devices, variance, max_permute_len)
+            return space
+        # a composition with more merged groups than the device kernel handles: enumerate on the host
+    cache: Dict[int, np.ndarray] = enumerate_device_group_tables(1, cap + 1, num_devices, variance, max_permute_len, lib,
+                                                                 rows_out)
+    blob = cache.pop(0)
+    base_addr = blob.__array_interface__['data'][0]
+    nrows_of = lambda st: len(cache[st]) if st in cache else 0                           # noqa: E731
+    offset_of = lambda st: cache[st].__array_interface__['data'][0] - base_addr         # noqa: E731
+    plan_blocks = _walk_blocks(num_node_sequences, cap, nrows_of, corrected)
+    blocks, total = _blocks_array(plan_blocks, nrows_of, offset_of, len(batches))
+    tables = {st: (offset_of(st), cache[st]) for _, _, st in plan_blocks}
     if blob.size > 0xFFFFFFFF:                               # list entries address a row with 32 bits
         raise NotImplementedError('device-group tables of 4 GiB or more are not supported')
-    if ordinal > 0xFFFFFFF0:
+    if total > 0xFFFFFFF0:
         raise NotImplementedError('more than 2^32 inter-stage plans')
-    return FlatPlanSpace(ordinal, blocks, np.asarray(batches, dtype=np.int32), blob, tables)
+    return FlatPlanSpace(total, blocks, np.asarray(batches, dtype=np.int32), blob, tables)
+
+
+class _LazyTables(dict):
+    """S -> (byte offset, rows): filled by the host enumerator on first use (device_rows spaces)."""
+
+    def __init__(self, cap, num_devices, variance, max_permute_len):
+        super().__init__()
+        self._args = (cap, num_devices, variance, max_permute_len)
+        self._done = False
+
+    def _fill(self):
+        if not self._done:
+            cap, num_devices, variance, mpl = self._args
+            cache = enumerate_device_group_tables(1, cap + 1, num_devices, variance, mpl)
+            blob = cache.pop(0)
+            base = blob.__array_interface__['data'][0]
+            for st, rows in cache.items():
+                dict.__setitem__(self, st, (rows.__array_interface__['data'][0] - base, rows))
+            self._done = True
+
+    def __getitem__(self, key):
+        self._fill()
+        return dict.__getitem__(self, key)
+
+    def __contains__(self, key):
+        self._fill()
+        return dict.__contains__(self, key)
+
+
+def enumerate_compositions(first_stage: int, last_stage: int, num_gpus: int, variance, max_permute_len: int, lib=None):
+    """metis_enum_compositions: (rows per stage count, MetisCompRec array, pool bytes, largest number of merged groups)."""
+    import ctypes as C
+    lib = lib or native.load_library()
+    n = last_stage - first_stage + 1
+    counts = np.zeros(n, dtype=np.int64)
+    pool_bytes, most = C.c_int64(0), C.c_int32(0)
+    ncomp = lib.metis_enum_compositions(first_stage, last_stage, num_gpus, float(variance), max_permute_len,
+                                        counts.ctypes.data, None, 0, None, 0, C.byref(pool_bytes), C.byref(most))
+    if ncomp < 0:
+        raise native.MetisNativeError(f'metis_enum_compositions failed ({ncomp})')
+    recs = np.zeros(max(int(ncomp), 1), dtype=native.COMP_DTYPE)
+    pool = np.zeros(max(int(pool_bytes.value), 16), dtype=np.uint8)
+    got = lib.metis_enum_compositions(first_stage, last_stage, num_gpus, float(variance), max_permute_len,
+                                      counts.ctypes.data, recs.ctypes.data, int(ncomp), pool.ctypes.data,
+                                      int(pool_bytes.value), C.byref(pool_bytes), C.byref(most))
+    if got != ncomp:
+        raise native.MetisNativeError('metis_enum_compositions: inconsistent count')
+    return counts, recs[:int(ncomp)], pool, int(most.value)

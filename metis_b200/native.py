@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'libmetis_b200.so')
 METIS_MAX_TYPES = 8
 METIS_MAX_STAGES = 128
 METIS_MAX_LAYERS = 256
+METIS_MAX_PERMUTE_GROUPS = 32
 DETAIL_STRIDE = 3 * METIS_MAX_STAGES + 1
 
 FATAL_NAMES = {1: 'KEY_EXEC', 2: 'KEY_MEMORY', 3: 'INDEX', 4: 'HANG', 5: 'SCRATCH', 6: 'ZERODIV'}
@@ -73,9 +74,12 @@ RECORD_DTYPE = [('cost', '<f8'), ('ordinal', '<u4'), ('step', '<u2'), ('num_repa
 BLOCK_DTYPE = [('first_ordinal', '<i8'), ('rows_offset', '<i8'), ('num_rows', '<i4'), ('ns_idx', '<i2'),
                ('label_stage', '<i2'), ('num_stage', '<i2'), ('reserved', '<i2', (3,))]
 
+COMP_DTYPE = [('row_offset', '<i8'), ('pool_offset', '<u4'), ('stages', '<u2'), ('num_groups', '<u2')]
+
 SYMBOLS = ['metis_last_error', 'metis_abi_version', 'metis_set_profile_events', 'metis_het_workspace_bytes', 'metis_het_search',
            'metis_het_detail', 'metis_het_trace', 'metis_homo_cost', 'metis_layer_balance', 'metis_enum_device_groups',
-           'metis_enum_device_group_tables', 'metis_sort_workspace_bytes', 'metis_sort_records']
+           'metis_enum_device_group_tables', 'metis_sort_workspace_bytes', 'metis_sort_records',
+           'metis_enum_compositions', 'metis_generate_rows']
 SORT_POSITION, SORT_RANKED, SORT_BY_COST_STABLE = 0, 1, 2
 
 _lib = None
@@ -122,6 +126,11 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.metis_enum_device_group_tables.restype = C.c_int64
     lib.metis_enum_device_group_tables.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p,
                                                    C.c_void_p, C.c_int64]
+    lib.metis_enum_compositions.restype = C.c_int64
+    lib.metis_enum_compositions.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.metis_generate_rows.restype = C.c_int
+    lib.metis_generate_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.metis_sort_workspace_bytes.restype = C.c_int64
     lib.metis_sort_workspace_bytes.argtypes = [C.c_int64]
     lib.metis_sort_records.restype = C.c_int

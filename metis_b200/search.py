@@ -29,7 +29,10 @@ def _align(n: int, a: int = 256) -> int:
 
 _PROBLEM_ARRAYS = ('key_index', 'layer_compute', 'layer_memory', 'exec_full', 'fb_sync', 'norm_lc', 'type_memory',
                    'type_bw_first', 'type_bw_min', 'ns_run_type', 'ns_run_end', 'ns_q10_end')
-_ARENA_ORDER = _PROBLEM_ARRAYS + ('blocks', 'batches', 'rows')
+# 'rows' is last: spaces whose rows the GPU writes itself (flatten.build_plan_space(device_rows=True)) upload
+# everything before it - the composition list instead of the rows - and fill it with metis_generate_rows
+_ARENA_ORDER = _PROBLEM_ARRAYS + ('blocks', 'batches', 'comp_recs', 'comp_pool', 'rows')
+_EMPTY = np.zeros(0, dtype=np.uint8)
 
 
 class DeviceProblem:
@@ -46,42 +49,52 @@ class DeviceProblem:
         self._host = self._dev = None
         self._off: Dict[str, Tuple[int, int]] = {}           # name -> (offset, capacity)
         self._used: Dict[str, int] = {}
-        self._allocate(self._arrays(problem, space), rows_capacity)
+        self._allocate(self._arrays(problem, space), space, rows_capacity)
         self.reload(problem, space)
         self.upload()
 
     @staticmethod
     def _arrays(problem: flatten.FlatProblem, space: flatten.FlatPlanSpace) -> Dict[str, np.ndarray]:
         arrays = {k: problem.arrays[k] for k in _PROBLEM_ARRAYS}
-        arrays.update(blocks=space.blocks.view(np.uint8).reshape(-1), batches=space.batches, rows=space.rows)
+        arrays.update(blocks=space.blocks.view(np.uint8).reshape(-1), batches=space.batches, rows=space.rows,
+                      comp_recs=space.comp_recs.view(np.uint8).reshape(-1) if space.comp_recs is not None else _EMPTY,
+                      comp_pool=space.comp_pool if space.comp_pool is not None else _EMPTY)
         return {k: np.ascontiguousarray(v).view(np.uint8).reshape(-1) for k, v in arrays.items()}
 
-    def _allocate(self, flat: Dict[str, np.ndarray], rows_capacity: int) -> None:
-        off = 0
+    @staticmethod
+    def _need(flat: Dict[str, np.ndarray], space: flatten.FlatPlanSpace, name: str) -> int:
+        if name == 'rows' and space.comp_recs is not None:
+            return int(space.rows_total_bytes)               # written by the GPU, never staged on the host
+        return int(flat[name].size)
+
+    def _allocate(self, flat: Dict[str, np.ndarray], space: flatten.FlatPlanSpace, rows_capacity: int) -> None:
+        off = host_bytes = 0
         self._off = {}
         for name in _ARENA_ORDER:
-            need = max(int(flat[name].size), 16)
-            cap = _align(need + need // 4 if name in ('rows', 'blocks') else need)
+            need = max(self._need(flat, space, name), 16)
+            cap = _align(need + need // 4 if name in ('rows', 'blocks', 'comp_recs', 'comp_pool') else need)
             if name == 'rows':
                 cap = max(cap, _align(rows_capacity))
+                host_bytes = off + (16 if space.comp_recs is not None and not rows_capacity else cap)
             self._off[name] = (off, cap)
             off += cap
-        host = torch.zeros(off, dtype=torch.uint8)
+        host = torch.zeros(host_bytes, dtype=torch.uint8)
         self._host = host.pin_memory() if self.pinned else host
         with torch.cuda.device(self.device):
             self._dev = torch.zeros(off, dtype=torch.uint8, device=self.device)
 
     def fits(self, problem: flatten.FlatProblem, space: flatten.FlatPlanSpace) -> bool:
         flat = self._arrays(problem, space)
-        return all(flat[n].size <= self._off[n][1] for n in _ARENA_ORDER)
+        return (all(self._need(flat, space, n) <= self._off[n][1] for n in _ARENA_ORDER)
+                and self._off['rows'][0] + flat['rows'].size <= self._host.numel())
 
     def reload(self, problem: flatten.FlatProblem, space: flatten.FlatPlanSpace) -> None:
         """Stage another problem / space (host side only; call upload()).  Tables that already live in the staging
         arena (``build_plan_space(rows_out=staging('rows'))``) are not copied again."""
         flat = self._arrays(problem, space)
-        if not all(flat[n].size <= self._off[n][1] for n in _ARENA_ORDER):
+        if not self.fits(problem, space):
             keep = {n: flat[n].copy() for n in _ARENA_ORDER}     # a view into the old arena must survive the swap
-            self._allocate(keep, 0)
+            self._allocate(keep, space, 0)
             flat = keep
         host = self._host.numpy()
         for name in _ARENA_ORDER:
@@ -95,7 +108,8 @@ class DeviceProblem:
         base = self._dev.data_ptr()
         self.p_struct = problem.as_struct(lambda n: base + self._off[n][0])
         self.s_struct = space.as_struct(lambda n: base + self._off[n][0])
-        self.h2d_bytes = self._off['rows'][0] + self._used['rows']
+        self.device_rows = space.comp_recs is not None
+        self.h2d_bytes = self._off['rows'][0] + self._used['rows']          # device_rows: nothing of 'rows'
 
     def staging(self, name: str) -> np.ndarray:
         """The pinned host region of one table (numpy view, full capacity): fill it in place, then upload()."""
@@ -111,6 +125,20 @@ class DeviceProblem:
         n = self.h2d_bytes
         with torch.cuda.device(self.device), torch.cuda.stream(stream or torch.cuda.current_stream(self.device)):
             self._dev[:n].copy_(self._host[:n], non_blocking=True)
+            if self.device_rows:                              # the GPU writes the rows itself
+                base = self._dev.data_ptr()
+                s = torch.cuda.current_stream(self.device)
+                rc = self.lib.metis_generate_rows(C.c_void_p(base + self._off['comp_recs'][0]),
+                                                  C.c_int64(len(self.space.comp_recs)),
+                                                  C.c_void_p(base + self._off['comp_pool'][0]),
+                                                  C.c_void_p(base + self._off['rows'][0]), C.c_void_p(s.cuda_stream))
+                native.check(rc, 'metis_generate_rows')
+
+    def rows_device(self) -> torch.Tensor:
+        """The row blob in HBM (uint8 view; MetisPlanBlock.rows_offset addresses it)."""
+        off = self._off['rows'][0]
+        n = int(self.space.rows_total_bytes) if self.device_rows else self._used['rows']
+        return self._dev[off:off + n]
 
     def workspace_bytes(self, num_plans: int) -> int:
         n = self.lib.metis_het_workspace_bytes(C.byref(self.p_struct), num_plans, self.s_struct.max_stage)
@@ -309,12 +337,16 @@ class Candidates:
     _BULK = 4096
 
     def __init__(self, records: np.ndarray, detail: Optional[np.ndarray], space: flatten.FlatPlanSpace,
-                 node_sequences: Sequence[Tuple], detail_dev: Optional[torch.Tensor] = None):
+                 node_sequences: Sequence[Tuple], detail_dev: Optional[torch.Tensor] = None,
+                 rows_dev: Optional[torch.Tensor] = None):
         self.records = records
         self.space = space
         self.node_sequences = [tuple(s) for s in node_sequences]
         self._detail = detail
         self._detail_dev = detail_dev
+        # device-group rows: the blob the GPU wrote (``rows_dev``) or the host enumerator's
+        self._rows_dev = rows_dev
+        self._rows = None if rows_dev is not None else space.rows
         self.cost = records['cost']
 
     def columns(self, idx=None) -> Dict[str, np.ndarray]:
@@ -326,9 +358,24 @@ class Candidates:
             else np.zeros(0, dtype=np.int64)
         rel = ordinal - blocks['first_ordinal'][blk]
         ndiv = len(self.space.batches)
-        return dict(row=rel // ndiv, batches=self.space.batches[rel % ndiv].astype(np.int64),
-                    ns_idx=blocks['ns_idx'][blk].astype(np.int64), num_stage=blocks['num_stage'][blk].astype(np.int64),
+        row, stages = rel // ndiv, blocks['num_stage'][blk].astype(np.int64)
+        return dict(row=row, batches=self.space.batches[rel % ndiv].astype(np.int64),
+                    ns_idx=blocks['ns_idx'][blk].astype(np.int64), num_stage=stages,
+                    row_byte=blocks['rows_offset'][blk].astype(np.int64) + row * stages,
                     num_repartition=rec['num_repartition'].astype(np.int64))
+
+    def group_codes(self, row_byte: np.ndarray, stages: np.ndarray) -> np.ndarray:
+        """log2(device count) of every stage, uint8 [n, max stages] (columns past a row's stage count are junk)."""
+        width = int(stages.max())
+        at = row_byte[:, None] + np.arange(width, dtype=np.int64)[None, :]
+        if self._rows is None:
+            if len(row_byte) > self._BULK:
+                self._rows = self._rows_dev.cpu().numpy()
+                self._rows_dev = None
+            else:
+                sel = torch.from_numpy(np.minimum(at, self._rows_dev.numel() - 1)).to(self._rows_dev.device)
+                return self._rows_dev[sel].cpu().numpy()
+        return self._rows[np.minimum(at, len(self._rows) - 1)]
 
     def __len__(self) -> int:
         return len(self.records)
@@ -354,12 +401,11 @@ class Candidates:
         col = self.columns(idx)
         cost = self.cost[idx]
         out = []
-        tables = self.space.tables
+        codes = self.group_codes(col['row_byte'], col['num_stage'])
         for k in range(len(idx)):
             S = int(col['num_stage'][k])
             d = det[k]
-            codes = tables[S][1][int(col['row'][k])]
-            groups = (1 << codes.astype(np.int64)).tolist()
+            groups = (1 << codes[k, :S].astype(np.int64)).tolist()
             dp = (1 << d[:S].astype(np.int64)).tolist()
             tp = (1 << d[S:2 * S].astype(np.int64)).tolist()
             part = d[2 * S:3 * S + 1].astype(np.int64).tolist()

@@ -14,6 +14,7 @@
 #include "../../metis_b200/csrc/metis_eval.cuh"
 #include "../../metis_b200/csrc/metis_coop.cuh"
 #include "../../metis_b200/csrc/metis_trace.cuh"
+#include "../../metis_b200/csrc/metis_rows.cuh"
 
 using namespace metis;
 
@@ -168,6 +169,12 @@ int hostsim_het_trace(const MetisProblem *p, const MetisPlanSpace *sp, const uin
         }
         out.finish();
     }
+    return 0;
+}
+
+// the row generator of SURVEY.md 8(f)-1 (metis_rows.cuh) on the host, composition by composition
+int hostsim_generate_rows(const MetisCompRec *recs, int64_t ncomp, const uint8_t *pool, uint8_t *rows) {
+    for (int64_t c = 0; c < ncomp; ++c) write_composition_rows(recs[c], pool, rows);
     return 0;
 }
 

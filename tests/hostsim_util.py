@@ -26,6 +26,8 @@ def hostsim():
     if _lib is None:
         deps = [SRC, os.path.join(HERE, '..', 'metis_b200', 'csrc', 'metis_eval.cuh'),
                 os.path.join(HERE, '..', 'metis_b200', 'csrc', 'metis_coop.cuh'),
+                os.path.join(HERE, '..', 'metis_b200', 'csrc', 'metis_trace.cuh'),
+                os.path.join(HERE, '..', 'metis_b200', 'csrc', 'metis_rows.cuh'),
                 os.path.join(HERE, '..', 'include', 'metis_b200.h')]
         if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
             os.makedirs(os.path.dirname(OUT), exist_ok=True)

@@ -314,3 +314,30 @@ def test_opt_in_strict_cluster_files(tmp_path):
     cl.write_text(json.dumps(nodes))
     with pytest.raises(ValueError, match="unknown instance_type 'MI300'"):
         GPUCluster(str(host), str(cl), strict=True)
+
+
+@pytest.mark.parametrize('ndev,var,mpl', [(8, 0.5, 4), (16, 1, 6), (32, 0.5, 6), (32, 0, 4), (64, 1, 4), (64, 0.5, 6),
+                                          (16, 0.5, 2), (128, 0, 4)])
+def test_row_generator_writes_the_host_enumerators_rows(ndev, var, mpl):
+    """compositions listed by the host + the per-composition prefix-shift walk of metis_rows.cuh
+    (the code of het_rows_kernel, built for the host) = the row blob of the host enumerator, byte for byte."""
+    import ctypes as C
+    import hostsim_util as hs
+    from metis_b200 import flatten
+    L = 24
+    host = flatten.build_plan_space(2, ndev, 64, L, var, mpl)
+    dev = flatten.build_plan_space(2, ndev, 64, L, var, mpl, device_rows=True)
+    assert dev.comp_recs is not None and dev.rows.size == 0
+    assert dev.num_plans == host.num_plans
+    assert dev.blocks.tobytes() == host.blocks.tobytes()
+    rows = np.full(dev.rows_total_bytes + 16, 0xEE, dtype=np.uint8)
+    hs.hostsim().hostsim_generate_rows(C.c_void_p(dev.comp_recs.ctypes.data), C.c_int64(len(dev.comp_recs)),
+                                       C.c_void_p(dev.comp_pool.ctypes.data), C.c_void_p(rows.ctypes.data))
+    used = max(int(b['rows_offset']) + int(b['num_rows']) * int(b['num_stage']) for b in host.blocks)
+    assert dev.rows_total_bytes >= used
+    assert rows[:dev.rows_total_bytes].tobytes() == host.rows[:dev.rows_total_bytes].tobytes()
+    assert (rows[dev.rows_total_bytes:] == 0xEE).all()
+    # the lazily filled host tables of a device-rows space describe the same rows
+    for b in host.blocks:
+        st = int(b['num_stage'])
+        assert dev.tables[st][0] == host.tables[st][0] and np.array_equal(dev.tables[st][1], host.tables[st][1])

@@ -632,3 +632,51 @@ def test_opt_in_corrections_on_gpu_vs_corrected_oracle(name, fix, workload_dir):
         assert g == (x[2], x[3], x[4], x[5], x[6], x[7], x[8])
     if 'Q5' in fix:
         assert all(g[4][-1] == w.num_layers for g in res)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device-group rows written by the GPU (het_rows_kernel) = the host enumerator's rows
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('ndev,var,mpl', [(8, 0.5, 4), (16, 1, 6), (32, 0.5, 6), (32, 0, 4), (64, 1, 4), (64, 0.5, 6),
+                                          (128, 1, 6), (128, 0, 4), (256, 0, 4)])
+def test_rows_written_by_the_gpu_equal_the_host_enumerators(ndev, var, mpl, workload_dir):
+    _gpu()
+    from metis_b200 import flatten, search
+    w, root, _ = workload_dir('sweep_n8_t1')          # any problem: only the candidate space matters here
+    cluster, profile, _, cfg = _inputs(root, 'profile', None, w.num_layers, w.hidden_size, w.sequence_length, w.vocab_size)
+    seqs = [tuple(w.device_types())]
+    problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
+    L = 96
+    host = flatten.build_plan_space(2, ndev, 64, L, var, mpl)
+    dev = flatten.build_plan_space(2, ndev, 64, L, var, mpl, device_rows=True)
+    assert dev.comp_recs is not None and dev.rows.size == 0
+    assert dev.num_plans == host.num_plans and dev.blocks.tobytes() == host.blocks.tobytes()
+    dp = search.DeviceProblem(problem, dev, 'cuda:0')
+    assert dp.h2d_bytes < 64 * 1024 + dev.comp_recs.nbytes + dev.comp_pool.nbytes + 4096      # no rows uploaded
+    got = dp.rows_device().cpu().numpy()
+    assert got.tobytes() == host.rows[:dev.rows_total_bytes].tobytes()
+    # a second upload into the same arena (engine reuse) rewrites the same bytes
+    dp.reload(problem, dev)
+    dp.upload()
+    assert dp.rows_device().cpu().numpy().tobytes() == got.tobytes()
+
+
+@pytest.mark.parametrize('name', ['mix32', 'c3_homo64_mpl4'])
+def test_search_over_gpu_written_rows_gives_the_same_records(name, workload_dir):
+    _gpu()
+    from metis_b200 import flatten, search
+    from metis_b200.workloads import profile_file_order
+    w, root, _ = workload_dir(name)
+    cluster, profile, _, cfg = _inputs(root, 'profile', profile_file_order(w), w.num_layers, w.hidden_size,
+                                       w.sequence_length, w.vocab_size)
+    seqs = list(itertools.permutations(w.device_types()))
+    problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
+    outs = []
+    for device_rows in (False, True):
+        space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance,
+                                         w.max_permute_len, device_rows=device_rows)
+        dp = search.DeviceProblem(problem, space, 'cuda:0')
+        outs.append(search.HetSearcher(dp, want_records=True, want_detail=True).run())
+    a, b = outs
+    assert len(a.records) > 0 and a.records.tobytes() == b.records.tobytes()
+    assert a.detail.tobytes() == b.detail.tobytes()

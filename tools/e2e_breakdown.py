@@ -26,7 +26,9 @@ cfg = ModelConfig('SYN', w.num_layers, w.sequence_length, w.vocab_size, w.hidden
 seqs = list(itertools.permutations(w.device_types()))
 problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
 ndev = cluster.get_total_num_devices()
-space = flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len)
+DEVICE_ROWS = os.environ.get('METIS_HOST_ROWS', '') in ('', '0')      # default: the GPU writes the rows (8(f)-1)
+space = flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len,
+                                 device_rows=DEVICE_ROWS)
 dp = search.DeviceProblem(problem, space, 'cuda:0')
 full = search.HetSearcher(dp, want_records=True)
 stream = torch.cuda.current_stream()
@@ -41,12 +43,12 @@ for it in range(N):
         torch.cuda.synchronize()
         marks.append((label, time.perf_counter()))
     sp2 = flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len,
-                                   rows_out=dp.staging('rows'))
+                                   rows_out=None if DEVICE_ROWS else dp.staging('rows'), device_rows=DEVICE_ROWS)
     mark('host enumeration')
     dp.restage_space(sp2)
     mark('restage')
     dp.upload(stream)
-    mark('H2D')
+    mark('H2D + row kernel' if DEVICE_ROWS else 'H2D')
     full.launch(stream)
     mark('search kernels')
     n = int(full.summary().num_records)

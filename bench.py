@@ -469,9 +469,10 @@ def run_ours(ns):
                            'cost_estimator, layer_load_balancer) + len(result) + result.best()',
                     'breakdown_ms': mean_part,
                     'timing': 'wall clock between device synchronisations, max over ranks; includes flattening of the '
-                              'profile dicts, host enumeration of the plan space, H2D, kernels, sort, D2H; excludes only '
+                              'profile dicts, host listing of the compositions, H2D, the row kernel, search kernels, sort, D2H; excludes only '
                               'the first two calls (allocation of pinned / device buffers, reused afterwards)'},
-            'gpu_launches': 7 * ns.steps,
+            # per timed step: pack_tables, range_sums, het_admit, het_scatter, het_first, het_order, het_chain, het_finalize
+            'gpu_launches': 8 * ns.steps,
             'kernel_ms': {'search_kernels_mean': kernel_ms, 'step_mean': ms_per_step,
                           'step_min': min(step_ms), 'step_max': max(step_ms),
                           'note': 'search_kernels = het_admit + het_scatter + het_first + het_chain (CUDA events '

@@ -699,7 +699,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform, ONE> {
         // ---- spare capacity (:300-306) ----
         METIS_PAR(x, s, S) {
             const int n = w.cnt[s];
-            w.capa[s] = n ? w.perf[s] - py_sum_range_compact(lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
+            w.capa[s] = n ? w.perf[s] - range_sum<SerialUniform>(T, kRangeNorm, 0, lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
         }
         x.sync();
         x.mark(15);
@@ -857,7 +857,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform, ONE> {
                 const int bs = bs_total >> (g - tpc);
                 const int key = key_of(T, type0, tpc, bs);
                 if (key < 0) err = (double)METIS_FATAL_KEY_MEMORY + (double)(((uint32_t)tpc << 16) | (uint32_t)bs) * 256.0;
-                else md += py_sum_range_compact(T.mem + (size_t)key * T.p.lpad, w.part[s], w.part[s + 1]) * kMemCoef;
+                else md += range_sum<SerialUniform>(T, kRangeMem, key, T.mem + (size_t)key * T.p.lpad, w.part[s], w.part[s + 1]) * kMemCoef;
             } else {
                 const int rc = this->hetero_memory_demand(s, type0, md);
                 if (rc) err = (double)rc + (double)aux * 256.0;
@@ -911,7 +911,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform, ONE> {
             if (ta == tb) {                                   // _get_execution_cost :175-188
                 const int key = key_of(T, ta, tpc, mbs);
                 if (key < 0) bad = true;
-                else len = py_sum_range_compact(T.lc + (size_t)key * T.p.lpad, la, lb);
+                else len = range_sum<SerialUniform>(T, kRangeLc, key, T.lc + (size_t)key * T.p.lpad, la, lb);
             } else if (this->hetero_exec_cost(a, b, 1 << ldp, tpc, la, lb, len)) {
                 bad = true;
             }

@@ -72,6 +72,11 @@ struct Tables {
     // to PREDICT where a stage's forward fill ends (metis_coop.cuh); every prediction is verified exactly
     const double *psub;        // [7 * num_layers + 1] (empty when norm_len < num_layers)
     const double *dsub;        // [7 * num_layers] demand of every sub-layer, dsub[j] = dlay[j / 7] (the same bits)
+    // range sums (fill_range_sums below): rsum[(t * n + b) * n + a] = sum(row_t[a:b]) as CPython adds it up, n =
+    // num_layers + 1; rows t: layer_memory of key t, then layer_compute of key t - num_keys, then norm_lc.  Every
+    // stage of every candidate needs such a sum (memory demand, execution time, compute left after the vote); the
+    // search kernels look them up, the other kernels (rsum == nullptr) add the slice up.
+    const double *rsum;
 };
 
 constexpr int kDpk = 16;
@@ -164,7 +169,24 @@ struct Serial {
     MB_HD double max_all(double v) const { return v; }
     MB_HD bool any(bool p) const { return p; }
     MB_HD void mark(int) const {}              // profiling hook (cooperative mode, profiling build)
+    // lockstep hooks (see Lockstep below): nothing to do when a thread works alone
+    MB_HD void converge() const {}
+    MB_HD void rejoin(bool) {}
 };
+#if defined(__CUDACC__)
+// `Lockstep`: the bulk round of the search (metis_search.cu, het_first_kernel) - the 32 lanes of a warp hold 32
+// different plans of equal stage count and should execute the same instruction stream.  Data-dependent branches
+// let lanes drift apart and the hardware only re-joins them at the post-dominator of the branch, which an error
+// exit deep inside a loop pushes to the end of the function (measured: 6 of 32 lanes active per instruction on a
+// 128-GPU space).  converge() re-joins the lanes that hold a plan at points every one of them reaches exactly once;
+// rejoin(p) is called by ALL 32 lanes between the phases and makes the lanes with p == true the group from there on.
+struct Lockstep : Serial {
+    unsigned mask;
+    __device__ Lockstep() : mask(0xFFFFFFFFu) {}
+    __device__ void converge() const { __syncwarp(mask); }
+    __device__ void rejoin(bool p) { mask = __ballot_sync(0xFFFFFFFFu, p); }
+};
+#endif
 struct SerialUniform : Serial {           // tests: the code paths of the cooperative mode, one lane
     static constexpr bool kUniform = true;
 };
@@ -237,6 +259,49 @@ template <class X>
 MB_HD double sum_range(const double *x, int a, int b) {
     if constexpr (X::kUniform) return py_sum_range_compact(x, a, b);
     else return py_sum_range(x, a, b);
+}
+
+// CPython's sum(row[a:b]) for every b in (a, L] in one pass: the running (f, c) of the compensated sum do not depend
+// on where the slice ends, only the final `f + c` does.  out[b * n + a], n = L + 1 (entries with b <= a unused).
+MB_HD void fill_range_sums(const double *row, int L, int a, double *out) {
+    const int n = L + 1;
+    double f = 0.0 + row[a];
+    double c = 0.0;
+    out[(size_t)(a + 1) * n + a] = f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = a + 1; i < L; ++i) {
+        const double v = row[i];
+        const double t = f + v;
+        if (fabs(f) >= fabs(v)) c += (f - t) + v;
+        else c += (v - t) + f;
+        f = t;
+        out[(size_t)(i + 1) * n + a] = (c != 0.0 && isfinite(c)) ? f + c : f;
+    }
+}
+MB_HD int range_sum_tables(const MetisProblem &p) { return 2 * p.num_keys + 1; }
+MB_HD const double *range_sum_row(const MetisProblem &p, int t, const double *mem, const double *lc, const double *norm) {
+    if (t < p.num_keys) return mem + (size_t)t * p.lpad;
+    if (t < 2 * p.num_keys) return lc + (size_t)(t - p.num_keys) * p.lpad;
+    return p.norm_len >= p.num_layers ? norm : nullptr;     // shorter norm_lc: the search aborts before using it
+}
+
+enum RangeTable { kRangeMem = 0, kRangeLc = 1, kRangeNorm = 2 };
+// sum(row[a:b]) of one of the three table families; `row` is the same row in T.mem / T.lc / T.norm_lc
+template <class X>
+MB_HD double range_sum(const Tables &T, int family, int key, const double *row, int a, int b) {
+    if (a >= b) return 0.0;
+    if (T.rsum && b <= T.p.num_layers) {
+        const int n = T.p.num_layers + 1;
+        const int t = family == kRangeMem ? key : family == kRangeLc ? T.p.num_keys + key : 2 * T.p.num_keys;
+#if defined(__CUDA_ARCH__)
+        return __ldg(&T.rsum[((size_t)t * n + b) * n + a]);
+#else
+        return T.rsum[((size_t)t * n + b) * n + a];
+#endif
+    }
+    return sum_range<X>(row, a, b);
 }
 
 // Running form of the same sum for values produced on the fly.
@@ -407,6 +472,9 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     const int N = kH * L;
     const int lim = (N - 1 - kH) > 0 ? (N - 1 - kH) : 0;   // :218
     const int last = S - 1;
+    int broken = METIS_FATAL_NONE;                           // scratch invariant violated (never observed): reported at
+                                                             // the end - an exit inside the loops below would keep
+                                                             // the lanes of the bulk round from re-joining (Lockstep)
 
     x.sync();                                                // lane-strided writes below: earlier readers are done
 #pragma unroll (X::kUniform ? 1 : 0)
@@ -485,6 +553,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     }
 
     x.mark(11);
+    x.converge();
     // ---- backward pass (:233-249): last stage takes a contiguous tail [m, N) -----------------
     int m;
     {
@@ -514,6 +583,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     }
 
     x.mark(12);
+    x.converge();
     // ---- leftovers (:251-287), ascending: first the skipped sub-layers, then the middle block --
     // get_proper_stage: lo = stage of the largest assigned id below j whose stage holds nothing
     // above j, hi = stage of the smallest assigned id above j whose stage holds nothing below j.
@@ -547,7 +617,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
 #pragma unroll (X::kUniform ? 1 : 0)
                 while (hi < last && (!fwd_nonempty(w, hi) || w.got[hi])) ++hi;
             }
-            if (lo > hi) return METIS_FATAL_SCRATCH;
+            if (lo > hi) { broken = METIS_FATAL_SCRATCH; hi = lo; }
             int pick = lo;
             double best = w.capa[lo];
 #pragma unroll (X::kUniform ? 1 : 0)
@@ -560,11 +630,13 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
             start = next_start;
         }
     }
-    if (m - k > Scratch<MAXS, MAXL>::kBlock) return METIS_FATAL_SCRATCH;
+    x.converge();
+    int nblk = m - k;
+    if (nblk > Scratch<MAXS, MAXL>::kBlock) { broken = METIS_FATAL_SCRATCH; nblk = Scratch<MAXS, MAXL>::kBlock; }
     {
         int below = -1;                                       // stage of the nearest block item not on `last`
 #pragma unroll (X::kUniform ? 1 : 0)
-        for (int t = 0; t < m - k; ++t) {
+        for (int t = 0; t < nblk; ++t) {
             const int j = k + t;
             int lo = 0;
             if (below >= 0) lo = below;
@@ -595,6 +667,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     }
 
     x.mark(13);
+    x.converge();
     // ---- majority vote back to real layers (:290-308) ------------------------------------------
     // A stage holding >= 4 of a layer's 7 sub-layers holds the middle one or one of the first
     // three, so at most four candidates are counted (SWAR byte compare on the packed layer word).
@@ -618,6 +691,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     }
     x.sync();
     x.mark(14);
+    x.converge();
     uint8_t *owner = reinterpret_cast<uint8_t *>(w.ownerw);
     if (X::kUniform) {
         // first / last / count of the layers of each stage: one lane per stage scans the owner bytes
@@ -653,10 +727,11 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     x.sync();
 #pragma unroll (X::kUniform ? 1 : 0)
     for (int s = x.lane(); s < S; s += x.width())            // :300-306
-        w.capa[s] = w.cnt[s] ? w.perf[s] - sum_range<X>(lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
+        w.capa[s] = w.cnt[s] ? w.perf[s] - range_sum<X>(T, kRangeNorm, 0, lc, w.first[s], (int)w.lastl[s] + 1) : w.perf[s];
     x.sync();
 
     x.mark(15);
+    x.converge();
     // ---- boundary adjustment (:310-356): at most three committed single-layer moves ---------
 #pragma unroll (X::kUniform ? 1 : 0)
     for (int n = 1; n <= 3; ++n) {
@@ -701,10 +776,11 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     }
 
     x.mark(16);
+    x.converge();
     w.part[0] = 0;                                           // :358-364
 #pragma unroll (X::kUniform ? 1 : 0)
     for (int s = 0; s < S; ++s) w.part[s + 1] = (uint16_t)(w.part[s] + w.cnt[s]);
-    return METIS_FATAL_NONE;
+    return broken;
 }
 
 // ---------------------------------------------------------------------------
@@ -965,6 +1041,7 @@ struct PlanEvaluator {
             w.extra[s] = fail ? (double)fail + (double)aux * 256.0 : 0.0;   // per-stage error mailbox (cooperative mode)
         }
         x.sync();
+        x.converge();
         PySum total;
 #pragma unroll (X::kUniform ? 1 : 0)
         for (int s = 0; s < pd.S; ++s) {                     // first failing stage in stage order, like the reference
@@ -1001,7 +1078,7 @@ struct PlanEvaluator {
                     if (!(h & piece)) continue;
                     const int key = key_of(T, type0, tpc, piece);
                     if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)piece; return METIS_FATAL_KEY_MEMORY; }
-                    demand += sum_range<X>(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
+                    demand += range_sum<X>(T, kRangeMem, key, T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
                 }
             }
         return 0;
@@ -1017,7 +1094,7 @@ struct PlanEvaluator {
             const int bs = bs_total >> (g - tpc);
             const int key = key_of(T, ta, tpc, bs);
             if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)bs; return METIS_FATAL_KEY_MEMORY; }
-            demand += py_sum_range_compact(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
+            demand += range_sum<SerialUniform>(T, kRangeMem, key, T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
             return 0;
         }
         HSplit hs;
@@ -1038,7 +1115,7 @@ struct PlanEvaluator {
                     if (!(h & piece)) continue;
                     const int key = key_of(T, hs.type[r], tpc, piece);
                     if (key < 0) { aux = ((uint32_t)tpc << 16) | (uint32_t)piece; return METIS_FATAL_KEY_MEMORY; }
-                    need += py_sum_range_compact(T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
+                    need += range_sum<SerialUniform>(T, kRangeMem, key, T.mem + (size_t)key * T.p.lpad, la, lb) * kMemCoef;
                 }
                 if (need > worst) worst = need;
             }
@@ -1142,7 +1219,7 @@ struct PlanEvaluator {
                 const int bs = bs_total >> (g - tpc);
                 const int key = key_of(T, type0, tpc, bs);
                 if (key < 0) err = (double)METIS_FATAL_KEY_MEMORY + (double)(((uint32_t)tpc << 16) | (uint32_t)bs) * 256.0;
-                else md += sum_range<X>(T.mem + (size_t)key * T.p.lpad, w.part[s], w.part[s + 1]) * kMemCoef;
+                else md += range_sum<X>(T, kRangeMem, key, T.mem + (size_t)key * T.p.lpad, w.part[s], w.part[s + 1]) * kMemCoef;
             } else {
                 const int rc = hetero_memory_demand(s, type0, md);
                 if (rc) err = (double)rc + (double)aux * 256.0;
@@ -1159,6 +1236,7 @@ struct PlanEvaluator {
             }
         }
         x.sync();
+        x.converge();
         bool oom = false;
 #pragma unroll (X::kUniform ? 1 : 0)
         for (int s = 0; s < S; ++s) {
@@ -1265,7 +1343,7 @@ struct PlanEvaluator {
                     if (piece > T.p.max_bs) return 1;            // :166-167
                     const int key = key_of(T, hs.type[r], tpc, piece);
                     if (key < 0) return 1;
-                    acc += sum_range<X>(T.lc + (size_t)key * T.p.lpad, la, lb);
+                    acc += range_sum<X>(T, kRangeLc, key, T.lc + (size_t)key * T.p.lpad, la, lb);
                 }
                 if (acc > len) len = acc;
             }
@@ -1321,7 +1399,7 @@ struct PlanEvaluator {
             if (ta == tb) {                                   // _get_execution_cost :175-188
                 const int key = key_of(T, ta, tpc, bs_total >> ldp);
                 if (key < 0) err = 1.0;
-                else len = sum_range<X>(T.lc + (size_t)key * T.p.lpad, la, lb);
+                else len = range_sum<X>(T, kRangeLc, key, T.lc + (size_t)key * T.p.lpad, la, lb);
             } else if (hetero_exec_cost(a, b, 1 << ldp, tpc, la, lb, len)) {
                 err = 1.0;
             }
@@ -1448,9 +1526,11 @@ struct PlanEvaluator {
 // returns true when the plan continues in the chain kernel; `chain_hint` then estimates how long its chain is
 // (used only to start long chains first).
 // ---------------------------------------------------------------------------
-template <int MAXS, int MAXL, bool ONE, class Sink>
+template <int MAXS, int MAXL, bool ONE, class X = Serial, class Sink>
 MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool has, const PlanDesc &plan, int &chain_hint) {
-    PlanEvaluator<MAXS, MAXL, Serial, ONE> ev(T, w);
+    // X = Lockstep (device, called by all 32 lanes of a warp, with or without a plan): the lanes are re-joined
+    // between the phases and inside the balancer.  X = Serial: one thread on its own.
+    PlanEvaluator<MAXS, MAXL, X, ONE> ev(T, w);
     bool cont = false;
     sink.phase(1);
     if (has) {                                               // ---- P ----
@@ -1458,18 +1538,21 @@ MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool 
         if (ok < 0) sink.fatal(plan.ordinal, METIS_FATAL_SCRATCH, 0);
         has = ok == 1;
     }
+    ev.x.rejoin(has);
     if (has) {
         sink.partition_call();
         const int rc = ev.compute_performance();
         if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
     }
     sink.phase(2);
+    ev.x.rejoin(has);
     if (has) {                                               // ---- R ----
         sink.balancer_run();
-        const int rc = balance_run<MAXS, MAXL>(T, plan.S, w, Serial());
+        const int rc = balance_run<MAXS, MAXL>(T, plan.S, w, ev.x);
         if (rc) { sink.fatal(plan.ordinal, rc, ev.aux); has = false; }
     }
     sink.phase(3);
+    ev.x.rejoin(has);
     bool costing = false;
     if (has) {                                               // ---- M ----
         const int r = ev.memory_phase(1, true);
@@ -1478,12 +1561,14 @@ MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool 
         else costing = true;                                 // r == 1: partition accepted at the first attempt
     }
     sink.phase(4);
+    ev.x.rejoin(costing);
     if (costing) {                                           // ---- C ---- (num_repartition == 1 ends the chain)
         double cost;
         if (ev.get_cost(cost) == 0) sink.emit(plan, 0, 1, cost, w.tpc, w.part);
         else sink.keyerror();
     }
     sink.phase(0);
+    ev.x.rejoin(true);
     return cont;
 }
 

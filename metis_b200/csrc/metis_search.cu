@@ -59,8 +59,9 @@ int fail_cuda(cudaError_t e, const char *what) { return cuda_fail(e, what); }   
 int fail_arg(const char *what) { return arg_fail(what); }
 
 struct BlobLayout {
-    uint32_t total;
+    uint32_t total;               // bytes staged into shared memory
     uint32_t key, lc, mem, exec_full, fb, norm, derived, tmem, bwf, bwm, runt, rune, q10e;
+    uint32_t rsum, rsum_bytes;    // range-sum tables (Tables::rsum): behind the staged part, read from L2
 };
 
 static uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -83,12 +84,19 @@ static BlobLayout make_layout(const MetisProblem &p) {
     l.rune = o;      o = align16(o + (uint32_t)p.num_node_sequences * p.num_types * 4);
     l.q10e = o;      o = align16(o + (uint32_t)p.num_node_sequences * p.num_types * 4);
     l.total = o;
+    const uint64_t n = (uint64_t)p.num_layers + 1;
+    l.rsum = (o + 127u) & ~127u;
+    l.rsum_bytes = (uint32_t)((uint64_t)(2 * p.num_keys + 1) * n * n * 8);    // <= 2 * 255 keys... checked in check_problem
     return l;
 }
 
-__device__ __forceinline__ Tables make_tables(const MetisProblem &p, const BlobLayout &l, const uint8_t *base) {
+// `base`: the staged tables (shared or global memory); `gblob`: the blob in global memory when its range-sum tables
+// were filled for this launch (search kernels), else nullptr
+__device__ __forceinline__ Tables make_tables(const MetisProblem &p, const BlobLayout &l, const uint8_t *base,
+                                              const uint8_t *gblob = nullptr) {
     Tables T;
     T.p = p;
+    T.rsum = gblob ? reinterpret_cast<const double *>(gblob + l.rsum) : nullptr;
     T.key_index = reinterpret_cast<const int16_t *>(base + l.key);
     T.lc = reinterpret_cast<const double *>(base + l.lc);
     T.mem = reinterpret_cast<const double *>(base + l.mem);
@@ -130,6 +138,20 @@ __global__ void pack_tables_kernel(MetisProblem p, BlobLayout l, uint8_t *blob) 
     const DerivedLayout d = derived_layout(p);
     for (uint32_t i = tid; i < (uint32_t)d.total; i += nthr)
         derived[i] = derive_entry(p, d, p.norm_lc, p.exec_full, p.type_bw_first, (int)i);
+}
+
+// Range-sum tables (metis_eval.cuh, fill_range_sums): one thread per (row, first layer) adds the row up once and
+// stores the sum of every slice that starts there; neighbouring threads write neighbouring addresses.
+__global__ void __launch_bounds__(128)
+range_sums_kernel(MetisProblem p, BlobLayout l, uint8_t *blob) {
+    const int L = p.num_layers;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)range_sum_tables(p) * L) return;
+    const int t = (int)(i / L), a = (int)(i % L);
+    const double *row = range_sum_row(p, t, p.layer_memory, p.layer_compute, p.norm_lc);
+    if (!row) return;
+    const size_t n = (size_t)L + 1;
+    fill_range_sums(row, L, a, reinterpret_cast<double *>(blob + l.rsum) + (size_t)t * n * n);
 }
 
 // ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier --------------------------
@@ -418,7 +440,7 @@ het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
             stage_blob_tma(smem, blob, lay.total, &mbar);
             base = smem;
         }
-        const Tables T = make_tables(p, lay, base);
+        const Tables T = make_tables(p, lay, base, blob);
         Scratch<MAXS, MAXL> w;
         const int lane = threadIdx.x & 31;
         for (;;) {                                           // batches of 32 plans, longest stage counts first
@@ -432,7 +454,7 @@ het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
             uint4 e = make_uint4(0, 0, 0, 0);
             if (has) { e = ls.b[pos]; decode_entry(sp, e, pd); }
             int hint = 0;
-            const bool cont = first_task<MAXS, MAXL, ONE>(T, w, sink, has, pd, hint);
+            const bool cont = first_task<MAXS, MAXL, ONE, Lockstep>(T, w, sink, has, pd, hint);
             const unsigned m = __ballot_sync(0xFFFFFFFFu, cont);
             if (m) {
                 const int leader = __ffs(m) - 1;
@@ -599,7 +621,7 @@ het_chain_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
         stage_blob_tma(smem, blob, lay.total, &mbar);
         base = smem;
     }
-    const Tables T = make_tables(p, lay, base);
+    const Tables T = make_tables(p, lay, base, blob);
     DeviceSink sink(out);
     const int lane = threadIdx.x & 31;
     sink.leader = lane == 0;
@@ -758,12 +780,33 @@ layer_balance_kernel(const double *__restrict__ capa, const int32_t *__restrict_
     for (int s = 0; s <= S; ++s) out[s] = w.part[s];
 }
 
-// one thread per composition writes its rows straight into the row blob in HBM (metis_rows.cuh)
-__global__ void __launch_bounds__(128)
+// one warp per composition.  The leader lane replays the prefix-shift walk (metis_rows.cuh) and
+// composes each row in shared memory; the whole warp copies it to the row blob in HBM (coalesced byte stores).
+constexpr int kRowWarps = 8;
+__global__ void __launch_bounds__(kRowWarps * 32)
 het_rows_kernel(const MetisCompRec *__restrict__ recs, long long ncomp, const uint8_t *__restrict__ pool,
                 uint8_t *__restrict__ rows) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < ncomp) write_composition_rows(recs[c], pool, rows);
+    __shared__ uint8_t s_row[kRowWarps][METIS_MAX_STAGES];
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * kRowWarps + wid;
+    if (c >= ncomp) return;                                   // whole warps leave together
+    const MetisCompRec rec = recs[c];
+    const int stages = rec.stages;
+    if (stages > METIS_MAX_STAGES) return;                    // such a space is refused by metis_het_search (max_stage)
+    uint8_t *dst = rows + rec.row_offset;
+    CompWalk cw;
+    if (lane == 0) cw.init(rec, pool);
+    for (;;) {
+        if (lane == 0) cw.compose(s_row[wid]);
+        __syncwarp();
+        for (int p = lane; p < stages; p += 32) dst[p] = s_row[wid][p];
+        __syncwarp();
+        int more = 0;
+        if (lane == 0) more = cw.advance() ? 1 : 0;
+        if (!__shfl_sync(full, more, 0)) break;
+        dst += stages;
+    }
 }
 
 __global__ void divide_by_seven_kernel(const double *lc, int n, double *out) {
@@ -819,7 +862,7 @@ int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans
     if (num_plans < 0) return METIS_E_ARG;
     const BlobLayout lay = make_layout(*problem);
     const int64_t cap = (num_plans + 127) & ~(int64_t)127;      // worst case: every plan of the shard is admitted
-    return 256 + kFixedWs + (int64_t)align16(lay.total) + kMaxBlocks * (int64_t)sizeof(MetisRecord) +
+    return 256 + kFixedWs + (int64_t)lay.rsum + (int64_t)align16(lay.rsum_bytes) + kMaxBlocks * (int64_t)sizeof(MetisRecord) +
            2 * cap * (int64_t)sizeof(uint4) + 1024;
 }
 
@@ -841,7 +884,7 @@ static Workspace carve(void *ws, const BlobLayout &lay) {
     w.counters = reinterpret_cast<unsigned long long *>(b + 1024);
     w.ctl = reinterpret_cast<unsigned int *>(b + 2048);
     w.blob = b + kFixedWs;
-    w.block_best = reinterpret_cast<MetisRecord *>(b + kFixedWs + align16(lay.total));
+    w.block_best = reinterpret_cast<MetisRecord *>(b + kFixedWs + lay.rsum + align16(lay.rsum_bytes));
     w.lists = reinterpret_cast<uint8_t *>(w.block_best + kMaxBlocks);
     return w;
 }
@@ -990,6 +1033,10 @@ int metis_het_search(const MetisProblem *problem, const MetisPlanSpace *space, c
     e = cudaMemsetAsync(ws.counters + 4, 0xFF, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "memset fatal key");
     pack_tables_kernel<<<8, 256, 0, stream>>>(*problem, lay, ws.blob);
+    {
+        const long long nthr = (long long)range_sum_tables(*problem) * problem->num_layers;
+        range_sums_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, stream>>>(*problem, lay, ws.blob);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "pack_tables_kernel");
 
@@ -1059,8 +1106,9 @@ int metis_het_trace(const MetisProblem *problem, const MetisPlanSpace *space, co
 int metis_generate_rows(const MetisCompRec *recs, int64_t num_comps, const uint8_t *pool, uint8_t *rows, void *stream_) {
     if (num_comps < 0 || (num_comps > 0 && (!recs || !pool || !rows))) return arg_fail("NULL argument");
     if (num_comps > 0) {
-        const unsigned nb = (unsigned)((num_comps + 127) / 128);
-        het_rows_kernel<<<nb, 128, 0, static_cast<cudaStream_t>(stream_)>>>(recs, (long long)num_comps, pool, rows);
+        const int64_t nb = (num_comps + kRowWarps - 1) / kRowWarps;
+        if (nb > 0x7FFFFFFFLL) return arg_fail("too many compositions for one launch");
+        het_rows_kernel<<<(unsigned)nb, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream_)>>>(recs, (long long)num_comps, pool, rows);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "het_rows_kernel");

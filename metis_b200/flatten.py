@@ -276,6 +276,13 @@ class FlatPlanSpace:
         s.rows = ptr_of('rows')
         return s
 
+    def host_rows(self) -> np.ndarray:
+        """The row blob on the host; a device_rows space enumerates it on first use (debug / test paths only)."""
+        if self.rows.size == 0 and self.comp_recs is not None:
+            self.tables._fill()
+            return self.tables.blob
+        return self.rows
+
     def locate(self, ordinal: int) -> Tuple[int, int, int, int, np.ndarray]:
         """ordinal -> (ns_idx, label_stage, dg_idx, batches, device_groups) like InterStagePlan."""
         firsts = self.blocks['first_ordinal']
@@ -384,12 +391,13 @@ class _LazyTables(dict):
         super().__init__()
         self._args = (cap, num_devices, variance, max_permute_len)
         self._done = False
+        self.blob = None
 
     def _fill(self):
         if not self._done:
             cap, num_devices, variance, mpl = self._args
             cache = enumerate_device_group_tables(1, cap + 1, num_devices, variance, mpl)
-            blob = cache.pop(0)
+            blob = self.blob = cache.pop(0)
             base = blob.__array_interface__['data'][0]
             for st, rows in cache.items():
                 dict.__setitem__(self, st, (rows.__array_interface__['data'][0] - base, rows))

@@ -346,7 +346,7 @@ class Candidates:
         self._detail_dev = detail_dev
         # device-group rows: the blob the GPU wrote (``rows_dev``) or the host enumerator's
         self._rows_dev = rows_dev
-        self._rows = None if rows_dev is not None else space.rows
+        self._rows = None if rows_dev is not None else space.host_rows()
         self.cost = records['cost']
 
     def columns(self, idx=None) -> Dict[str, np.ndarray]:

@@ -20,9 +20,24 @@ using namespace metis;
 
 namespace {
 
-Tables host_tables(const MetisProblem &p, std::vector<double> &dlay) {
+// `with_rsum`: the range-sum tables of the search kernels (filled by the same fill_range_sums); without them the
+// evaluator adds the slices up, like the replay / trace kernels do
+Tables host_tables(const MetisProblem &p, std::vector<double> &dlay, bool with_rsum = false) {
     Tables T;
     T.p = p;
+    T.rsum = nullptr;
+    if (with_rsum) {
+        static thread_local std::vector<double> rs;
+        const int L = p.num_layers;
+        const size_t n = (size_t)L + 1;
+        rs.assign((size_t)range_sum_tables(p) * n * n, -1.0);
+        for (int t = 0; t < range_sum_tables(p); ++t) {
+            const double *row = range_sum_row(p, t, p.layer_memory, p.layer_compute, p.norm_lc);
+            if (!row) continue;
+            for (int a = 0; a < L; ++a) fill_range_sums(row, L, a, rs.data() + (size_t)t * n * n);
+        }
+        T.rsum = rs.data();
+    }
     T.key_index = p.key_index;
     T.lc = p.layer_compute;
     T.mem = p.layer_memory;
@@ -106,7 +121,7 @@ extern "C" {
 int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const MetisShard *sh, MetisRecord *records,
                        int64_t capacity, uint8_t *detail, int32_t stride, MetisSearchSummary *summary, int32_t mode) {
     std::vector<double> dlay;
-    const Tables T = host_tables(*p, dlay);
+    const Tables T = host_tables(*p, dlay, mode != 0);
     memset(summary, 0, sizeof(*summary));
     summary->fatal_ordinal = ~0ULL;
     summary->best.cost = INFINITY;

@@ -652,7 +652,8 @@ def test_rows_written_by_the_gpu_equal_the_host_enumerators(ndev, var, mpl, work
     assert dev.comp_recs is not None and dev.rows.size == 0
     assert dev.num_plans == host.num_plans and dev.blocks.tobytes() == host.blocks.tobytes()
     dp = search.DeviceProblem(problem, dev, 'cuda:0')
-    assert dp.h2d_bytes < 64 * 1024 + dev.comp_recs.nbytes + dev.comp_pool.nbytes + 4096      # no rows uploaded
+    assert dp.h2d_bytes == dp._off['rows'][0]                 # the upload stops where the row blob starts
+    assert dp.h2d_bytes < 64 * 1024 + 2 * (dev.comp_recs.nbytes + dev.comp_pool.nbytes)
     got = dp.rows_device().cpu().numpy()
     assert got.tobytes() == host.rows[:dev.rows_total_bytes].tobytes()
     # a second upload into the same arena (engine reuse) rewrites the same bytes

@@ -23,7 +23,7 @@ rep = sys.argv[1]
 kern = sys.argv[2] if len(sys.argv) > 2 else 'het_search_kernelILi64'
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 45
 repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(repo, 'metis_b200', 'libmetis_b200.so')
+lib = os.environ.get('NCU_BY_LINE_LIB') or os.path.join(repo, 'metis_b200', 'libmetis_b200.so')
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', lib], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.startswith('metis_search.') and f.endswith('.cubin')][0]

@@ -306,7 +306,7 @@ def run_ours(ns):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device(f'cuda:{local}')
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group('nccl', device_id=dev)
     assert world == ns.gpus or world == 1 and ns.gpus == 1, f'--gpus {ns.gpus} but WORLD_SIZE {world}'
 
@@ -329,7 +329,7 @@ def run_ours(ns):
 
     # ---- device-resident problem for `value` -----------------------------------------------------
     t0 = time.perf_counter()
-    problem, space, _ = api.het_problem(args, cluster, profile, cfg, balancer, seqs)
+    problem, space, _ = api.het_problem(args, cluster, profile, cfg, balancer, seqs, device_rows=True)
     host_prep_s = time.perf_counter() - t0
     dp = search.DeviceProblem(problem, space, dev)
     tile = 128
@@ -496,7 +496,9 @@ def run_ours(ns):
         emit_result(line)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    del full, probe, dp, flush
+    api.release_engines()
+    torch.cuda.empty_cache()
     tmp.cleanup()
 
 
@@ -518,8 +520,16 @@ def main():
     os.dup2(2, 1)
     if ns.impl == 'reference':
         run_reference_arm(ns)
-    else:
+        return
+    # --workload a,b,c (developer use: the scaling table of profiles/) runs the workloads one after the other in
+    # this process group and prints one line each; the default invocation prints exactly one line
+    names = ns.workload.split(',')
+    for name in names:
+        ns.workload = name
         run_ours(ns)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 _RESULT_FD = None

@@ -780,27 +780,37 @@ layer_balance_kernel(const double *__restrict__ capa, const int32_t *__restrict_
     for (int s = 0; s <= S; ++s) out[s] = w.part[s];
 }
 
-// one warp per composition.  The leader lane replays the prefix-shift walk (metis_rows.cuh) and
-// composes each row in shared memory; the whole warp copies it to the row blob in HBM (coalesced byte stores).
+// one warp per composition.  The walk (metis_rows.cuh) is sequential - every permutation is one
+// node of a linked list moved to the front of the previous one - so the leader lane advances it, on a state kept
+// in shared memory; writing a row out is not: group by group, the lanes copy the codes (coalesced byte stores).
 constexpr int kRowWarps = 8;
 __global__ void __launch_bounds__(kRowWarps * 32)
 het_rows_kernel(const MetisCompRec *__restrict__ recs, long long ncomp, const uint8_t *__restrict__ pool,
                 uint8_t *__restrict__ rows) {
-    __shared__ uint8_t s_row[kRowWarps][METIS_MAX_STAGES];
+    __shared__ CompWalk s_walk[kRowWarps];
+    __shared__ uint8_t s_pool[kRowWarps][METIS_MAX_PERMUTE_GROUPS + METIS_MAX_STAGES];
     const unsigned full = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long c = (long long)blockIdx.x * kRowWarps + wid;
     if (c >= ncomp) return;                                   // whole warps leave together
     const MetisCompRec rec = recs[c];
-    const int stages = rec.stages;
-    if (stages > METIS_MAX_STAGES) return;                    // such a space is refused by metis_het_search (max_stage)
+    const int stages = rec.stages, n = rec.num_groups;
+    if (stages > METIS_MAX_STAGES || n > METIS_MAX_PERMUTE_GROUPS) return;   // refused on the host
+    for (int p = lane; p < n + stages; p += 32) s_pool[wid][p] = pool[rec.pool_offset + p];
+    __syncwarp();
+    CompWalk &cw = s_walk[wid];
+    MetisCompRec local = rec;
+    local.pool_offset = 0;
+    if (lane == 0) cw.init(local, s_pool[wid]);
     uint8_t *dst = rows + rec.row_offset;
-    CompWalk cw;
-    if (lane == 0) cw.init(rec, pool);
     for (;;) {
-        if (lane == 0) cw.compose(s_row[wid]);
-        __syncwarp();
-        for (int p = lane; p < stages; p += 32) dst[p] = s_row[wid][p];
+        __syncwarp();                                         // the list as the leader left it
+        int at = 0;
+        for (int h = cw.head; h >= 0; h = cw.nxt[h]) {        // every lane walks the (short) list
+            const int len = cw.len[h], off = cw.off[h];
+            for (int b = lane; b < len; b += 32) dst[at + b] = cw.codes[off + b];
+            at += len;
+        }
         __syncwarp();
         int more = 0;
         if (lane == 0) more = cw.advance() ? 1 : 0;

@@ -680,4 +680,5 @@ def test_search_over_gpu_written_rows_gives_the_same_records(name, workload_dir)
         outs.append(search.HetSearcher(dp, want_records=True, want_detail=True).run())
     a, b = outs
     assert len(a.records) > 0 and a.records.tobytes() == b.records.tobytes()
-    assert a.detail.tobytes() == b.detail.tobytes()
+    used = np.arange(a.detail.shape[1])[None, :] < (3 * a.records['num_stage'].astype(np.int64) + 1)[:, None]
+    assert (np.where(used, a.detail, 0) == np.where(used, b.detail, 0)).all()     # bytes past 3S+1 are not written

@@ -279,18 +279,22 @@ int64_t metis_enum_device_group_tables(int32_t first_stage, int32_t last_stage, 
 /*
  * Device-side generation of the device-group rows.  The host lists the compositions of every
  * stage count and merges their groups (search_space/device_group.py:7-81) - thousands of compositions - and the GPU
- * writes their multiset permutations in the reference's order (search_space/utils.py:72-88), one thread per
- * composition: millions of rows that never exist on the host or on PCIe.
+ * writes their multiset permutations in the reference's order (search_space/utils.py:72-88): millions of rows that
+ * never exist on the host or on PCIe.  One record = one slice of at most METIS_COMP_SLICE_ROWS consecutive
+ * permutations of one composition (the walk is sequential, so a warp skips to its slice and writes only that).
  */
 typedef struct MetisCompRec {
-    int64_t row_offset;           /* byte offset of the composition's first row in the row blob               */
-    uint32_t pool_offset;         /* its entry in the pool: num_groups lengths, then `stages` log2 codes of the
-                                     groups in sorted order (utils.py:57)                                     */
+    int64_t row_offset;           /* byte offset of the slice's first row in the row blob                      */
+    uint32_t pool_offset;         /* the composition's entry in the pool: num_groups lengths, then `stages` log2
+                                     codes of the groups in sorted order (utils.py:57)                         */
     uint16_t stages;
     uint16_t num_groups;          /* merged groups (<= METIS_MAX_PERMUTE_GROUPS on the device)                 */
+    uint32_t first_row;           /* permutations of the composition before this slice                        */
+    uint32_t num_rows;            /* permutations in this slice                                                */
 } MetisCompRec;
+#define METIS_COMP_SLICE_ROWS 64
 #define METIS_MAX_PERMUTE_GROUPS 32
-/* host: fills recs / pool (call with recs == NULL to size: returns the number of compositions, *pool_bytes the
+/* host: fills recs / pool (call with recs == NULL to size: returns the number of records, *pool_bytes the
  * pool size, *max_groups the largest num_groups); rows_per_stage like metis_enum_device_group_tables */
 int64_t metis_enum_compositions(int32_t first_stage, int32_t last_stage, int32_t num_gpus, double variance,
                                 int32_t max_permute_len, int64_t *rows_per_stage, MetisCompRec *recs,

@@ -401,7 +401,7 @@ extern "C" int64_t metis_enum_compositions(int32_t first_stage, int32_t last_sta
         cache.set.prepare(first_stage, last_stage, num_gpus, variance, max_permute_len);
     }
     const TableSet &set = cache.set;
-    int64_t ncomp = 0, pbytes = 0, byte_off = 0;
+    int64_t nrec = 0, pbytes = 0, byte_off = 0;
     int most = 0;
     for (int i = 0; i < n; ++i) {
         const StageTable &t = set.tables[i];
@@ -409,28 +409,36 @@ extern "C" int64_t metis_enum_compositions(int32_t first_stage, int32_t last_sta
         for (size_t c = 0; c < t.merged.size(); ++c) {
             pbytes += (int64_t)t.merged[c].size() + t.stages;
             most = std::max(most, (int)t.merged[c].size());
+            const int64_t perms = t.offset[c + 1] - t.offset[c];
+            nrec += (perms + METIS_COMP_SLICE_ROWS - 1) / METIS_COMP_SLICE_ROWS;
         }
-        ncomp += (int64_t)t.merged.size();
     }
     *pool_bytes = pbytes;
     if (max_groups) *max_groups = most;
-    if (!recs) return ncomp;
-    if (ncomp > recs_capacity || pbytes > pool_capacity || !pool) return METIS_E_CAPACITY;
+    if (!recs) return nrec;
+    if (nrec > recs_capacity || pbytes > pool_capacity || !pool) return METIS_E_CAPACITY;
     int64_t k = 0, po = 0;
     for (int i = 0; i < n; ++i) {
         const StageTable &t = set.tables[i];
         for (size_t c = 0; c < t.merged.size(); ++c) {
-            MetisCompRec &r = recs[k++];
-            r.row_offset = byte_off + t.offset[c] * t.stages;
-            r.pool_offset = (uint32_t)po;
-            r.stages = (uint16_t)t.stages;
-            r.num_groups = (uint16_t)t.merged[c].size();
+            const int64_t perms = t.offset[c + 1] - t.offset[c];
+            const uint32_t entry = (uint32_t)po;
             for (const Group &g : t.merged[c]) pool[po++] = (uint8_t)g.size();
             for (const Group &g : t.merged[c])
                 for (int v : g) pool[po++] = ilog2(v);
+            for (int64_t first = 0; first < perms; first += METIS_COMP_SLICE_ROWS) {
+                MetisCompRec &r = recs[k++];
+                r.row_offset = byte_off + (t.offset[c] + first) * t.stages;
+                r.pool_offset = entry;
+                r.stages = (uint16_t)t.stages;
+                r.num_groups = (uint16_t)t.merged[c].size();
+                r.first_row = (uint32_t)first;
+                r.num_rows = (uint32_t)std::min<int64_t>(METIS_COMP_SLICE_ROWS, perms - first);
+            }
         }
         byte_off += t.rows() * t.stages;
     }
+    const int64_t ncomp = nrec;
     cache.first = cache.last = 0;
     cache.set = TableSet();
     return ncomp;

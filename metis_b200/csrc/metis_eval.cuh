@@ -860,6 +860,26 @@ struct TraceTap {
     double cost[5];     // execution_cost, fb_sync_cost, max parameter update, max dp, pp_cost (cost_estimator.py:239-240)
 };
 
+MB_HD int halvings_of(const MetisProblem &p, int S, const uint8_t *gcode, const uint8_t *tpc, int bs_total) {
+    int ltp = 0, lbs = 0;
+    while ((2 << ltp) <= p.max_tp) ++ltp;                     // floor(log2(max_tp))
+    while ((2 << lbs) <= p.max_bs) ++lbs;
+    int u = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = 0; s < S; ++s) {
+        const int g = gcode[s], t = tpc[s];
+        int lm = 0;                                           // floor(log2(mbs)), mbs = bs_total >> log2(dp)
+        while ((2 << lm) <= (bs_total >> (g - t))) ++lm;
+        int room = g - t;
+        if (ltp - t < room) room = ltp - t;
+        if (lbs - lm < room) room = lbs - lm;
+        if (room > 0) u += room;
+    }
+    return u;
+}
+
 template <int MAXS, int MAXL, class X = Serial, bool ONE = false>
 struct PlanEvaluator {
     const Tables &T;
@@ -869,11 +889,10 @@ struct PlanEvaluator {
     int bs_total;         // gbs // batches
     int nbad;             // stages of the current strategy that violate _is_valid_strategies
     uint32_t aux;
-    int chain_hint;       // scheduling hint only: how many halvings the out-of-memory stages are away from fitting
     TraceTap *tap;        // verbose transcript only
 
     MB_HD PlanEvaluator(const Tables &t, Scratch<MAXS, MAXL> &s, const X &lanes = X())
-        : T(t), w(s), x(lanes), bs_total(0), nbad(0), aux(0), chain_hint(0), tap(nullptr) {}
+        : T(t), w(s), x(lanes), bs_total(0), nbad(0), aux(0), tap(nullptr) {}
 
     MB_HD int group(int s) const { return 1 << w.gcode[s]; }
     MB_HD int dp_of(int s) const { return (1 << w.gcode[s]) >> w.tpc[s]; }
@@ -940,6 +959,12 @@ struct PlanEvaluator {
     }
 
     MB_HD bool valid() const { return nbad == 0; }
+
+    // Scheduling hint only (never part of a result): how many more strategies the chain of this plan can visit.
+    // Every step of IntraStagePlanGenerator halves the dp of ONE stage (search_space/plan.py:257-266), a stage can
+    // be halved until dp = 1, tp = max_tp or mbs = max_bs; measured on BASELINE configs[2], the number of
+    // LayerComputeBalancer runs of a chain is 2 * halvings + 2 with correlation 0.98.
+    MB_HD int halvings() const { return halvings_of(T.p, pd.S, w.gcode, w.tpc, bs_total); }
 
     // StagePerformance.get_device_group_memory_capacity, one stage (model/device_group.py:87-101)
     MB_HD double memory_capacity(int a, int b) const {
@@ -1229,11 +1254,6 @@ struct PlanEvaluator {
             w.capa[s] = mc - md;
             w.mstate[s] = err;
             if (tap) { tap->demand[s] = md; tap->state[s] = mc - md; }
-            if (defer && md > mc && mc > 0.0) {              // log2(demand / capacity), rounded up, from the exponents
-                uint64_t bd, bc;
-                memcpy(&bd, &md, 8); memcpy(&bc, &mc, 8);
-                chain_hint += (int)((bd >> 52) & 0x7FF) - (int)((bc >> 52) & 0x7FF) + 1;
-            }
         }
         x.sync();
         x.converge();
@@ -1524,7 +1544,7 @@ struct PlanEvaluator {
 // plan whose first attempt runs out of memory is handed, unchanged, to the chain kernel (one warp
 // per plan, metis_coop.cuh), which replays that attempt and walks the rest of the chain.
 // returns true when the plan continues in the chain kernel; `chain_hint` then estimates how long its chain is
-// (used only to start long chains first).
+// (PlanEvaluator::halvings; used only to start long chains first).
 // ---------------------------------------------------------------------------
 template <int MAXS, int MAXL, bool ONE, class X = Serial, class Sink>
 MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool has, const PlanDesc &plan, int &chain_hint) {
@@ -1557,7 +1577,7 @@ MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool 
     if (has) {                                               // ---- M ----
         const int r = ev.memory_phase(1, true);
         if (r < 0) sink.fatal(plan.ordinal, -r, ev.aux);
-        else if (r == 2) { cont = true; chain_hint = ev.chain_hint; }   // out of memory: the rest in the chain kernel
+        else if (r == 2) { cont = true; chain_hint = ev.halvings(); }    // out of memory: the rest in the chain kernel
         else costing = true;                                 // r == 1: partition accepted at the first attempt
     }
     sink.phase(4);

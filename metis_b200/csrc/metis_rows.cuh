@@ -67,10 +67,12 @@ MB_HD void write_composition_rows(const MetisCompRec &rec, const uint8_t *pool, 
     uint8_t *dst = rows + rec.row_offset;
     CompWalk cw;
     cw.init(rec, pool);
-    do {
+    for (uint32_t skip = 0; skip < rec.first_row; ++skip) cw.advance();       // the slice starts here
+    for (uint32_t r = 0; r < rec.num_rows; ++r) {
         cw.compose(dst);
         dst += rec.stages;
-    } while (cw.advance());
+        if (!cw.advance()) break;
+    }
 }
 
 }  // namespace metis

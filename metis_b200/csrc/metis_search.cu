@@ -346,6 +346,8 @@ struct SearchLists {
 };
 constexpr int kCtlHist = 16, kCtlCursor = 16 + 160;
 constexpr int kCtlHist2 = 512, kCtlCursor2 = 512 + 160;   // ordering of the continuations by chain hint
+constexpr int kCtlHist3 = 832, kCtlCursor3 = 832 + 160;   // ordering of the admitted plans by chain hint (no bulk round)
+constexpr unsigned kHintMax = 127;
 
 __device__ __forceinline__ uint4 make_entry(uint32_t ordinal, uint32_t flags, uint64_t geo) {
     return make_uint4(ordinal, flags, (uint32_t)geo, (uint32_t)(geo >> 32));
@@ -366,18 +368,26 @@ het_admit_kernel(const __grid_constant__ MetisPlanSpace sp, const MetisShard sh,
     if (lane == 0 && first < sp.num_plans) hint = find_block(sp, first);
     hint = __shfl_sync(0xFFFFFFFFu, hint, 0);
     PlanDesc pd;
+    int halvings = 0;
     bool ok = b0 + lane < slots && decode_plan(sp, first + lane, pd, hint);
     if (ok) {
         // PlanEvaluator::begin: tp_s = max(1, group_s / B), B = 2^floor(log2(gbs // batches)); the plan has a
         // valid strategy iff that one is valid (search_space/plan.py:238-249)
         const int bs_total = gbs / pd.batches;
         const int lb = 31 - __clz(bs_total > 0 ? bs_total : 1);
+        const int ltp = 31 - __clz(max_tp > 0 ? max_tp : 1), lbs = 31 - __clz(max_bs > 0 ? max_bs : 1);
         if (bs_total <= 0) ok = false;
         for (int s = 0; ok && s < pd.S; ++s) {
             const int g = __ldg(&pd.row[s]);
             const int t = g > lb ? g - lb : 0;
             const int mbs = bs_total >> (g - t);
             if (mbs == 0 || mbs > max_bs || (1 << t) > max_tp) ok = false;
+            else {                                           // PlanEvaluator::halvings (scheduling hint)
+                const int lm = 31 - __clz(mbs);
+                int room = g - t;
+                room = min(room, min(ltp - t, lbs - lm));
+                if (room > 0) halvings += room;
+            }
         }
     }
     const unsigned full = 0xFFFFFFFFu;
@@ -389,24 +399,27 @@ het_admit_kernel(const __grid_constant__ MetisPlanSpace sp, const MetisShard sh,
     base = __shfl_sync(full, base, leader);
     const int k = ok ? pd.S - 1 : -1;
     const unsigned peers = __match_any_sync(full, k);        // neighbours mostly share the stage count
+    const unsigned key = (unsigned)halvings > kHintMax ? kHintMax : (unsigned)halvings;
+    const unsigned peers3 = __match_any_sync(full, ok ? (int)key : -1);
     if (ok) {
-        ls.a[base + __popc(m & ((1u << lane) - 1u))] = make_entry(pd.ordinal, 0u, pd.geo);
+        ls.a[base + __popc(m & ((1u << lane) - 1u))] = make_entry(pd.ordinal, key << 8, pd.geo);
         if (lane == __ffs(peers) - 1) atomicAdd(&ls.ctl[kCtlHist + k], (unsigned int)__popc(peers));
+        if (lane == __ffs(peers3) - 1) atomicAdd(&ls.ctl[kCtlHist3 + key], (unsigned int)__popc(peers3));
     }
 }
 
 __global__ void __launch_bounds__(256)
 het_scatter_kernel(const SearchLists ls) {
-    __shared__ unsigned int s_base[METIS_MAX_STAGES];
+    __shared__ unsigned int s_base[160];
     const unsigned int n = ls.ctl[0];
+    // bulk round next: by stage count, longest first (equal trip counts inside a warp, long batches early).  Chain
+    // kernel alone: by chain hint, longest expected chain first - the chain kernel walks a plan's whole chain on one
+    // warp, so the long ones must start early (LPT order; see het_order_kernel for the same after a bulk round)
+    const bool bulk = (long long)n >= ls.bulk_min;
+    const int hist = bulk ? kCtlHist : kCtlHist3, cursor = bulk ? kCtlCursor : kCtlCursor3;
     if (threadIdx.x == 0) {
-        // bulk round: longest stage counts first (equal trip counts inside a warp, long batches early).  Chain kernel
-        // alone: shortest first - measured on BASELINE configs[2], where the plans with long chains have middle stage
-        // counts, descending order starts them late (makespan 136 vs 114 time units; 113.5 is perfect balance)
-        const bool bulk = (long long)n >= ls.bulk_min;
         unsigned int acc = 0;
-        if (bulk) for (int k = METIS_MAX_STAGES - 1; k >= 0; --k) { s_base[k] = acc; acc += ls.ctl[kCtlHist + k]; }
-        else      for (int k = 0; k < METIS_MAX_STAGES; ++k)      { s_base[k] = acc; acc += ls.ctl[kCtlHist + k]; }
+        for (int k = 127; k >= 0; --k) { s_base[k] = acc; acc += ls.ctl[hist + k]; }
     }
     __syncthreads();
     const long long span = (long long)gridDim.x * blockDim.x;
@@ -415,11 +428,12 @@ het_scatter_kernel(const SearchLists ls) {
         const bool live = pos < (long long)n;
         uint4 e = make_uint4(0, 0, 0, 0);
         if (live) e = ls.a[pos];
-        const int k = live ? (int)(e.w & 0xFF) : -1;         // geometry bits 32..39 = S - 1
+        // geometry bits 32..39 = S - 1; flag bits 8..14 = chain hint
+        const int k = !live ? -1 : bulk ? (int)(e.w & 0xFF) : (int)((e.y >> 8) & 0x7F);
         const unsigned int peers = __match_any_sync(0xFFFFFFFFu, k);
         const int leader = __ffs(peers) - 1, me = threadIdx.x & 31;
         unsigned int at = 0;
-        if (live && me == leader) at = atomicAdd(&ls.ctl[kCtlCursor + k], (unsigned int)__popc(peers));
+        if (live && me == leader) at = atomicAdd(&ls.ctl[cursor + k], (unsigned int)__popc(peers));
         at = __shfl_sync(0xFFFFFFFFu, at, leader);
         if (live) ls.b[(long long)s_base[k] + at + __popc(peers & ((1u << me) - 1u))] = e;
     }
@@ -780,7 +794,7 @@ layer_balance_kernel(const double *__restrict__ capa, const int32_t *__restrict_
     for (int s = 0; s <= S; ++s) out[s] = w.part[s];
 }
 
-// one warp per composition.  The walk (metis_rows.cuh) is sequential - every permutation is one
+// one warp per record = a slice of <= 64 permutations of one composition.  The walk (metis_rows.cuh) is sequential - every permutation is one
 // node of a linked list moved to the front of the previous one - so the leader lane advances it, on a state kept
 // in shared memory; writing a row out is not: group by group, the lanes copy the codes (coalesced byte stores).
 constexpr int kRowWarps = 8;
@@ -801,9 +815,12 @@ het_rows_kernel(const MetisCompRec *__restrict__ recs, long long ncomp, const ui
     CompWalk &cw = s_walk[wid];
     MetisCompRec local = rec;
     local.pool_offset = 0;
-    if (lane == 0) cw.init(local, s_pool[wid]);
+    if (lane == 0) {
+        cw.init(local, s_pool[wid]);
+        for (uint32_t skip = 0; skip < rec.first_row; ++skip) cw.advance();   // to the first permutation of the slice
+    }
     uint8_t *dst = rows + rec.row_offset;
-    for (;;) {
+    for (uint32_t r = 0;;) {
         __syncwarp();                                         // the list as the leader left it
         int at = 0;
         for (int h = cw.head; h >= 0; h = cw.nxt[h]) {        // every lane walks the (short) list
@@ -812,6 +829,7 @@ het_rows_kernel(const MetisCompRec *__restrict__ recs, long long ncomp, const ui
             at += len;
         }
         __syncwarp();
+        if (++r >= rec.num_rows) break;                       // warp-uniform
         int more = 0;
         if (lane == 0) more = cw.advance() ? 1 : 0;
         if (!__shfl_sync(full, more, 0)) break;

@@ -8,6 +8,7 @@ include/metis_b200.h.  There is no CPU path: without CUDA these functions raise.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -178,7 +179,7 @@ class HetSearcher:
         self.capacity = 0
         self.workspace = None
         self.summary_host = torch.zeros(C.sizeof(native.MetisSearchSummary), dtype=torch.uint8).pin_memory()
-        self._host_buf: Dict[str, torch.Tensor] = {}
+        self._host_buf: Dict[str, list] = {}                 # name -> [[pinned tensor, weakref to the array handed out]]
         self.records = self.detail = None
         self._fixed_capacity = capacity
         self.rebind()
@@ -220,16 +221,30 @@ class HetSearcher:
         return native.MetisSearchSummary.from_buffer_copy(self.summary_host.numpy().tobytes())
 
     def _to_host(self, name: str, dev_tensor: torch.Tensor, stream: torch.cuda.Stream) -> np.ndarray:
-        """Device -> pinned host buffer (grow-only, reused per output) -> fresh numpy array."""
+        """Device -> pinned host memory, handed out WITHOUT another copy.
+
+        A pinned buffer is reused only when the array handed out from it last time is gone (its weak reference is
+        dead: numpy views keep their root array alive), so a result a caller still holds is never overwritten; a
+        caller that keeps every result makes each call allocate a new buffer (slow, correct)."""
         n = dev_tensor.numel() * dev_tensor.element_size()
-        buf = self._host_buf.get(name)
-        if buf is None or buf.numel() < n:
-            buf = self._host_buf[name] = torch.empty(max(n + n // 8, 1 << 16), dtype=torch.uint8).pin_memory()
-        view = buf[:n]
+        pool = self._host_buf.setdefault(name, [])
+        slot = None
+        for entry in pool:
+            if entry[1] is None or entry[1]() is None:
+                if entry[0].numel() >= n:
+                    slot = entry
+                    break
+        if slot is None:
+            pool[:] = [e for e in pool if not (e[1] is None or e[1]() is None)]     # too small and free: drop
+            slot = [torch.empty(max(n + n // 8, 1 << 16), dtype=torch.uint8).pin_memory(), None]
+            pool.append(slot)
+        view = slot[0][:n]
         with torch.cuda.stream(stream):
             view.copy_(dev_tensor.reshape(-1).view(torch.uint8), non_blocking=True)
         stream.synchronize()
-        return view.numpy().copy()
+        arr = view.numpy()
+        slot[1] = weakref.ref(arr)
+        return arr
 
     def run(self, stream: Optional[torch.cuda.Stream] = None) -> HetSearchOutput:
         """launch + synchronise + bring results to the host; grows the record buffer if needed."""

@@ -194,7 +194,7 @@ int hostsim_generate_rows(const MetisCompRec *recs, int64_t ncomp, const uint8_t
 }
 
 // developer statistics: LayerComputeBalancer runs per inter-stage plan (0 = plan without a valid strategy)
-int hostsim_runs_per_plan(const MetisProblem *p, const MetisPlanSpace *sp, int32_t *runs_out) {
+int hostsim_runs_per_plan(const MetisProblem *p, const MetisPlanSpace *sp, int32_t *runs_out, int32_t *hints_out) {
     std::vector<double> dlay;
     const Tables T = host_tables(*p, dlay);
     MetisSearchSummary sum;
@@ -211,6 +211,16 @@ int hostsim_runs_per_plan(const MetisProblem *p, const MetisPlanSpace *sp, int32
         if (!decode(*sp, ordinal, pd)) continue;
         PlanEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS> probe(T, w);
         if (probe.begin(pd) != 1) continue;
+        if (hints_out) {                                  // the scheduling hint of the bulk round (-1: plan ends there)
+            MetisSearchSummary scratch_sum;
+            memset(&scratch_sum, 0, sizeof(scratch_sum));
+            scratch_sum.fatal_ordinal = ~0ULL;
+            scratch_sum.best.cost = INFINITY;
+            HostSink quiet{nullptr, 0, nullptr, 0, &scratch_sum};
+            int hint = 0;
+            const bool cont = first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS, false>(T, w, quiet, true, pd, hint);
+            hints_out[ordinal] = cont ? hint : -1;
+        }
         const uint64_t before = sum.num_balancer_runs;
         CoopEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS, OneLane> ev(T, w, mail, lanes);
         ev.run_chain(pd, sink, false);

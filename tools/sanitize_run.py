@@ -16,7 +16,9 @@ for name in sys.argv[1:] or ['c2_v100', 'mix32']:
     cfg = ModelConfig('SYN', w.num_layers, w.sequence_length, w.vocab_size, w.hidden_size, 32)
     seqs = list(itertools.permutations(w.device_types()))
     problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
-    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance, w.max_permute_len)
+    # rows written by the GPU (het_rows_kernel) so that kernel runs under the sanitizer too
+    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance, w.max_permute_len,
+                                     device_rows=True)
     dp = search.DeviceProblem(problem, space, 'cuda:0')
     for coop in (1, 2 ** 31 - 1):
         s = search.HetSearcher(dp, want_records=True, want_detail=True, want_ranking=True)

@@ -170,11 +170,13 @@ class HetSearchResult(Sequence):
     sort) taken from the device sort's permutation instead of sorting Python objects."""
 
     def __init__(self, candidates, rank_order: Optional[np.ndarray], summary: Dict[str, int],
-                 timings: Optional[Dict[str, float]] = None):
+                 timings: Optional[Dict[str, float]] = None, ranker=None, best_key: Optional[Tuple[int, int]] = None):
         self.candidates = candidates
-        self.rank_order = rank_order
+        self.rank_order = rank_order          # permutation of sorted(..., key=cost); computed on first use (``ranker``)
         self.summary = summary
         self.timings = timings or {}
+        self._ranker = ranker                 # () -> uint32 permutation, the stable device sort by cost
+        self._best_key = best_key             # (ordinal, step) of the argmin found by the search kernels
 
     def __len__(self) -> int:
         return len(self.candidates)
@@ -209,15 +211,25 @@ class HetSearchResult(Sequence):
 
     def ranked(self, k: Optional[int] = None) -> List[Tuple]:
         """The first ``k`` (default: all) entries of ``sorted(result, key=lambda kv: kv[6])``."""
+        if self.rank_order is None:
+            self.rank_order = self._ranker() if self._ranker is not None \
+                else np.argsort(self.candidates.cost, kind='stable')
+            self._ranker = None
         order = self.rank_order
-        if order is None:
-            order = np.argsort(self.candidates.cost, kind='stable')
         if k is not None:
             order = order[:k]
         return self.candidates.tuples(order)
 
     def best(self) -> Optional[Tuple]:
-        """argmin (cost, position): the first entry of the ranked list."""
+        """argmin (cost, position): the first entry of the ranked list.  The search kernels reduce it on the device
+        (het_finalize_kernel: lowest cost, then lowest ordinal, then lowest step), so no sort is needed for it."""
+        if self.rank_order is None and self._best_key is not None and len(self):
+            rec = self.candidates.records
+            key = (rec['ordinal'].astype(np.uint64) << np.uint64(16)) | rec['step'].astype(np.uint64)
+            want = (np.uint64(self._best_key[0]) << np.uint64(16)) | np.uint64(self._best_key[1])
+            i = int(np.searchsorted(key, want))
+            if i < len(rec) and key[i] == want:
+                return self.candidates.tuples([i])[0]
         top = self.ranked(1)
         return top[0] if top else None
 
@@ -252,7 +264,7 @@ def _engine(problem, space, device, rank: int, world: int, stride: int):
     eng = _ENGINES.get(key)
     if eng is None:
         dp = search.DeviceProblem(problem, space, dev)
-        searcher = search.HetSearcher(dp, rank, world, want_records=True, want_detail=True, want_ranking=world == 1,
+        searcher = search.HetSearcher(dp, rank, world, want_records=True, want_detail=True, want_ranking=False,
                                       detail_to_host=False, detail_stride=stride)
         _ENGINES[key] = (dp, searcher)
         return dp, searcher
@@ -303,7 +315,7 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
     dp, searcher = _engine(problem, space, dev, rank, world, stride)
     dp.upload()
     failure = None
-    out = None
+    out = best = None
     try:
         out = searcher.run()
     except Exception as exc:                                  # noqa: BLE001 - re-raised below on every rank
@@ -312,7 +324,8 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
         failure = exc
     if dist:
         # a rank whose search raised must not leave the others waiting in a collective
-        summary = search.global_counters(out.summary if out is not None else {}, dp.device, int(failure is not None))
+        summary, best = search.global_exchange(out.summary if out is not None else {}, out.best if out is not None else None,
+                                               dp.device, int(failure is not None))
         if summary['any_rank_failed']:
             raise failure if failure is not None else native.MetisNativeError('the search failed on another rank')
         if summary['global_fatal_ordinal'] < 2 ** 62:
@@ -320,9 +333,9 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
                            fatal_aux=summary['global_fatal_aux'])
         else:
             summary['fatal_ordinal'] = 2 ** 64 - 1
-            out = search.gather_records(out, searcher)
+            out = search.gather_records(out, searcher, want_rank=False, counts=summary['records_per_rank'])
     else:
-        summary = out.summary
+        summary, best = out.summary, out.best
     if summary['fatal_ordinal'] != 2 ** 64 - 1:
         # the reference dies at that plan: nothing is returned (quirk Q8)
         search.raise_fatal(summary, problem)
@@ -330,8 +343,12 @@ def cost_het_cluster(args: argparse.Namespace, gpu_cluster, profile_data: Dict, 
     # the row blob of the engine is rewritten by the next call: a lazy result keeps its own copy (a few MB, on the GPU)
     cand = search.Candidates(out.records, out.detail, space, seqs, detail_dev=out.detail_dev,
                              rows_dev=dp.rows_device().clone())
+    # sorted(result, key=cost) is the CALLER's step in the reference (cost_het_cluster.py:76): its permutation is
+    # computed by the device sort when ranked() is first asked for; best() needs no sort at all
     result = HetSearchResult(cand, out.rank_order,
-                             dict(summary, num_plans=space.num_plans, corrected=tuple(sorted(corrected))))
+                             dict(summary, num_plans=space.num_plans, corrected=tuple(sorted(corrected))),
+                             ranker=search.make_ranker(searcher, out.records_dev) if len(out.records) else None,
+                             best_key=(best[1], best[2]) if best else None)
     result.timings = {'flatten_enumerate_s': t1 - t0, 'gpu_search_s': t2 - t1,
                       'decode_columns_s': time.perf_counter() - t2}
     return result

@@ -956,12 +956,13 @@ static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg,
     size_t chain_dyn = 0;
     unsigned int chain_off = 0;
     const int forced = env_int("METIS_CHAIN_THREADS", 32, 512, 0);
+    const int chain_pad = env_int("METIS_CHAIN_SMEM_PAD", 0, 200 * 1024, 0);     // developer knob: fewer resident warps
     for (int pass = 0; pass < 2 && chain_threads == 0; ++pass) {       // second pass: tables in global memory
         int best_warps = 0;
         for (int threads = 64; threads <= 512; threads *= 2) {
             if (forced && threads != ((forced + 31) & ~31)) continue;
             const unsigned int off = chain_smem_tables ? blob_pad : 0u;
-            const size_t dyn = off + (size_t)(threads / 32) * per_warp;
+            const size_t dyn = off + (size_t)(threads / 32) * per_warp + (size_t)chain_pad;
             if (dyn > (size_t)smem_optin) continue;
             if (dyn > 48 * 1024) {
                 e = cudaFuncSetAttribute(chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

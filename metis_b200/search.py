@@ -439,74 +439,122 @@ def materialize(records: np.ndarray, detail: np.ndarray, space: flatten.FlatPlan
 # ---------------------------------------------------------------------------------------------
 # multi-GPU: shard by plan ordinal, one collective at the end
 # ---------------------------------------------------------------------------------------------
-def global_best(local_best: Optional[Tuple[float, int, int, int, int]], device) -> Optional[Tuple]:
-    """all_gather of one 32-byte (cost, ordinal, step, meta) record per rank, then exact lexicographic min."""
+def _gather_rows(vec: torch.Tensor) -> torch.Tensor:
+    """all_gather of one small vector per rank -> [world, len] on the host (ONE collective, one synchronisation)."""
     import torch.distributed as dist
     world = dist.get_world_size()
-    mine = torch.zeros(4, dtype=torch.float64, device=device)
-    if local_best is not None:
-        cost, ordinal, step, nrep, nstage = local_best
-        mine[0], mine[1], mine[2], mine[3] = cost, float(ordinal), float(step), float(nrep * 256 + nstage)
-    else:
-        mine[0], mine[1] = float('inf'), float(2 ** 40)
-    allb = torch.empty(4 * world, dtype=torch.float64, device=device)
-    dist.all_gather_into_tensor(allb, mine)
-    rows = allb.view(world, 4).cpu().tolist()
-    rows = [r for r in rows if r[1] < 2 ** 40]
-    if not rows:
+    out = torch.empty(world * vec.numel(), dtype=vec.dtype, device=vec.device)
+    dist.all_gather_into_tensor(out, vec)
+    return out.view(world, vec.numel()).cpu()
+
+
+_NO_ORDINAL = 2 ** 40
+_COUNTER_KEYS = ['num_records', 'num_partition_calls', 'num_balancer_runs', 'num_keyerror']
+
+
+def _best_row(local_best: Optional[Tuple[float, int, int, int, int]]) -> List[int]:
+    """(cost bits, ordinal, step, meta) as int64; a rank without records sends an ordinal nobody has."""
+    if local_best is None:
+        return [0, _NO_ORDINAL, 0, 0]
+    cost, ordinal, step, nrep, nstage = local_best
+    return [int(np.array([cost], dtype=np.float64).view(np.int64)[0]), int(ordinal), int(step), int(nrep) * 256 + int(nstage)]
+
+
+def _pick_best(rows: List[List[int]]) -> Optional[Tuple]:
+    """Exact lexicographic min of (cost, ordinal, step) over the ranks' bests."""
+    cand = []
+    for bits, o, st, m in rows:
+        if o < _NO_ORDINAL:
+            cand.append((float(np.array([bits], dtype=np.int64).view(np.float64)[0]), int(o), int(st), int(m)))
+    if not cand:
         return None
-    c, o, s, m = min(rows, key=lambda r: (r[0], r[1], r[2]))
-    return (c, int(o), int(s), int(m) // 256, int(m) % 256)
+    c, o, st, m = min(cand, key=lambda r: (r[0], r[1], r[2]))
+    return (c, o, st, m // 256, m % 256)
 
 
-def global_counters(summary: Dict[str, int], device, local_error: int = 0) -> Dict[str, int]:
-    """Sum of the counters over the ranks, the lowest fatal ordinal with ITS code and aux, and an error flag
-    (``any_rank_failed``) so that a rank whose search raised can make every rank raise instead of hanging."""
-    import torch.distributed as dist
-    keys = ['num_records', 'num_partition_calls', 'num_balancer_runs', 'num_keyerror']
-    t = torch.tensor([summary.get(k, 0) for k in keys] + [int(local_error != 0)], dtype=torch.int64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    vals = t.cpu().tolist()
+def _merge_counters(summary: Dict[str, int], rows: List[List[int]]) -> Dict[str, int]:
+    """rows[r] = counters (4), error flag, fatal ordinal, fatal code, fatal aux of rank r."""
     out = dict(summary)
-    out.update({k: int(v) for k, v in zip(keys, vals)})
-    out['any_rank_failed'] = int(vals[-1])
-    none = 2 ** 40
-    fo = min(summary.get('fatal_ordinal', 2 ** 64 - 1), none)
-    packed = (fo << 8) | (summary.get('fatal_code', 0) & 0xFF)          # MIN: lowest ordinal, with its code
-    f = torch.tensor([packed], dtype=torch.int64, device=device)
-    dist.all_reduce(f, op=dist.ReduceOp.MIN)
-    g = int(f.item())
-    gfo = g >> 8
-    aux = torch.tensor([summary.get('fatal_aux', 0) if (fo == gfo and fo < none) else 0], dtype=torch.int64, device=device)
-    dist.all_reduce(aux, op=dist.ReduceOp.MAX)
-    out['global_fatal_ordinal'] = gfo if gfo < none else 2 ** 62
-    out['global_fatal_code'] = g & 0xFF if gfo < none else 0
-    out['global_fatal_aux'] = int(aux.item())
+    for i, k in enumerate(_COUNTER_KEYS):
+        out[k] = int(sum(r[i] for r in rows))
+    out['records_per_rank'] = [int(r[0]) for r in rows]
+    out['any_rank_failed'] = int(sum(r[4] for r in rows))
+    fatal = [(r[5], r[6], r[7]) for r in rows if r[5] < _NO_ORDINAL]
+    if fatal:
+        fo, code, aux = min(fatal)                            # the lowest ordinal, with ITS code and aux
+        out.update(global_fatal_ordinal=int(fo), global_fatal_code=int(code), global_fatal_aux=int(aux))
+    else:
+        out.update(global_fatal_ordinal=2 ** 62, global_fatal_code=0, global_fatal_aux=0)
     return out
 
 
-def gather_records(out: HetSearchOutput, searcher: HetSearcher) -> HetSearchOutput:
+def _counter_row(summary: Dict[str, int], local_error: int) -> List[int]:
+    fo = min(summary.get('fatal_ordinal', 2 ** 64 - 1), _NO_ORDINAL)
+    return [int(summary.get(k, 0)) for k in _COUNTER_KEYS] + \
+        [int(local_error != 0), int(fo), int(summary.get('fatal_code', 0)) & 0xFF, int(summary.get('fatal_aux', 0))]
+
+
+def global_best(local_best: Optional[Tuple[float, int, int, int, int]], device) -> Optional[Tuple]:
+    """all_gather of one (cost, ordinal, step, meta) record per rank, then the exact lexicographic min."""
+    rows = _gather_rows(torch.tensor(_best_row(local_best), dtype=torch.int64, device=device)).tolist()
+    return _pick_best(rows)
+
+
+def global_counters(summary: Dict[str, int], device, local_error: int = 0) -> Dict[str, int]:
+    """Sum of the counters over the ranks, the records of every rank, the lowest fatal ordinal with ITS code and aux,
+    and an error flag (``any_rank_failed``) so that a rank whose search raised makes every rank raise instead of
+    leaving the others in a collective."""
+    rows = _gather_rows(torch.tensor(_counter_row(summary, local_error), dtype=torch.int64, device=device)).tolist()
+    return _merge_counters(summary, rows)
+
+
+def global_exchange(summary: Dict[str, int], local_best, device, local_error: int = 0):
+    """global_counters and global_best in ONE collective (the API path)."""
+    vec = torch.tensor(_counter_row(summary, local_error) + _best_row(local_best), dtype=torch.int64, device=device)
+    rows = _gather_rows(vec).tolist()
+    return _merge_counters(summary, [r[:8] for r in rows]), _pick_best([r[8:] for r in rows])
+
+
+def make_ranker(searcher: 'HetSearcher', records_dev: torch.Tensor):
+    """() -> permutation of ``sorted(records, key=cost)`` (stable): the device sort on a private copy of the ordered
+    records, run when a caller first asks for the ranking."""
+    snap = records_dev.clone()
+    n = snap.numel() // 2
+    dev = searcher.dp.device
+
+    def rank() -> np.ndarray:
+        with torch.cuda.device(dev):
+            s = torch.cuda.current_stream(dev)
+            perm = searcher.sort_records(n, native.SORT_BY_COST_STABLE, s, want_perm=True, buf=snap)
+            s.synchronize()
+            return perm.cpu().numpy().view(np.uint32)
+    return rank
+
+
+def gather_records(out: HetSearchOutput, searcher: HetSearcher, want_rank: bool = True,
+                   counts: Optional[List[int]] = None) -> HetSearchOutput:
     """Every rank receives every rank's records (+ detail rows): padded tensor all_gathers over NCCL (no pickling),
     then the merged list is put into estimate_costs order and ranked by the device sort."""
     import torch.distributed as dist
     dev = searcher.dp.device
     world = dist.get_world_size()
     n_local = len(out.records)
-    counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    counts[dist.get_rank()] = n_local
-    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    counts = counts.cpu().tolist()
+    if counts is None:                                        # records of every rank (global_counters has them too)
+        mine = torch.zeros(world, dtype=torch.int64, device=dev)
+        mine[dist.get_rank()] = n_local
+        dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+        counts = mine.cpu().tolist()
     cap = max(max(counts), 1)
     stride = searcher.detail_stride
     with torch.cuda.device(dev):
-        rec_pad = torch.zeros(cap * 2, dtype=torch.int64, device=dev)
+        rec_pad = torch.empty(cap * 2, dtype=torch.int64, device=dev)
         rec_pad[:2 * n_local] = out.records_dev
         rec_g = torch.empty(world * cap * 2, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(rec_g, rec_pad)
         rec_all = torch.cat([rec_g[2 * cap * r:2 * cap * r + 2 * counts[r]] for r in range(world)]).contiguous()
         det_all = None
         if out.detail_dev is not None:
-            det_pad = torch.zeros((cap, stride), dtype=torch.uint8, device=dev)
+            det_pad = torch.empty((cap, stride), dtype=torch.uint8, device=dev)
             det_pad[:n_local] = out.detail_dev
             det_g = torch.empty((world * cap, stride), dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(det_g, det_pad)
@@ -516,9 +564,11 @@ def gather_records(out: HetSearchOutput, searcher: HetSearcher) -> HetSearchOutp
         perm = searcher.sort_records(n, native.SORT_POSITION, s, want_perm=True, buf=rec_all)
         records = searcher._to_host('records_all', rec_all[:2 * n], s).view(native.RECORD_DTYPE)
         detail_dev = det_all.index_select(0, perm.long()) if det_all is not None else None
-        by_cost = rec_all[:2 * n].clone()
-        rank = searcher.sort_records(n, native.SORT_BY_COST_STABLE, s, want_perm=True, buf=by_cost)
-        rank_order = searcher._to_host('rank_all', rank, s).view(np.uint32)
+        rank_order = None
+        if want_rank:
+            by_cost = rec_all[:2 * n].clone()
+            rank = searcher.sort_records(n, native.SORT_BY_COST_STABLE, s, want_perm=True, buf=by_cost)
+            rank_order = searcher._to_host('rank_all', rank, s).view(np.uint32)
         detail = None
         if detail_dev is not None and searcher.detail_to_host:
             detail = searcher._to_host('detail_all', detail_dev, s).reshape(n, stride)

@@ -161,6 +161,15 @@ assert best[:3] == (float(arr['cost'][i]), int(arr['ordinal'][i]), int(arr['step
 c = meta['counters']
 assert (counters['num_records'], counters['num_partition_calls'], counters['num_balancer_runs']) == (c['C'], c['B'], c['runs']), counters
 assert 0 < sm.num_records < c['C']
+# the API path's single collective gives the same counters / winner, the records of every rank, and spreads an error
+both, best2 = search.global_exchange(dict(num_records=int(sm.num_records), num_partition_calls=int(sm.num_partition_calls),
+    num_balancer_runs=int(sm.num_balancer_runs), num_keyerror=int(sm.num_keyerror), fatal_ordinal=int(sm.fatal_ordinal)),
+    local_best, 'cpu', local_error=int(rank == 1))
+assert best2 == best and both['num_records'] == c['C'] and both['any_rank_failed'] == 1
+assert sum(both['records_per_rank']) == c['C'] and both['records_per_rank'][rank] == int(sm.num_records)
+assert both['global_fatal_ordinal'] == 2 ** 62
+fatal = search.global_counters(dict(fatal_ordinal=1000 + rank, fatal_code=3 + rank, fatal_aux=70 + rank), 'cpu')
+assert (fatal['global_fatal_ordinal'], fatal['global_fatal_code'], fatal['global_fatal_aux']) == (1000, 3, 70)
 dist.barrier(); dist.destroy_process_group()
 print('rank', rank, 'ok')
 '''

@@ -46,10 +46,15 @@ def run_point(ndev, ntypes, variance, mpl, check):
     seqs = list(itertools.permutations(w.device_types()))
     t0 = time.perf_counter()
     problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
+    # the host lists the compositions; the GPU writes the rows
     space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance,
-                                     w.max_permute_len)
+                                     w.max_permute_len, device_rows=True)
     enum_ms = 1e3 * (time.perf_counter() - t0)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     dp = search.DeviceProblem(problem, space, 'cuda:0')
+    torch.cuda.synchronize()
+    upload_ms = 1e3 * (time.perf_counter() - t1)              # arena allocation + H2D + row kernel (first call)
     searcher = search.HetSearcher(dp, want_records=True, want_detail=False)
     out = searcher.run()
     best_only = search.HetSearcher(dp, want_records=False)
@@ -60,7 +65,7 @@ def run_point(ndev, ntypes, variance, mpl, check):
     a.record(); best_only.launch(); b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b)
     row = {'ndev': ndev, 'types': ntypes, 'variance': variance, 'mpl': mpl, 'layers': w.num_layers, 'gbs': w.gbs,
-           'A_plans': space.num_plans, 'B_partition_calls': out.summary['num_partition_calls'],
+           'A_plans': space.num_plans, 'row_bytes': int(space.rows_total_bytes), 'upload_rows_ms': upload_ms, 'B_partition_calls': out.summary['num_partition_calls'],
            'runs': out.summary['num_balancer_runs'], 'C_costed': out.summary['num_records'],
            'keyerror': out.summary['num_keyerror'],
            'fatal_ordinal': None if out.summary['fatal_ordinal'] == 2 ** 64 - 1 else out.summary['fatal_ordinal'],

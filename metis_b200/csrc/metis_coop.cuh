@@ -976,29 +976,48 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform, ONE> {
     }
 
     // cost_het_cluster.py:31-48 for one inter-stage plan with IntraStagePlanGenerator.has_next
-    // (search_space/plan.py:192-226) inlined: the whole chain, depth first.  `skip_first` = the first partition
-    // attempt was already counted by the caller's first-task round (it is recomputed, not recounted).
+    // (search_space/plan.py:192-226) inlined: the whole chain, depth first.
+    // How the chain starts (the bulk round of the search evaluates the first partition attempt of every plan):
+    //   kFresh   nothing was done yet
+    //   kReplay  the first attempt was counted by the bulk round; it is recomputed here, not recounted
+    //   kRetry   the first attempt ran out of memory and the bulk round re-weighted the stage performance
+    //            (load_balancer.py:137-141): continue with attempt 2 from `perf[s * perf_stride]`
+    //   kAdvance the first attempt ran out of memory and no re-weighting exists (:142-143): the first strategy is
+    //            over, continue with the next one (memory_state None, plan.py:225)
+    enum Start { kFresh = 0, kReplay = 1, kRetry = 2, kAdvance = 3 };
     template <class Sink>
-    MB_HD void run_chain(const PlanDesc &plan, Sink &sink, bool skip_first) {
+    MB_HD void run_chain(const PlanDesc &plan, Sink &sink, int start, const double *perf = nullptr, size_t perf_stride = 0) {
         begin_coop(plan);
         bool started = false, have_state = false;
+        bool skip_first = start == kReplay;
         int nrep = 0, step = 0;
+        if (start == kRetry) {
+            METIS_PAR(x, s, pd.S) w.perf[s] = perf[(size_t)s * perf_stride];
+            x.sync();
+        }
 #pragma unroll 1
         for (;;) {
             if (nrep == 1) return;                            // plan.py:194-195
             int attempt = 0;
 #pragma unroll 1
             for (;;) {
-                if (!started) started = true;                 // first strategy that can be valid (see begin)
-                else if (!next_strategy_coop(have_state)) return;  // :203-204
+                int first_attempt = 1;
+                if (!started) {                               // first strategy that can be valid (see begin)
+                    started = true;
+                    if (start == kAdvance && !next_strategy_coop(false)) return;
+                    if (start == kRetry) first_attempt = 2;
+                } else if (!next_strategy_coop(have_state)) return;   // :203-204
                 if (!this->valid()) continue;
-                if (!skip_first) sink.partition_call();
-                x.mark(2);
-                int rc = compute_performance_coop();
-                if (rc) { sink.fatal(pd.ordinal, rc, aux); return; }
+                int rc = 0;
+                if (first_attempt == 1) {
+                    if (!skip_first) sink.partition_call();
+                    x.mark(2);
+                    rc = compute_performance_coop();
+                    if (rc) { sink.fatal(pd.ordinal, rc, aux); return; }
+                }
                 attempt = 0;
 #pragma unroll 1
-                for (int a = 1; a <= 3; ++a) {                // LayerLoadBalancer.partition_layer (:121-144)
+                for (int a = first_attempt; a <= 3; ++a) {    // LayerLoadBalancer.partition_layer (:121-144)
                     if (!skip_first) sink.balancer_run();
                     skip_first = false;
                     rc = balance_coop();

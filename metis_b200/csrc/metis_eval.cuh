@@ -1221,9 +1221,8 @@ struct PlanEvaluator {
     // capacity re-weighting.  returns 1 = partition accepted (w.mstate = memory_state), 2 = retry
     // with the adjusted w.perf, 0 = (None, -1, None), <0 = fatal (negated code).  After the third
     // failed attempt the reference still evaluates _adj_compute_performance and discards it; that
-    // call is skipped here.  `defer`: report 2 on the first out-of-memory state without re-weighting (the
-    // first-task round hands such plans to the chain kernel, which replays the attempt).
-    MB_HD int memory_phase(int attempt, bool defer = false) {
+    // call is skipped here.
+    MB_HD int memory_phase(int attempt) {
         const int S = pd.S;
         const bool one_type = ONE || T.p.num_types == 1;
         const int type0 = T.run_type[pd.ns * T.p.num_types];
@@ -1275,7 +1274,6 @@ struct PlanEvaluator {
             return 1;
         }
         if (attempt >= 3) return 0;
-        if (defer) return 2;
         x.mark(21);
         const int rc = adjust_performance();
         if (rc < 0) return rc;
@@ -1541,13 +1539,16 @@ struct PlanEvaluator {
 // run (their first strategy is partitioned at the first attempt, which also ends the chain,
 // plan.py:194-195); a few per cent need 10-36 *sequential* runs.  The first attempt of the first
 // strategy of every admitted plan is therefore evaluated with 32 plans per warp in lockstep; a
-// plan whose first attempt runs out of memory is handed, unchanged, to the chain kernel (one warp
-// per plan, metis_coop.cuh), which replays that attempt and walks the rest of the chain.
+// plan whose first attempt runs out of memory is handed to the chain kernel (one warp per plan,
+// metis_coop.cuh), which walks the rest of the chain: from attempt 2 with the re-weighted stage
+// performance left in w.perf (`resume` = CoopEvaluator::kRetry), or from the next strategy when the
+// reference finds no re-weighting (kAdvance).
 // returns true when the plan continues in the chain kernel; `chain_hint` then estimates how long its chain is
 // (PlanEvaluator::halvings; used only to start long chains first).
 // ---------------------------------------------------------------------------
 template <int MAXS, int MAXL, bool ONE, class X = Serial, class Sink>
-MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool has, const PlanDesc &plan, int &chain_hint) {
+MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool has, const PlanDesc &plan, int &chain_hint,
+                      int &resume) {
     // X = Lockstep (device, called by all 32 lanes of a warp, with or without a plan): the lanes are re-joined
     // between the phases and inside the balancer.  X = Serial: one thread on its own.
     PlanEvaluator<MAXS, MAXL, X, ONE> ev(T, w);
@@ -1575,10 +1576,13 @@ MB_HD bool first_task(const Tables &T, Scratch<MAXS, MAXL> &w, Sink &sink, bool 
     ev.x.rejoin(has);
     bool costing = false;
     if (has) {                                               // ---- M ----
-        const int r = ev.memory_phase(1, true);
+        const int r = ev.memory_phase(1);
         if (r < 0) sink.fatal(plan.ordinal, -r, ev.aux);
-        else if (r == 2) { cont = true; chain_hint = ev.halvings(); }    // out of memory: the rest in the chain kernel
-        else costing = true;                                 // r == 1: partition accepted at the first attempt
+        else if (r != 1) {                                   // out of memory: the rest in the chain kernel
+            cont = true;
+            chain_hint = ev.halvings();
+            resume = r == 2 ? 2 : 3;                         // CoopEvaluator::kRetry (w.perf re-weighted) : kAdvance
+        } else costing = true;                               // partition accepted at the first attempt
     }
     sink.phase(4);
     ev.x.rejoin(costing);

@@ -343,7 +343,14 @@ struct SearchLists {
     unsigned int *ctl;            // [0] admitted [1] bulk fetch cursor [2] continuations [3] chain fetch cursor
                                   // [16..16+128) histogram by stage count, [160+16..) scatter cursors
     long long bulk_min;           // lists shorter than this skip the bulk round
+    // hand-over of the bulk round's failed first attempts (CoopEvaluator::kRetry): the re-weighted stage performance of
+    // continuation c, stage s, at perf[s * save_cap + c] for c < save_cap (later continuations replay the attempt);
+    // src[i] = c of the i-th entry of list B after het_order_kernel
+    double *perf;
+    unsigned int *src;
+    unsigned int save_cap;
 };
+// list entry flags: bit 0 = first attempt counted by the bulk round, bits 1-2 = CoopEvaluator::Start, bits 8-14 = hint
 constexpr int kCtlHist = 16, kCtlCursor = 16 + 160;
 constexpr int kCtlHist2 = 512, kCtlCursor2 = 512 + 160;   // ordering of the continuations by chain hint
 constexpr int kCtlHist3 = 832, kCtlCursor3 = 832 + 160;   // ordering of the admitted plans by chain hint (no bulk round)
@@ -467,8 +474,8 @@ het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
             const bool has = pos < (long long)n;
             uint4 e = make_uint4(0, 0, 0, 0);
             if (has) { e = ls.b[pos]; decode_entry(sp, e, pd); }
-            int hint = 0;
-            const bool cont = first_task<MAXS, MAXL, ONE, Lockstep>(T, w, sink, has, pd, hint);
+            int hint = 0, start = 1;                         // CoopEvaluator::kReplay unless first_task says more
+            const bool cont = first_task<MAXS, MAXL, ONE, Lockstep>(T, w, sink, has, pd, hint, start);
             const unsigned m = __ballot_sync(0xFFFFFFFFu, cont);
             if (m) {
                 const int leader = __ffs(m) - 1;
@@ -477,8 +484,14 @@ het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
                 at = __shfl_sync(0xFFFFFFFFu, at, leader);
                 if (cont) {
                     const unsigned key = hint < 0 ? 0u : (hint > 127 ? 127u : (unsigned)hint);
-                    e.y = 1u | (key << 8);
-                    ls.a[at + __popc(m & ((1u << lane) - 1u))] = e;
+                    const unsigned int c = at + __popc(m & ((1u << lane) - 1u));
+                    if (start == 2) {                        // kRetry: hand the re-weighted performance over
+                        if (c < ls.save_cap) {
+                            for (int s = 0; s < pd.S; ++s) ls.perf[(size_t)s * ls.save_cap + c] = w.perf[s];
+                        } else start = 1;                    // no room: the chain kernel replays the attempt
+                    }
+                    e.y = 1u | ((unsigned)start << 1) | (key << 8);
+                    ls.a[c] = e;
                     atomicAdd(&ls.ctl[kCtlHist2 + key], 1u);
                 }
             }
@@ -503,7 +516,9 @@ het_order_kernel(const SearchLists ls) {
     for (long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x; pos < (long long)n; pos += span) {
         const uint4 e = ls.a[pos];
         const unsigned key = (e.y >> 8) & 0x7Fu;
-        ls.b[s_base[key] + atomicAdd(&ls.ctl[kCtlCursor2 + key], 1u)] = e;
+        const unsigned int to = s_base[key] + atomicAdd(&ls.ctl[kCtlCursor2 + key], 1u);
+        ls.b[to] = e;
+        ls.src[to] = (unsigned int)pos;                      // where its saved stage performance lives
     }
 }
 
@@ -655,7 +670,11 @@ het_chain_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
         PlanDesc pd;
         decode_entry(sp, e, pd);
         lanes.mark(1);
-        ev.run_chain(pd, sink, (e.y & 1u) != 0u);
+        // flags: not touched by a bulk round -> kFresh; else what first_task decided (kReplay / kRetry / kAdvance)
+        const int start = (e.y & 1u) ? (int)((e.y >> 1) & 3u) : 0;
+        const double *perf = nullptr;
+        if (start == 2) perf = ls.perf + __ldcg(&ls.src[i]);
+        ev.run_chain(pd, sink, start, perf, (size_t)ls.save_cap);
         lanes.mark(0);
     }
     sink.leader = true;                                      // lanes 1-31 carry empty counters / bests
@@ -884,14 +903,18 @@ static int64_t shard_plan_slots(int64_t num_plans, const MetisShard *sh) {
 constexpr int64_t kFixedWs = 16384;                // summary + counters + list control words
 constexpr int64_t kMaxBlocks = 4096;               // per-block best records (bulk round + chain kernel)
 
+// continuations of the bulk round whose re-weighted stage performance is kept for the chain kernel (the others replay
+// their first attempt): a quarter of the plans, at most 128 Ki
+static int64_t save_slots(int64_t cap) { return cap / 4 < 131072 ? (cap / 4 > 0 ? cap / 4 : 1) : 131072; }
+
 int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans, int32_t max_stage) {
     if (check_problem(problem)) return METIS_E_ARG;
-    (void)max_stage;
     if (num_plans < 0) return METIS_E_ARG;
     const BlobLayout lay = make_layout(*problem);
     const int64_t cap = (num_plans + 127) & ~(int64_t)127;      // worst case: every plan of the shard is admitted
+    const int64_t stages = max_stage < 1 ? 1 : (max_stage > METIS_MAX_STAGES ? METIS_MAX_STAGES : max_stage);
     return 256 + kFixedWs + (int64_t)lay.rsum + (int64_t)align16(lay.rsum_bytes) + kMaxBlocks * (int64_t)sizeof(MetisRecord) +
-           2 * cap * (int64_t)sizeof(uint4) + 1024;
+           2 * cap * (int64_t)sizeof(uint4) + cap * 4 + save_slots(cap) * stages * 8 + 1024;
 }
 
 struct Workspace {
@@ -947,6 +970,9 @@ static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg,
     ls.a = reinterpret_cast<uint4 *>(ws.lists);
     ls.b = ls.a + cap;
     ls.ctl = ws.ctl;
+    ls.src = reinterpret_cast<unsigned int *>(ls.b + cap);
+    ls.perf = reinterpret_cast<double *>(ls.src + cap);     // cap is a multiple of 128: 8-byte aligned
+    ls.save_cap = (unsigned int)save_slots(cap);
 
     // ---- chain kernel: warps per block chosen so that tables + per-warp scratch fill the SM with warps ----
     auto chain = het_chain_kernel<MAXS, MAXL, ONE>;

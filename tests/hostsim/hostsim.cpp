@@ -141,8 +141,9 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
         }
     } else {
         // the search kernel's schedule: mode 1 = first-task round (one plan per thread) + chain evaluator for the
-        // plans that continue; mode 2 = chain evaluator for every admitted plan; mode 3 = mode 2 with the
-        // iterations of every PAR section visited in reverse order (they must be independent)
+        // plans that continue, from where the first-task round left them; mode 4 = the same, the chain evaluator
+        // replaying the first attempt (hand-over store full); mode 2 = chain evaluator for every admitted plan;
+        // mode 3 = mode 2 with the iterations of every PAR section visited in reverse order (they must be independent)
         static thread_local CoopMail mail;
         OneLane lanes;
         lanes.reverse = mode == 3;
@@ -156,14 +157,17 @@ int hostsim_het_search(const MetisProblem *p, const MetisPlanSpace *sp, const Me
                 if (ok < 0) { sink.fatal(pd.ordinal, METIS_FATAL_SCRATCH, 0); continue; }
                 if (ok == 0) continue;
             }
-            bool skip_first = false;
-            if (mode == 1) {
-                int hint = 0;
-                if (!first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS, false>(T, w, sink, true, pd, hint)) continue;
-                skip_first = true;
+            int start = 0;                                    // CoopEvaluator::kFresh
+            static thread_local std::vector<double> saved;
+            if (mode == 1 || mode == 4) {
+                int hint = 0, resume = 1;
+                if (!first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS, false>(T, w, sink, true, pd, hint, resume)) continue;
+                start = resume;
+                if (mode == 4 && start == 2) start = 1;       // no room in the hand-over store: replay the attempt
+                if (start == 2) saved.assign(w.perf, w.perf + pd.S);
             }
             CoopEvaluator<METIS_MAX_STAGES, METIS_MAX_LAYERS, OneLane> ev(T, w, mail, lanes);
-            ev.run_chain(pd, sink, skip_first);
+            ev.run_chain(pd, sink, start, saved.data(), 1);
         }
     }
     return 0;
@@ -217,8 +221,8 @@ int hostsim_runs_per_plan(const MetisProblem *p, const MetisPlanSpace *sp, int32
             scratch_sum.fatal_ordinal = ~0ULL;
             scratch_sum.best.cost = INFINITY;
             HostSink quiet{nullptr, 0, nullptr, 0, &scratch_sum};
-            int hint = 0;
-            const bool cont = first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS, false>(T, w, quiet, true, pd, hint);
+            int hint = 0, resume = 1;
+            const bool cont = first_task<METIS_MAX_STAGES, METIS_MAX_LAYERS, false>(T, w, quiet, true, pd, hint, resume);
             hints_out[ordinal] = cont ? hint : -1;
         }
         const uint64_t before = sum.num_balancer_runs;

@@ -49,8 +49,8 @@ def test_c1_het():
     assert summary.best.cost == 621.8881853975784 and summary.best.ordinal == 7
 
 
-@pytest.mark.parametrize('mode', [0, 1, 2, 3], ids=['sequential_run', 'first_task_then_chain', 'chain_only',
-                                                'chain_only_reversed_par_sections'])
+@pytest.mark.parametrize('mode', [0, 1, 2, 3, 4], ids=['sequential_run', 'first_task_then_chain', 'chain_only',
+                                                   'chain_only_reversed_par_sections', 'first_task_then_replay'])
 @pytest.mark.parametrize('name', ['c2_het16', 'c2_v100', 'mix32', 'het32_tight', 'sweep_n8_t1', 'sweep_n16_t2_v0',
                                   'long_profile', 'q10_big_first'])
 def test_synthetic(name, mode, workload_dir):

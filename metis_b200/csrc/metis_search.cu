@@ -39,6 +39,11 @@ namespace metis {
 #ifndef METIS_MIN_BLOCKS
 #define METIS_MIN_BLOCKS 3
 #endif
+#ifndef METIS_MIN_BLOCKS_BIG
+// instantiations for more than 64 stages: 80 registers cost 80 B of spills and buy a third block per SM
+// (measured: BASELINE configs[3] 149 -> 140 ms, 128 GPUs / 1 type / mpl 6 24.6 -> 20.9 ms)
+#define METIS_MIN_BLOCKS_BIG METIS_MIN_BLOCKS
+#endif
 constexpr int kThreads = METIS_THREADS;
 constexpr int kMaxS = METIS_MAX_STAGES;
 constexpr int kMaxL = METIS_MAX_LAYERS;
@@ -447,7 +452,7 @@ het_scatter_kernel(const SearchLists ls) {
 }
 
 template <int MAXS, int MAXL, bool ONE>
-__global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? METIS_MIN_BLOCKS : (METIS_MIN_BLOCKS * 2 + 2) / 3))
+__global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? METIS_MIN_BLOCKS : METIS_MIN_BLOCKS_BIG))
 het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                  const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob, const int use_smem,
                  const __grid_constant__ DeviceOut out, const SearchLists ls, const int best_slot) {
@@ -903,9 +908,22 @@ static int64_t shard_plan_slots(int64_t num_plans, const MetisShard *sh) {
 constexpr int64_t kFixedWs = 16384;                // summary + counters + list control words
 constexpr int64_t kMaxBlocks = 4096;               // per-block best records (bulk round + chain kernel)
 
+static int env_int(const char *name, int lo, int hi, int dflt) {
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    char *end = nullptr;
+    const long v = strtol(e, &end, 10);
+    if (end == e || *end != '\0' || v < lo || v > hi) return dflt;     // malformed or out of range: ignored
+    return (int)v;
+}
+
 // continuations of the bulk round whose re-weighted stage performance is kept for the chain kernel (the others replay
-// their first attempt): a quarter of the plans, at most 128 Ki
-static int64_t save_slots(int64_t cap) { return cap / 4 < 131072 ? (cap / 4 > 0 ? cap / 4 : 1) : 131072; }
+// their first attempt): a quarter of the plans, at most 128 Ki (METIS_SAVE_SLOTS: test knob for the replay path)
+static int64_t save_slots(int64_t cap) {
+    const int forced = env_int("METIS_SAVE_SLOTS", 1, 1 << 20, 0);
+    if (forced) return forced;
+    return cap / 4 < 131072 ? (cap / 4 > 0 ? cap / 4 : 1) : 131072;
+}
 
 int64_t metis_het_workspace_bytes(const MetisProblem *problem, int64_t num_plans, int32_t max_stage) {
     if (check_problem(problem)) return METIS_E_ARG;
@@ -940,14 +958,6 @@ static Workspace carve(void *ws, const BlobLayout &lay) {
     return w;
 }
 
-static int env_int(const char *name, int lo, int hi, int dflt) {
-    const char *e = getenv(name);
-    if (!e || !*e) return dflt;
-    char *end = nullptr;
-    const long v = strtol(e, &end, 10);
-    if (end == e || *end != '\0' || v < lo || v > hi) return dflt;     // malformed or out of range: ignored
-    return (int)v;
-}
 
 }  // extern "C"
 
@@ -982,13 +992,12 @@ static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg,
     size_t chain_dyn = 0;
     unsigned int chain_off = 0;
     const int forced = env_int("METIS_CHAIN_THREADS", 32, 512, 0);
-    const int chain_pad = env_int("METIS_CHAIN_SMEM_PAD", 0, 200 * 1024, 0);     // developer knob: fewer resident warps
     for (int pass = 0; pass < 2 && chain_threads == 0; ++pass) {       // second pass: tables in global memory
         int best_warps = 0;
         for (int threads = 64; threads <= 512; threads *= 2) {
             if (forced && threads != ((forced + 31) & ~31)) continue;
             const unsigned int off = chain_smem_tables ? blob_pad : 0u;
-            const size_t dyn = off + (size_t)(threads / 32) * per_warp + (size_t)chain_pad;
+            const size_t dyn = off + (size_t)(threads / 32) * per_warp;
             if (dyn > (size_t)smem_optin) continue;
             if (dyn > 48 * 1024) {
                 e = cudaFuncSetAttribute(chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -1013,11 +1022,6 @@ static int launch_search(const MetisProblem &p_arg, const MetisPlanSpace &s_arg,
     auto first = het_first_kernel<MAXS, MAXL, ONE>;
     int first_smem_tables = (int)lay.total <= blob_max && blob_pad <= (unsigned int)smem_optin;
     size_t first_dyn = first_smem_tables ? blob_pad : 0;
-    first_dyn += (size_t)env_int("METIS_FIRST_SMEM_PAD", 0, 128 * 1024, 0);       // developer knob (L1 / shared split)
-    {
-        const int carve = env_int("METIS_FIRST_CARVEOUT", 0, 100, -1);
-        if (carve >= 0) cudaFuncSetAttribute(first, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    }
     if (first_dyn > 48 * 1024) {
         e = cudaFuncSetAttribute(first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first_dyn);
         if (e != cudaSuccess) { cudaGetLastError(); first_smem_tables = 0; first_dyn = 0; }

@@ -150,11 +150,12 @@ def test_full_size_c3_vs_golden(name, workload_dir):
 
 
 @pytest.mark.parametrize('env', [{'METIS_CHAIN_THREADS': '64'}, {'METIS_SMEM_BLOB_MAX': '0'},
-                                 {'METIS_CHAIN_THREADS': '128', 'METIS_SMEM_BLOB_MAX': '0'}],
-                         ids=['chain_blocks_of_2_warps', 'tables_in_global_memory', 'both'])
+                                 {'METIS_CHAIN_THREADS': '128', 'METIS_SMEM_BLOB_MAX': '0'}, {'METIS_SAVE_SLOTS': '40'}],
+                         ids=['chain_blocks_of_2_warps', 'tables_in_global_memory', 'both', 'hand_over_store_full'])
 def test_launch_shapes_give_the_same_records(env, workload_dir, monkeypatch):
-    """Other block shapes of the chain kernel and tables left in global memory (instead of the TMA-staged shared
-    copy) must still produce every golden candidate of the 8.3e4-plan space."""
+    """Other block shapes of the chain kernel, tables left in global memory (instead of the TMA-staged shared copy)
+    and a hand-over store with room for 40 continuations only (the others replay their first attempt) must still
+    produce every golden candidate of the 8.3e4-plan space."""
     _gpu()
     for k, v in env.items():
         monkeypatch.setenv(k, v)

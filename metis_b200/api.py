@@ -224,12 +224,18 @@ class HetSearchResult(Sequence):
         """argmin (cost, position): the first entry of the ranked list.  The search kernels reduce it on the device
         (het_finalize_kernel: lowest cost, then lowest ordinal, then lowest step), so no sort is needed for it."""
         if self.rank_order is None and self._best_key is not None and len(self):
-            rec = self.candidates.records
-            key = (rec['ordinal'].astype(np.uint64) << np.uint64(16)) | rec['step'].astype(np.uint64)
-            want = (np.uint64(self._best_key[0]) << np.uint64(16)) | np.uint64(self._best_key[1])
-            i = int(np.searchsorted(key, want))
-            if i < len(rec) and key[i] == want:
-                return self.candidates.tuples([i])[0]
+            rec = self.candidates.records                     # sorted by (ordinal, step): bisect, no temporaries
+            want = (int(self._best_key[0]), int(self._best_key[1]))
+            lo, hi = 0, len(rec)
+            while lo < hi:
+                mid = (lo + hi) >> 1
+                r = rec[mid]
+                if (int(r['ordinal']), int(r['step'])) < want:
+                    lo = mid + 1
+                else:
+                    hi = mid
+            if lo < len(rec) and (int(rec[lo]['ordinal']), int(rec[lo]['step'])) == want:
+                return self.candidates.tuples([lo])[0]
         top = self.ranked(1)
         return top[0] if top else None
 

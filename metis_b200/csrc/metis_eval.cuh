@@ -520,13 +520,17 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
                 j += nsub;
                 continue;
             }
+            // one plan per thread: the layer's packed stage word is built in registers and stored once (the skipped
+            // sub-layers' bytes are filled in by the leftover pass below)
+            const int s_in = s;
+            uint64_t v = 0;
 #pragma unroll
             for (int q = 0; q < kH; ++q) {
                 if (q < nsub) {
                     if (s < last) {
                         if (c > d) {
                             c -= d;
-                            subb[r * 8 + q] = (uint8_t)s;
+                            v |= (uint64_t)(uint32_t)s << (8 * q);
                         } else {                                 // sub-layer j does not fit: skipped, stage closes
                             w.capa[s] = c;
                             w.fe[s] = (uint16_t)(j | kBroke);
@@ -537,6 +541,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
                     ++j;
                 }
             }
+            if (s_in < last) w.subw[r] = v;
         }
         if (s < last) {                                          // ran into the reserved tail
             w.capa[s] = c;
@@ -672,6 +677,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     // A stage holding >= 4 of a layer's 7 sub-layers holds the middle one or one of the first
     // three, so at most four candidates are counted (SWAR byte compare on the packed layer word).
     x.sync();
+    int run_own = (int)kDropped, run_first = 0, run_len = 0;
 #pragma unroll (X::kUniform ? 1 : 0)
     for (int r = x.lane(); r < L; r += x.width()) {
         const int nlow = m - kH * r;                         // sub-layers of r below the backward tail
@@ -688,6 +694,23 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
             own = layer_owner(v, (T.p.corrected & METIS_FIX_Q5) != 0);
         }
         reinterpret_cast<uint8_t *>(w.ownerw)[r] = (uint8_t)own;
+        if (!X::kUniform) {
+            // first / last / count of the layers of each stage (:300-306), one update per run of equal owners
+            if (own == run_own) ++run_len;
+            else {
+                if (run_own != (int)kDropped) {
+                    if (w.cnt[run_own] == 0) w.first[run_own] = (uint16_t)run_first;
+                    w.lastl[run_own] = (uint16_t)(r - 1);
+                    w.cnt[run_own] = (uint16_t)(w.cnt[run_own] + run_len);
+                }
+                run_own = own; run_first = r; run_len = 1;
+            }
+        }
+    }
+    if (!X::kUniform && run_own != (int)kDropped) {
+        if (w.cnt[run_own] == 0) w.first[run_own] = (uint16_t)run_first;
+        w.lastl[run_own] = (uint16_t)(L - 1);
+        w.cnt[run_own] = (uint16_t)(w.cnt[run_own] + run_len);
     }
     x.sync();
     x.mark(14);
@@ -713,17 +736,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
             }
             w.cnt[s] = (uint16_t)n; w.first[s] = (uint16_t)fi; w.lastl[s] = (uint16_t)la;
         }
-    } else {
-#pragma unroll (X::kUniform ? 1 : 0)
-        for (int r = 0; r < L; ++r) {                        // first / last / count of layers per stage
-            const int own = owner[r];
-            if (own != (int)kDropped) {
-                if (w.cnt[own] == 0) w.first[own] = (uint16_t)r;
-                w.lastl[own] = (uint16_t)r;
-                ++w.cnt[own];
-            }
-        }
-    }
+    }                                                        // (one plan per thread: done inside the vote loop)
     x.sync();
 #pragma unroll (X::kUniform ? 1 : 0)
     for (int s = x.lane(); s < S; s += x.width())            // :300-306

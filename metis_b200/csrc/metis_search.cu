@@ -1,16 +1,24 @@
 // metis_search.cu - sm_100a kernels + C ABI of libmetis_b200.so (see include/metis_b200.h).
 //
 // Kernel map:
-//   pack_tables_kernel    flattens the profile tables into one 16 B-aligned blob (+ norm_lc/7)
-//   het_admit_kernel      a2: ordinal -> plan, plans without a valid strategy dropped, survivors listed
-//   het_scatter_kernel    counting sort of the list by stage count (longest first)
-//   het_first_kernel      a5..a16, bulk round: first partition attempt of every listed plan, one plan per thread
+//   het_rows_kernel       a3/a4: device-group rows of every composition, in the reference's visiting order
+//                         (metis_rows.cuh; once per plan space, not per search)
+//   pack_tables_kernel    flattens the profile tables into one 16 B-aligned blob (+ norm_lc/7, derived tables)
+//   range_sums_kernel     sum(row[a:b]) of every profile row and slice, as CPython adds it up (looked up by a5..a16)
+//   het_admit_kernel      a2: ordinal -> plan, plans without a valid strategy dropped, survivors listed with a
+//                         chain-length hint
+//   het_scatter_kernel    counting sort of the list: by stage count (bulk round next) or by hint (chain kernel only)
+//   het_first_kernel      a5..a16, bulk round: first partition attempt of every listed plan, one plan per thread,
+//                         lanes re-joined explicitly (policy Lockstep, metis_eval.cuh); plans that run out of memory
+//                         are re-weighted and handed to the chain kernel
+//   het_order_kernel      those continuations by hint, longest expected chain first
 //   het_chain_kernel      a5..a16: one warp per plan walks the whole strategy chain (metis_coop.cuh);
 //                         both evaluation kernels stage the tables into shared memory by one TMA bulk copy
 //                         (cp.async.bulk + mbarrier) per block, write a 16 B record per costed candidate and
 //                         reduce their best candidate by warp shuffles + shared memory
 //   het_finalize_kernel   grid argmin over the per-block bests, counters -> summary
 //   het_detail_kernel     replays chosen (ordinal, step) candidates to materialise strategies/partition
+//   het_trace_kernel      replays plans and records what the reference prints (metis_trace.cuh)
 //   homo_cost_kernel      a17: one thread per UniformPlan
 //   layer_balance_kernel  a10 alone, for unit parity
 //   (rank_records_kernel, the stable record sort, lives in metis_rank.cu)

@@ -47,10 +47,14 @@ namespace metis {
 #ifndef METIS_MIN_BLOCKS
 #define METIS_MIN_BLOCKS 3
 #endif
+// instantiations for more than 64 stages: 80 registers cost 80 B of spills and buy a third block per SM (measured:
+// BASELINE configs[3] 149 -> 140 ms); single-type clusters gain from a fourth one at 64 registers (128 GPUs / 1 type /
+// mpl 6: 24.6 -> 20.9 -> 19.5 ms), mixed-type ones lose (configs[3] at mpl 4: 9.96 -> 10.2 ms)
 #ifndef METIS_MIN_BLOCKS_BIG
-// instantiations for more than 64 stages: 80 registers cost 80 B of spills and buy a third block per SM
-// (measured: BASELINE configs[3] 149 -> 140 ms, 128 GPUs / 1 type / mpl 6 24.6 -> 20.9 ms)
 #define METIS_MIN_BLOCKS_BIG METIS_MIN_BLOCKS
+#endif
+#ifndef METIS_MIN_BLOCKS_BIG_ONE
+#define METIS_MIN_BLOCKS_BIG_ONE (METIS_MIN_BLOCKS + 1)
 #endif
 constexpr int kThreads = METIS_THREADS;
 constexpr int kMaxS = METIS_MAX_STAGES;
@@ -460,7 +464,7 @@ het_scatter_kernel(const SearchLists ls) {
 }
 
 template <int MAXS, int MAXL, bool ONE>
-__global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? METIS_MIN_BLOCKS : METIS_MIN_BLOCKS_BIG))
+__global__ void __launch_bounds__(kThreads, (MAXS <= 64 ? METIS_MIN_BLOCKS : ONE ? METIS_MIN_BLOCKS_BIG_ONE : METIS_MIN_BLOCKS_BIG))
 het_first_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__ MetisPlanSpace sp,
                  const __grid_constant__ BlobLayout lay, const uint8_t *__restrict__ blob, const int use_smem,
                  const __grid_constant__ DeviceOut out, const SearchLists ls, const int best_slot) {

@@ -48,6 +48,7 @@ import numpy as np  # noqa: E402
 
 METRIC = 'candidate plans evaluated/sec'
 DEFAULT_WORKLOAD = 'c3_homo64_mpl6'
+EXTRA_WORKLOADS = ('c4_het128', 'c4_het128_mpl6')       # BASELINE configs[3] at max_permute_len 4 and 6
 REF_DIR = os.path.join(REPO, 'baseline', '_ref')
 
 
@@ -287,7 +288,8 @@ class ClockSampler(threading.Thread):
                 'window': 'device-timed steps + end-to-end steps (both keep the GPU busy)'}
 
 
-def run_ours(ns):
+def run_ours(ns, emit=True):
+    """One workload; rank 0 returns the JSON line (and prints it when ``emit``)."""
     import torch
     import torch.distributed as dist
     from metis_b200 import api, flatten, native, search
@@ -495,13 +497,15 @@ def run_ours(ns):
             line['cpu_baseline'] = {'value': a / t, 'unit': 'plans/s', 'cores': arm.cores, 'kind': arm.kind,
                                     'sample': arm.describe(a, c, A, t)}
             arm.close()
-        emit_result(line)
+        if emit:
+            emit_result(line)
     if world > 1:
         dist.barrier()
     del full, probe, dp, flush
     api.release_engines()
     torch.cuda.empty_cache()
     tmp.cleanup()
+    return line if rank == 0 else None
 
 
 def main():
@@ -513,6 +517,7 @@ def main():
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD)
     ap.add_argument('--cpu-sample', type=int, default=3000, help='plans per host core for cpu_baseline')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-extra', action='store_true', help='skip the configs[3] measurements reported under `extra`')
     ns = ap.parse_args()
     # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version there when
     # NCCL_DEBUG=VERSION) are sent to stderr for the duration of the run
@@ -526,9 +531,27 @@ def main():
     # --workload a,b,c (developer use: the scaling table of profiles/) runs the workloads one after the other in
     # this process group and prints one line each; the default invocation prints exactly one line
     names = ns.workload.split(',')
-    for name in names:
-        ns.workload = name
-        run_ours(ns)
+    if names == [DEFAULT_WORKLOAD] and not ns.no_extra:
+        # the headline line (BASELINE configs[2]) + the two configs[3] spaces, measured the same way with fewer steps,
+        # under `extra` (the 1 -> 8 scaling of the large spaces is where the GPUs pay off)
+        line = run_ours(ns, emit=False)
+        extra = {}
+        for name in EXTRA_WORKLOADS:
+            sub = argparse.Namespace(**vars(ns))
+            sub.workload, sub.steps, sub.no_cpu = name, min(ns.steps, 5), True
+            other = run_ours(sub, emit=False)
+            if other is not None:
+                extra[name] = {'inter_stage_plans': other['config']['inter_stage_plans'], 'value': other['value'],
+                               'ms_per_step': other['ms_per_step'], 'steps': other['steps'],
+                               'e2e_value': other['e2e']['value'], 'e2e_ms_per_step': other['e2e']['ms_per_step'],
+                               'C_costed': other['counters']['C_costed'], 'unit': 'plans/s'}
+        if line is not None:
+            line['extra'] = extra
+            emit_result(line)
+    else:
+        for name in names:
+            ns.workload = name
+            run_ours(ns)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()

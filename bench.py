@@ -539,7 +539,11 @@ def main():
         for name in EXTRA_WORKLOADS:
             sub = argparse.Namespace(**vars(ns))
             sub.workload, sub.steps, sub.no_cpu = name, min(ns.steps, 5), True
-            other = run_ours(sub, emit=False)
+            try:
+                other = run_ours(sub, emit=False)
+            except Exception as exc:                          # noqa: BLE001 - the headline line must still be printed
+                extra[name] = {'error': f'{type(exc).__name__}: {exc}'[:200]}
+                continue
             if other is not None:
                 extra[name] = {'inter_stage_plans': other['config']['inter_stage_plans'], 'value': other['value'],
                                'ms_per_step': other['ms_per_step'], 'steps': other['steps'],

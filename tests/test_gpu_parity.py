@@ -683,3 +683,67 @@ def test_search_over_gpu_written_rows_gives_the_same_records(name, workload_dir)
     assert len(a.records) > 0 and a.records.tobytes() == b.records.tobytes()
     used = np.arange(a.detail.shape[1])[None, :] < (3 * a.records['num_stage'].astype(np.int64) + 1)[:, None]
     assert (np.where(used, a.detail, 0) == np.where(used, b.detail, 0)).all()     # bytes past 3S+1 are not written
+
+
+def test_random_small_clusters_on_gpu_vs_oracle(tmp_path):
+    """Seeded fuzz through the C ABI: 60 random small clusters (1-3 device types, 2-32 GPUs, odd layer counts and
+    batch sizes, tight memories, variance 0 / 0.5 / 1; the generator of the host-build fuzz, another seed), searched
+    on the GPU - bulk round forced / chain kernel only, rows from the host enumerator / written by the GPU, in turn -
+    and by the oracle: every candidate, counter and fp64 cost bit must agree; a search the oracle aborts with a
+    KeyError must report a fatal plan."""
+    _gpu()
+    from oracle import metis_oracle as orc
+    from metis_b200 import flatten, search
+    from metis_b200.workloads import materialize, profile_file_order
+    from test_device_logic_on_host import _random_workload
+    import hostsim_util as hs
+    rng = random.Random(20260922)
+    done = fatal = candidates = 0
+    idx = 0
+    while done < 60 and idx < 900:
+        idx += 1
+        w = _random_workload(rng, idx)
+        root = str(tmp_path / w.name)
+        materialize(w, root)
+        order = profile_file_order(w)
+        cluster, profile, _types, cfg = _inputs(root, 'profile', order, w.num_layers, w.hidden_size,
+                                                w.sequence_length, w.vocab_size)
+        seqs = list(itertools.permutations(w.device_types()))
+        ndev = cluster.get_total_num_devices()
+        try:
+            space = flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers, w.variance, w.max_permute_len,
+                                             device_rows=bool(done & 2))
+        except IndexError:
+            continue
+        if not 1 <= space.num_plans <= 6000:
+            continue
+        problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
+        dp = search.DeviceProblem(problem, space, 'cuda:0')
+        s = search.HetSearcher(dp, want_records=True, want_detail=True)
+        s.shard.reserved = 1 if done & 1 else 2 ** 31 - 1
+        out = s.run()
+        ocl = orc.OracleCluster(os.path.join(root, 'hostfile'), os.path.join(root, 'clusterfile.json'))
+        oprof, _ = orc.load_profile_dir(os.path.join(root, 'profile'), order)
+        omodel = orc.OracleModel(w.num_layers, w.hidden_size, w.sequence_length, w.vocab_size, oprof['model']['parameters'])
+        try:
+            want, counters = orc.het_search(oprof, ocl, omodel, seqs, w.gbs, w.num_layers, w.variance,
+                                            w.max_permute_len, w.max_tp, w.max_bs)
+        except KeyError:
+            assert out.summary['fatal_ordinal'] != 2 ** 64 - 1 and out.summary['fatal_code'] in (1, 2), w
+            fatal += 1
+            done += 1
+            continue
+        sm = out.summary
+        assert sm['fatal_ordinal'] == 2 ** 64 - 1, w
+        assert (space.num_plans, sm['num_partition_calls'], sm['num_balancer_runs'], sm['num_records']) == \
+            (counters['A'], counters['B'], counters['runs'], counters['C']), w
+        host_space = space if space.rows.size else flatten.build_plan_space(len(seqs), ndev, w.gbs, w.num_layers,
+                                                                            w.variance, w.max_permute_len)
+        got = hs.unpack_candidates(out.records, out.detail, host_space)
+        assert len(got) == len(want), w
+        for g, x in zip(got, want):
+            assert (g[0], g[1], g[3], g[4], g[5], g[6], g[7]) == (x[0], x[1], x[3], x[4], x[5], x[6], x[7]), (w, g, x)
+            assert g[8] == x[8], (w, g[0], g[1], g[8].hex(), x[8].hex())
+        candidates += len(want)
+        done += 1
+    assert done == 60 and candidates > 500, (done, fatal, candidates)

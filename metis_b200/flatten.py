@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import sys
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -21,6 +22,8 @@ from . import native
 def py312_sum(values) -> float:
     """CPython >= 3.12 ``sum`` (Neumaier-compensated for floats, Python/bltinmodule.c) so that
     load-time constants do not depend on the interpreter version running the host code."""
+    if sys.version_info >= (3, 12):
+        return sum(values)                                  # the interpreter's own sum IS this algorithm
     it = iter(values)
     acc = 0
     for x in it:

@@ -488,38 +488,10 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     if (S > 1) {
         int s = 0, j = 0;
         double c = w.capa[0];
-        uint8_t *subb = reinterpret_cast<uint8_t *>(w.subw);
 #pragma unroll (X::kUniform ? 1 : 0)
         for (int r = 0; r + 1 < L; ++r) {
             const double d = dlay[r];
             const int nsub = (r == L - 2) ? kH - 1 : kH;     // the last 8 sub-layers are reserved
-            if (X::kUniform) {
-                // one task per warp: every lane runs this scalar loop on the same data
-                if (s >= last) break;
-                if (nsub == kH && c > 9.0 * d) {
-                    // whole layer fits with room to spare: all seven compare-and-subtract steps take the
-                    // "fits" branch (c - 7d > d even after rounding), so only the subtractions remain
-                    c -= d; c -= d; c -= d; c -= d; c -= d; c -= d; c -= d;
-                    w.subw[r] = (uint64_t)s * kOnes;
-                    j += kH;
-                    continue;
-                }
-                int q = 0;
-#pragma unroll 1
-                while (q < nsub && s < last) {
-#pragma unroll 1
-                    while (q < nsub && c > d) { c -= d; subb[r * 8 + q] = (uint8_t)s; ++q; }   // sub-layers that fit on stage s
-                    if (q < nsub) {                                      // sub-layer q does not fit: skipped
-                        w.capa[s] = c;
-                        w.fe[s] = (uint16_t)((j + q) | kBroke);
-                        ++s;
-                        c = w.capa[s];
-                        ++q;
-                    }
-                }
-                j += nsub;
-                continue;
-            }
             // one plan per thread: the layer's packed stage word is built in registers and stored once (the skipped
             // sub-layers' bytes are filled in by the leftover pass below)
             const int s_in = s;
@@ -694,7 +666,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
             own = layer_owner(v, (T.p.corrected & METIS_FIX_Q5) != 0);
         }
         reinterpret_cast<uint8_t *>(w.ownerw)[r] = (uint8_t)own;
-        if (!X::kUniform) {
+        {
             // first / last / count of the layers of each stage (:300-306), one update per run of equal owners
             if (own == run_own) ++run_len;
             else {
@@ -707,7 +679,7 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
             }
         }
     }
-    if (!X::kUniform && run_own != (int)kDropped) {
+    if (run_own != (int)kDropped) {
         if (w.cnt[run_own] == 0) w.first[run_own] = (uint16_t)run_first;
         w.lastl[run_own] = (uint16_t)(L - 1);
         w.cnt[run_own] = (uint16_t)(w.cnt[run_own] + run_len);
@@ -716,27 +688,6 @@ MB_HD int balance_run(const Tables &T, int S, Scratch<MAXS, MAXL> &w, const X &x
     x.mark(14);
     x.converge();
     uint8_t *owner = reinterpret_cast<uint8_t *>(w.ownerw);
-    if (X::kUniform) {
-        // first / last / count of the layers of each stage: one lane per stage scans the owner bytes
-        const int nw = (L + 7) / 8;
-#pragma unroll (X::kUniform ? 1 : 0)
-        for (int r = L + x.lane(); r < nw * 8; r += x.width()) owner[r] = kDropped;   // pad the last word
-        x.sync();
-#pragma unroll (X::kUniform ? 1 : 0)
-        for (int s = x.lane(); s < S; s += x.width()) {
-            int n = 0, fi = 0, la = 0;
-#pragma unroll (X::kUniform ? 1 : 0)
-            for (int k = 0; k < nw; ++k) {
-                const uint64_t z = swar_eq(w.ownerw[k], s) & 0x8080808080808080ULL;
-                if (z) {
-                    if (n == 0) fi = 8 * k + (ctz64(z) >> 3);
-                    la = 8 * k + ((63 - clz64(z)) >> 3);
-                    n += popc64(z);
-                }
-            }
-            w.cnt[s] = (uint16_t)n; w.first[s] = (uint16_t)fi; w.lastl[s] = (uint16_t)la;
-        }
-    }                                                        // (one plan per thread: done inside the vote loop)
     x.sync();
 #pragma unroll (X::kUniform ? 1 : 0)
     for (int s = x.lane(); s < S; s += x.width())            // :300-306

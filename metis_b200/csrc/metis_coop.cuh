@@ -80,6 +80,7 @@ struct OneLane {
     MB_HD int incl_scan(int v) const { return v; }
     MB_HD int last_lane(int v) const { return v; }
     MB_HD void mark(int) const {}
+    MB_HD void gate() const {}
 };
 
 // index of PAR iteration number `i` (0-based count of this lane's iterations) - lets the host policy reverse
@@ -1021,6 +1022,7 @@ struct CoopEvaluator : PlanEvaluator<MAXS, MAXL, SerialUniform, ONE> {
                 for (int a = first_attempt; a <= 3; ++a) {    // LayerLoadBalancer.partition_layer (:121-144)
                     if (!skip_first) sink.balancer_run();
                     skip_first = false;
+                    x.gate();                                 // (device) the block's warps start their runs together
                     rc = balance_coop();
                     if (rc) { sink.fatal(pd.ordinal, rc, aux); return; }
                     x.mark(20);

@@ -556,6 +556,23 @@ struct WarpCoop {
 #else
     __device__ void mark(int) const {}
 #endif
+    // Start of every balancer run: meet the other warps of the block.  The 16 warps of a block walk different plans
+    // through the same 55 KB of live code; left alone they spread over all its phases and miss the instruction cache
+    // (icc hit rate 70 %, `no_instruction` the largest stall).  Starting each run together keeps them within a phase
+    // or two of each other: measured 4.25 -> 3.93 ms on BASELINE configs[2] although every run now waits for the
+    // slowest neighbour (16 warps evaluating the SAME plan, perfectly aligned, gain 17 %).  A warp that is out of
+    // work keeps answering the barrier (het_chain_kernel) until nobody in the block works any more.
+    // PTX named barrier 1 over the whole block with an OR reduction: arrivals from different program points (this gate
+    // and the drain loop of het_chain_kernel) meet at the same barrier, which PTX defines (`bar.red`, all lanes of a
+    // warp arrive together) and CUDA C++'s __syncthreads_or does not promise.
+    // (one copy of the instruction, out of line: both callers arrive at the same program point)
+    static __device__ __noinline__ int block_or(int pred) {
+        int any;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.or.pred p, 1, %2, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+                     : "=r"(any) : "r"(pred), "r"((int)blockDim.x) : "memory");
+        return any;
+    }
+    __device__ void gate() const { block_or(1); }
     __device__ int lane() const { return threadIdx.x & 31; }
     __device__ int width() const { return 32; }
     __device__ bool leader() const { return (threadIdx.x & 31) == 0; }
@@ -694,6 +711,7 @@ het_chain_kernel(const __grid_constant__ MetisProblem p, const __grid_constant__
         ev.run_chain(pd, sink, start, perf, (size_t)ls.save_cap);
         lanes.mark(0);
     }
+    while (WarpCoop::block_or(0)) {}                         // out of work: answer the others' gates until all are done
     sink.leader = true;                                      // lanes 1-31 carry empty counters / bests
     if (lane != 0) { sink.n_part = sink.n_run = sink.n_key = 0; }
     finish_block(sink, out, best_slot + blockIdx.x);

@@ -461,3 +461,41 @@ def test_verbose_transcript_equals_the_reference(name, workload_dir):
     end = next(i for i, l in enumerate(gold) if l.startswith('search_time:'))
     assert len(lines) == end - 1
     assert lines == gold[1:end]
+
+
+@pytest.mark.parametrize('name', ['mix32', 'c2_het16'])
+def test_lazy_result_object_on_host_records(name, workload_dir):
+    """Host logic of the drop-in API without a GPU: records / detail rows of the host build go through
+    search.Candidates and api.HetSearchResult (the objects cost_het_cluster() returns) - length, indexing, slices,
+    iteration, ranked() (Python's stable sort when no device permutation is given), best() by bisection on the
+    kernels' argmin key - and must give the golden 7-tuples."""
+    from metis_b200 import api, search
+    meta, arr = load_golden(name)
+    w, root, _ = workload_dir(name)
+    cluster, profile, _types, cfg = hs.load_inputs(root, 'profile', meta['file_order'], w.num_layers, w.hidden_size,
+                                                   w.sequence_length, w.vocab_size)
+    seqs = [tuple(s) for s in meta['node_sequences']]
+    problem = flatten.build_problem(profile, cluster, cfg, w.gbs, w.max_tp, w.max_bs, seqs)
+    space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance,
+                                     w.max_permute_len)
+    rec, det, summary = hs.host_het_search(problem, space, mode=1)
+    order = np.lexsort((rec['step'], rec['ordinal']))              # estimate_costs order, like metis_sort_records
+    rec, det = rec[order], det[order]
+    cand = search.Candidates(rec, det, space, seqs)
+    best = (int(summary.best.ordinal), int(summary.best.step))
+    res = api.HetSearchResult(cand, None, {}, best_key=best)
+    gold = [(tuple(meta['node_sequences'][g[2]]), g[3], g[4], g[5], g[6], g[7], g[8]) for g in golden_rows(arr)]
+    assert len(res) == len(gold) and list(res) == gold and res == gold
+    assert res[0] == gold[0] and res[-1] == gold[-1] and res[3:7] == gold[3:7]
+    with pytest.raises(IndexError):
+        res[len(gold)]
+    want = sorted(gold, key=lambda kv: kv[6])
+    assert res.best() == want[0]                                   # before any ranking exists: bisection
+    assert res.rank_order is None
+    assert res.ranked(5) == want[:5] and res.ranked() == want      # stable sort fallback
+    assert res.best() == want[0]
+    assert (res.costs == np.array([g[6] for g in gold])).all()
+    # a device-rows space (rows only on the GPU) falls back to the host enumerator when asked on the host
+    lazy_space = flatten.build_plan_space(len(seqs), cluster.get_total_num_devices(), w.gbs, w.num_layers, w.variance,
+                                          w.max_permute_len, device_rows=True)
+    assert list(api.HetSearchResult(search.Candidates(rec, det, lazy_space, seqs), None, {})) == gold
